@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's interface for the hot path, over the
+C ABI in include/gtscaffold_b200.h (ctypes; no torch types cross the boundary).
+
+    g = ScaffoldGraphB200.new_from_records(inp)      # gt_scaffolder_graph_new_from_file, graph.c:346
+    g.mark_repeats(copy_num_cutoff, astat_cutoff)    # gt_scaffolder_graph_mark_repeats, algorithms.c:90
+    g.filter(pcutoff, cncutoff, ocutoff)             # gt_scaffolder_graph_filter, algorithms.c:261
+
+There is no CPU fallback: if libgtscaffold_b200.so is missing or no CUDA device
+is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgtscaffold_b200.so")
+
+# defaults of the reference's driver (test.c:35-42)
+MIN_CONTIG_LEN = 200
+COPY_NUM_CUTOFF = 0.3
+ASTAT_NUM_CUTOFF = 20.0
+PROBABILITY_CUTOFF = 0.01
+COPY_NUM_CUTOFF_2 = 1.5
+OVERLAP_CUTOFF = 400
+
+EXPORTS = [
+    "gtsb_create", "gtsb_destroy", "gtsb_error", "gtsb_set_stream", "gtsb_want_win_rec",
+    "gtsb_set_vertices_host", "gtsb_set_vertices_device", "gtsb_set_records_host",
+    "gtsb_set_records_device", "gtsb_set_graph_host", "gtsb_build", "gtsb_mark_repeats",
+    "gtsb_filter", "gtsb_pipeline", "gtsb_nof_edges", "gtsb_get_vertex_states", "gtsb_get_csr",
+    "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [("nof_vertices", C.c_uint64), ("nof_records", C.c_uint64), ("nof_edges", C.c_uint64),
+                ("max_degree", C.c_uint32), ("big_rows", C.c_uint32), ("large_buckets", C.c_uint32),
+                ("proposals", C.c_uint32), ("poly_sweeps", C.c_uint32), ("fire_rounds", C.c_uint32),
+                ("kernel_launches", C.c_uint64), ("ms_build", C.c_float),
+                ("ms_mark_repeats", C.c_float), ("ms_filter", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make -C gt-scaffold_b200/csrc` "
+            "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, f32, i32, i64 = C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_int64
+    L.gtsb_create.argtypes = [C.POINTER(vp), i32]
+    L.gtsb_destroy.argtypes = [vp]
+    L.gtsb_destroy.restype = None
+    L.gtsb_error.argtypes = [vp]
+    L.gtsb_error.restype = C.c_char_p
+    L.gtsb_set_stream.argtypes = [vp, vp]
+    L.gtsb_want_win_rec.argtypes = [vp, i32]
+    for n in ("gtsb_set_vertices_host", "gtsb_set_vertices_device"):
+        getattr(L, n).argtypes = [vp, u64, vp, vp, vp]
+    for n in ("gtsb_set_records_host", "gtsb_set_records_device"):
+        getattr(L, n).argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.gtsb_set_graph_host.argtypes = [vp, u64, u64] + [vp] * 10
+    L.gtsb_build.argtypes = [vp]
+    L.gtsb_mark_repeats.argtypes = [vp, f32, f32, i32]
+    L.gtsb_filter.argtypes = [vp, f32, f32, i64]
+    L.gtsb_pipeline.argtypes = [vp, f32, f32, i32, f32, f32, i64]
+    L.gtsb_nof_edges.argtypes = [vp]
+    L.gtsb_nof_edges.restype = u64
+    L.gtsb_get_vertex_states.argtypes = [vp, vp]
+    L.gtsb_get_csr.argtypes = [vp] * 9
+    L.gtsb_device_pointers.argtypes = [vp] + [C.POINTER(vp)] * 5
+    L.gtsb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.gtsb_synchronize.argtypes = [vp]
+    L.gtsb_ambig_thresholds.argtypes = [f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    _lib = L
+    return L
+
+
+def ambig_thresholds(cutoff: float):
+    L = load_library()
+    tp, tn, inf = C.c_float(), C.c_float(), C.c_int()
+    rc = L.gtsb_ambig_thresholds(cutoff, C.byref(tp), C.byref(tn), C.byref(inf))
+    return rc, tp.value, tn.value, inf.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class ScaffoldGraphB200:
+    """A scaffold graph resident in B200 HBM."""
+
+    def __init__(self, device: int = 0, want_win_rec: bool = False, stream: int | None = None):
+        self.L = load_library()
+        h = C.c_void_p()
+        if self.L.gtsb_create(C.byref(h), device) != 0:
+            raise RuntimeError("gtsb_create failed: no usable CUDA device (no CPU fallback)")
+        self.h = h
+        self.V = 0
+        self._keep = []
+        if want_win_rec:
+            self._ck(self.L.gtsb_want_win_rec(self.h, 1))
+        if stream is not None:
+            self._ck(self.L.gtsb_set_stream(self.h, C.c_void_p(stream)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.gtsb_error(self.h).decode())
+
+    # ---- inputs
+    def set_vertices(self, seq_len, astat, copy_num):
+        a = [np.ascontiguousarray(seq_len, np.uint32), np.ascontiguousarray(astat, np.float32),
+             np.ascontiguousarray(copy_num, np.float32)]
+        self.V = a[0].shape[0]
+        self._ck(self.L.gtsb_set_vertices_host(self.h, self.V, *[_ptr(x) for x in a]))
+
+    def set_records(self, root, ctg, dist, std_dev, flags):
+        a = [np.ascontiguousarray(root, np.uint32), np.ascontiguousarray(ctg, np.uint32),
+             np.ascontiguousarray(dist, np.int32), np.ascontiguousarray(std_dev, np.float32),
+             np.ascontiguousarray(flags, np.uint8)]
+        self._ck(self.L.gtsb_set_records_host(self.h, a[0].shape[0], *[_ptr(x) for x in a]))
+
+    def set_vertices_device(self, V, seq_len_ptr, astat_ptr, copy_num_ptr):
+        self.V = int(V)
+        self._ck(self.L.gtsb_set_vertices_device(self.h, self.V, seq_len_ptr, astat_ptr, copy_num_ptr))
+
+    def set_records_device(self, R, root_ptr, ctg_ptr, dist_ptr, std_ptr, flags_ptr):
+        self._ck(self.L.gtsb_set_records_device(self.h, int(R), root_ptr, ctg_ptr, dist_ptr, std_ptr,
+                                                flags_ptr))
+
+    def set_graph(self, row_ptr, dst, dist, std_dev, flags, seq_len, astat, copy_num, vstate, estate):
+        a = [np.ascontiguousarray(row_ptr, np.uint32), np.ascontiguousarray(dst, np.uint32),
+             np.ascontiguousarray(dist, np.int32), np.ascontiguousarray(std_dev, np.float32),
+             np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(seq_len, np.uint32),
+             np.ascontiguousarray(astat, np.float32), np.ascontiguousarray(copy_num, np.float32),
+             np.ascontiguousarray(vstate, np.uint8), np.ascontiguousarray(estate, np.uint8)]
+        self.V = a[5].shape[0]
+        self._ck(self.L.gtsb_set_graph_host(self.h, self.V, a[1].shape[0], *[_ptr(x) for x in a]))
+
+    @classmethod
+    def new_from_records(cls, inp, device: int = 0, want_win_rec: bool = False):
+        """Vertices + file-ordered records -> device CSR (the record loop of
+        gt_scaffolder_parser_read_distances, parser.c:357-379)."""
+        g = cls(device, want_win_rec)
+        g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+        g.set_records(inp.root, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+        g.build()
+        return g
+
+    # ---- the hot path
+    def build(self):
+        self._ck(self.L.gtsb_build(self.h))
+
+    def mark_repeats(self, copy_num_cutoff=COPY_NUM_CUTOFF, astat_cutoff=ASTAT_NUM_CUTOFF,
+                     use_copy_num=True):
+        self._ck(self.L.gtsb_mark_repeats(self.h, copy_num_cutoff, astat_cutoff, int(use_copy_num)))
+
+    def filter(self, pcutoff=PROBABILITY_CUTOFF, cncutoff=COPY_NUM_CUTOFF_2, ocutoff=OVERLAP_CUTOFF):
+        self._ck(self.L.gtsb_filter(self.h, pcutoff, cncutoff, int(ocutoff)))
+
+    def pipeline(self, copy_num_cutoff=COPY_NUM_CUTOFF, astat_cutoff=ASTAT_NUM_CUTOFF,
+                 use_copy_num=True, pcutoff=PROBABILITY_CUTOFF, cncutoff=COPY_NUM_CUTOFF_2,
+                 ocutoff=OVERLAP_CUTOFF):
+        self._ck(self.L.gtsb_pipeline(self.h, copy_num_cutoff, astat_cutoff, int(use_copy_num),
+                                      pcutoff, cncutoff, int(ocutoff)))
+
+    def synchronize(self):
+        self._ck(self.L.gtsb_synchronize(self.h))
+
+    # ---- results
+    @property
+    def E(self):
+        return int(self.L.gtsb_nof_edges(self.h))
+
+    def vstate(self):
+        out = np.zeros(self.V, np.uint8)
+        self._ck(self.L.gtsb_get_vertex_states(self.h, _ptr(out)))
+        return out
+
+    def csr(self, eid=True, win_rec=False):
+        E, V = self.E, self.V
+        o = dict(row_ptr=np.zeros(V + 1, np.uint32), dst=np.zeros(E, np.uint32),
+                 dist=np.zeros(E, np.int32), std_dev=np.zeros(E, np.float32),
+                 flags=np.zeros(E, np.uint8), estate=np.zeros(E, np.uint8))
+        o["eid"] = np.zeros(E, np.uint32) if eid else None
+        o["win_rec"] = np.zeros(E, np.uint32) if win_rec else None
+        self._ck(self.L.gtsb_get_csr(self.h, _ptr(o["row_ptr"]), _ptr(o["dst"]), _ptr(o["dist"]),
+                                     _ptr(o["std_dev"]), _ptr(o["flags"]), _ptr(o["eid"]),
+                                     _ptr(o["win_rec"]), _ptr(o["estate"])))
+        return o
+
+    def result(self):
+        """Same layout as the oracles' result(): edge arrays in graph->edges[]
+        order, adjacency as eids in row order."""
+        c = self.csr()
+        V, E = self.V, self.E
+        deg = np.diff(c["row_ptr"].astype(np.int64))
+        src = np.repeat(np.arange(V, dtype=np.uint32), deg)
+        eid = c["eid"].astype(np.int64)
+        perm = np.empty(E, np.int64)
+        perm[eid] = np.arange(E)
+        if E and not np.array_equal(np.sort(eid), np.arange(E)):
+            raise AssertionError("eid is not a permutation of 0..E-1")
+        return dict(vstate=self.vstate(), row_ptr=c["row_ptr"].astype(np.uint64),
+                    adj_eid=c["eid"].astype(np.uint32), src=src[perm], dst=c["dst"][perm],
+                    dist=c["dist"][perm].astype(np.int64), std_dev=c["std_dev"][perm],
+                    flags=(c["flags"][perm] & 3).astype(np.uint8), estate=c["estate"][perm])
+
+    def device_pointers(self):
+        ps = [C.c_void_p() for _ in range(5)]
+        self._ck(self.L.gtsb_device_pointers(self.h, *[C.byref(p) for p in ps]))
+        return dict(zip(["row_ptr", "dst", "eid", "estate", "vstate"], [p.value for p in ps]))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.L.gtsb_get_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gtsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,682 @@
+// gtsb_api.cu -- context, device memory and the C ABI (include/gtscaffold_b200.h).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gtscaffold_b200.h"
+#include "gtsb_common.cuh"
+#include "gtsb_kernels.h"
+#include "gtsb_scan.cuh"
+#include "gtsb_threshold.h"
+
+using namespace gtsb;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool owned = true;
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace
+
+struct gtsb_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  bool want_win = false;
+
+  uint64_t V = 0, R = 0, E = 0;
+  bool have_vertices = false, have_records = false, have_graph = false;
+
+  // inputs
+  DevBuf vattr, astat, seq_len_in, copy_num_in;
+  DevBuf root, ctg, dist, std_dev, flags;
+  // graph
+  DevBuf row_ptr, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
+  // build work
+  DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
+      big_rows, counters, lscratch, ltag;
+  // filter work
+  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch;
+  uint32_t n_big_rows = 0, max_deg = 0;
+
+  uint32_t *h_counters = nullptr;   // pinned
+  gtsb_stats stats{};
+  Timer t_build, t_rep, t_filter;
+
+  // cached ambiguous-order thresholds
+  bool ambig_valid = false;
+  float ambig_cutoff = 0.f;
+  AmbigParams ambig{};
+};
+
+namespace {
+
+int fail(gtsb_context *c, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  c->err = buf;
+  return -1;
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(c, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__,     \
+                  __LINE__, cudaGetErrorString(e_));                                    \
+  } while (0)
+
+int ensure(gtsb_context *c, DevBuf &b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.owned && b.cap >= bytes && b.p != nullptr) return 0;
+  if (b.owned && b.p != nullptr) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.owned = true;
+  b.cap = 0;
+  // grow with some headroom so that repeated calls at one size never realloc
+  CK(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return 0;
+}
+
+void adopt(DevBuf &b, const void *p) {
+  if (b.owned && b.p != nullptr) cudaFree(b.p);
+  b.p = const_cast<void *>(p);
+  b.owned = false;
+  b.cap = 0;
+}
+
+void release(DevBuf &b) {
+  if (b.owned && b.p != nullptr) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  b.owned = true;
+}
+
+#define ENSURE(buf, bytes)                      \
+  do {                                          \
+    if (ensure(c, buf, (bytes)) != 0) return -1; \
+  } while (0)
+
+int read_counters(gtsb_context *c) {
+  CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_NUM * sizeof(uint32_t),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int timer_begin(gtsb_context *c, Timer &t) {
+  if (t.a == nullptr) {
+    CK(cudaEventCreate(&t.a));
+    CK(cudaEventCreate(&t.b));
+  }
+  CK(cudaEventRecord(t.a, c->stream));
+  return 0;
+}
+
+int timer_end(gtsb_context *c, Timer &t, float *ms) {
+  CK(cudaEventRecord(t.b, c->stream));
+  CK(cudaEventSynchronize(t.b));
+  CK(cudaEventElapsedTime(ms, t.a, t.b));
+  return 0;
+}
+
+__global__ void k_pack_vattr(uint32_t V, const uint32_t *__restrict__ seq_len,
+                             const float *__restrict__ copy_num, VAttr *__restrict__ out) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) {
+    VAttr a;
+    a.copy_num = copy_num[v];
+    a.seq_len = seq_len[v];
+    out[v] = a;
+  }
+}
+
+// big-row list + max degree for a graph that did not come from gtsb_build
+__global__ void k_classify_rows(uint32_t V, const uint32_t *__restrict__ row_ptr,
+                                uint32_t *__restrict__ big_rows, uint32_t *__restrict__ counters) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t d = 0;
+  if (v < V) d = row_ptr[v + 1] - row_ptr[v];
+  const bool big = d > BIG_ROW;
+  if (big) atomicMax(&counters[CNT_MAX_DEG], d);
+  warp_append(big, v, big_rows, &counters[CNT_BIG_ROWS]);
+}
+
+int vertices_common(gtsb_context *c, uint64_t V) {
+  if (V > GTSB_MAX_VERTICES) return fail(c, "too many vertices (%llu > %u)", (unsigned long long) V,
+                                         GTSB_MAX_VERTICES);
+  c->V = V;
+  ENSURE(c->vattr, V * sizeof(VAttr));
+  if (V) {
+    k_pack_vattr<<<(uint32_t) ((V + 255) / 256), 256, 0, c->stream>>>(
+        (uint32_t) V, c->seq_len_in.as<uint32_t>(), c->copy_num_in.as<float>(), c->vattr.as<VAttr>());
+    c->stats.kernel_launches++;
+  }
+  ENSURE(c->vstate, V);
+  ENSURE(c->rep_pred, V);
+  CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, c->stream));   // GIS_UNVISITED, graph.c:129
+  c->have_vertices = true;
+  c->have_graph = false;
+  return 0;
+}
+
+GraphArgs graph_args(gtsb_context *c) {
+  GraphArgs g{};
+  g.V = (uint32_t) c->V;
+  g.sm_count = c->sm_count;
+  g.row_ptr = c->row_ptr.as<uint32_t>();
+  g.dst = c->dst.as<uint32_t>();
+  g.dist = c->edist.as<int32_t>();
+  g.std_dev = c->estd.as<float>();
+  g.flags = c->eflags.as<uint8_t>();
+  g.vattr = c->vattr.as<VAttr>();
+  g.astat = c->astat.as<float>();
+  g.vstate = c->vstate.as<uint8_t>();
+  g.estate = c->estate.as<uint8_t>();
+  g.big_rows = c->big_rows.as<uint32_t>();
+  g.n_big_rows = c->n_big_rows;
+  g.max_deg = c->max_deg;
+  g.counters = c->counters.as<uint32_t>();
+  return g;
+}
+
+int get_ambig(gtsb_context *c, float pcutoff) {
+  if (c->ambig_valid && memcmp(&c->ambig_cutoff, &pcutoff, sizeof(float)) == 0) return 0;
+  AmbigParams ap{};
+  if (gtsb_ambig_thresholds(pcutoff, &ap.t_pos, &ap.t_neg, &ap.inf_true) != 0)
+    return fail(c, "ambiguous-order test is not a step function of the interval for pcutoff %g "
+                   "with this libm; refusing to guess", (double) pcutoff);
+  ap.c_pos = ap.t_pos * ap.t_pos;
+  ap.c_neg = ap.t_neg * ap.t_neg;
+  c->ambig = ap;
+  c->ambig_cutoff = pcutoff;
+  c->ambig_valid = true;
+  return 0;
+}
+
+int do_build(gtsb_context *c) {
+  if (!c->have_vertices || !c->have_records) return fail(c, "gtsb_build: vertices and records must be set first");
+  const uint64_t V = c->V, R = c->R;
+  if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records");
+  cudaStream_t s = c->stream;
+
+  ENSURE(c->cnt, (V + 1) * 4);
+  ENSURE(c->bptr, (V + 1) * 4);
+  ENSURE(c->cursor, (V + 1) * 4);
+  ENSURE(c->deg, (V + 1) * 4);
+  ENSURE(c->row_ptr, (V + 1) * 4);
+  ENSURE(c->krank, (R + 1) * 4);
+  const uint64_t scan_n = V > R ? V : R;
+  ENSURE(c->scan_scratch, scan_scratch_elems(scan_n) * 4);
+  ENSURE(c->entries, 2 * R * sizeof(uint4));
+  if (c->want_win) ENSURE(c->bwin, 2 * R * 4);
+  ENSURE(c->creator_flag, R);
+  ENSURE(c->large_list, (V + 1) * sizeof(uint2));
+  ENSURE(c->big_rows, (V + 1) * 4);
+  ENSURE(c->dst, 2 * R * 4);
+  ENSURE(c->edist, 2 * R * 4);
+  ENSURE(c->estd, 2 * R * 4);
+  ENSURE(c->eflags, 2 * R);
+  ENSURE(c->eid, 2 * R * 4);
+  ENSURE(c->estate, 2 * R);
+  if (c->want_win) ENSURE(c->win_rec, 2 * R * 4);
+
+  CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
+  CK(cudaMemsetAsync(c->cnt.p, 0, (V + 1) * 4, s));
+  CK(cudaMemsetAsync(c->cursor.p, 0, (V + 1) * 4, s));
+  CK(cudaMemsetAsync(c->creator_flag.p, 0, R ? R : 1, s));
+  CK(cudaMemsetAsync(c->estate.p, 0, 2 * R ? 2 * R : 1, s));   // GIS_UNVISITED, graph.c:162
+  CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, s));
+
+  BuildArgs a{};
+  a.R = R;
+  a.V = (uint32_t) V;
+  a.sm_count = c->sm_count;
+  a.root = c->root.as<uint32_t>();
+  a.ctg = c->ctg.as<uint32_t>();
+  a.dist = c->dist.as<int32_t>();
+  a.std_dev = c->std_dev.as<float>();
+  a.flags = c->flags.as<uint8_t>();
+  a.cnt = c->cnt.as<uint32_t>();
+  a.bptr = c->bptr.as<uint32_t>();
+  a.cursor = c->cursor.as<uint32_t>();
+  a.deg = c->deg.as<uint32_t>();
+  a.krank = c->krank.as<uint32_t>();
+  a.scan_scratch = c->scan_scratch.as<uint32_t>();
+  a.entries = c->entries.as<uint4>();
+  a.bwin = c->want_win ? c->bwin.as<uint32_t>() : nullptr;
+  a.creator_flag = c->creator_flag.as<uint8_t>();
+  a.large_list = c->large_list.as<uint2>();
+  a.big_rows = c->big_rows.as<uint32_t>();
+  a.counters = c->counters.as<uint32_t>();
+  a.row_ptr = c->row_ptr.as<uint32_t>();
+  a.dst = c->dst.as<uint32_t>();
+  a.eid = c->eid.as<uint32_t>();
+  a.win_rec = c->want_win ? c->win_rec.as<uint32_t>() : nullptr;
+  a.edist = c->edist.as<int32_t>();
+  a.estd = c->estd.as<float>();
+  a.eflags = c->eflags.as<uint8_t>();
+
+  if (R) {
+    launch_build_count(a, s);
+    launch_build_scatter_resolve(a, s);
+    c->stats.kernel_launches += 1 + 3 + 2;
+  } else {
+    CK(cudaMemsetAsync(c->bptr.p, 0, (V + 1) * 4, s));
+    CK(cudaMemsetAsync(c->deg.p, 0, (V + 1) * 4, s));
+  }
+  if (read_counters(c) != 0) return -1;
+  if (c->h_counters[CNT_ERROR] & 1u) return fail(c, "gtsb_build: a record names a vertex id >= nof_vertices");
+  if (c->h_counters[CNT_ERROR] & 2u)
+    return fail(c, "gtsb_build: self link (root == ctg) is not supported (the reference would "
+                   "create two parallel self edges, parser.c:374-377)");
+  const uint32_t nlarge = c->h_counters[CNT_LARGE_BUCKETS];
+  c->stats.large_buckets = nlarge;
+  if (nlarge) {
+    const uint64_t pad = c->h_counters[CNT_LARGE_PAD];
+    ENSURE(c->lscratch, pad * sizeof(uint4));
+    ENSURE(c->ltag, pad * 4);
+    launch_build_resolve_large(a, c->lscratch.as<uint4>(), c->ltag.as<uint32_t>(), nlarge, s);
+    c->stats.kernel_launches += 1;
+  }
+  launch_build_emit(a, s);
+  c->stats.kernel_launches += 3 + (R ? 3 : 0) + (V ? 1 : 0);
+  uint32_t e32 = 0;
+  CK(cudaMemcpyAsync(&e32, c->row_ptr.as<uint32_t>() + V, 4, cudaMemcpyDeviceToHost, s));
+  if (read_counters(c) != 0) return -1;
+  c->E = e32;
+  c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
+  c->max_deg = c->h_counters[CNT_MAX_DEG];
+  c->stats.nof_edges = c->E;
+  c->stats.big_rows = c->n_big_rows;
+  c->stats.max_degree = c->max_deg;
+  c->have_graph = true;
+  return 0;
+}
+
+int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
+  if (!c->have_graph) return fail(c, "gtsb_mark_repeats: no graph (call gtsb_build or gtsb_set_graph_host)");
+  launch_mark_repeats(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
+  c->stats.kernel_launches += c->V ? 2 : 0;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
+  if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
+  if (get_ambig(c, pcutoff) != 0) return -1;
+  const uint64_t V = c->V, E = c->E;
+  cudaStream_t s = c->stream;
+  ENSURE(c->proposals, (E + 1) * sizeof(uint2));
+  ENSURE(c->poly_cur, (V + 1) * 4);
+  ENSURE(c->poly_new, (V + 1) * 4);
+  ENSURE(c->gbits, V + 1);
+  ENSURE(c->fstat, V + 1);
+  ENSURE(c->work_a, (V + 1) * 4);
+  ENSURE(c->work_b, (V + 1) * 4);
+  FilterArgs a{};
+  a.big_blocks = (uint32_t) c->sm_count * 2;
+  if (c->n_big_rows) {
+    if (a.big_blocks > c->n_big_rows) a.big_blocks = c->n_big_rows;
+    ENSURE(c->big_scratch, (size_t) a.big_blocks * c->max_deg * BIG_SCRATCH_STRIDE);
+  }
+  a.g = graph_args(c);
+  a.ambig = c->ambig;
+  a.cncutoff = cncutoff;
+  a.ocutoff = ocutoff;
+  a.proposals = c->proposals.as<uint2>();
+  a.proposals_cap = (uint32_t) E;
+  a.poly_cur = c->poly_cur.as<uint32_t>();
+  a.poly_new = c->poly_new.as<uint32_t>();
+  a.gbits = c->gbits.as<uint8_t>();
+  a.fstat = c->fstat.as<uint8_t>();
+  a.work_a = c->work_a.as<uint32_t>();
+  a.work_b = c->work_b.as<uint32_t>();
+  a.big_scratch = c->big_scratch.as<uint8_t>();
+
+  uint32_t *cnt = c->counters.as<uint32_t>();
+  CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
+  CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (V + 1) * 4, s));
+  CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (V + 1) * 4, s));
+
+  // phase 1: who proposes whom
+  launch_filter_pairs(a, s);
+  c->stats.kernel_launches += (V ? 1 : 0) + (c->n_big_rows ? 1 : 0);
+  if (read_counters(c) != 0) return -1;
+  if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
+  const uint32_t nprop = c->h_counters[CNT_PROPOSALS];
+  c->stats.proposals = nprop;
+  c->stats.poly_sweeps = 0;
+  if (nprop) {
+    for (;;) {
+      CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
+      launch_poly_sweep(a, nprop, s);
+      c->stats.kernel_launches += 3;
+      c->stats.poly_sweeps++;
+      if (read_counters(c) != 0) return -1;
+      if (!c->h_counters[CNT_POLY_CHANGED]) break;
+      if (c->stats.poly_sweeps > V + 2) return fail(c, "gtsb_filter: polyTime sweeps did not converge");
+    }
+  }
+  // phase 2: overlap candidates, then the order-respecting fire fixpoint
+  launch_filter_overlap(a, s);
+  c->stats.kernel_launches += (V ? 1 : 0) + (c->n_big_rows ? 1 : 0);
+  c->stats.fire_rounds = 0;
+  if (read_counters(c) != 0) return -1;
+  uint32_t n_in = c->h_counters[CNT_WORK_A];
+  uint32_t *win = a.work_a, *wout = a.work_b;
+  int in_idx = CNT_WORK_A, out_idx = CNT_WORK_B;
+  while (n_in) {
+    CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
+    launch_fire_round(a, win, n_in, wout, cnt + out_idx, s);
+    c->stats.kernel_launches += 1;
+    c->stats.fire_rounds++;
+    if (read_counters(c) != 0) return -1;
+    const uint32_t n_out = c->h_counters[out_idx];
+    if (n_out >= n_in && c->stats.fire_rounds > V + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
+    n_in = n_out;
+    uint32_t *t = win; win = wout; wout = t;
+    int ti = in_idx; in_idx = out_idx; out_idx = ti;
+  }
+  launch_filter_finalize(a, s);
+  c->stats.kernel_launches += V ? 1 : 0;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================== C ABI
+
+extern "C" {
+
+int gtsb_create(gtsb_context **out, int device) {
+  if (out == nullptr) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "gtscaffold_b200: no CUDA device available (there is no CPU fallback)\n");
+    return -1;
+  }
+  if (device < 0 || device >= ndev) {
+    fprintf(stderr, "gtscaffold_b200: device %d out of range (%d devices)\n", device, ndev);
+    return -1;
+  }
+  gtsb_context *c = new gtsb_context();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return -1; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }
+  if (cudaMallocHost(&c->h_counters, CNT_NUM * sizeof(uint32_t)) != cudaSuccess) { delete c; return -1; }
+  if (cudaMalloc(&c->counters.p, CNT_NUM * sizeof(uint32_t)) != cudaSuccess) { delete c; return -1; }
+  c->counters.cap = CNT_NUM * sizeof(uint32_t);
+  cudaMemset(c->counters.p, 0, CNT_NUM * sizeof(uint32_t));
+  *out = c;
+  return 0;
+}
+
+void gtsb_destroy(gtsb_context *c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->vattr, &c->astat, &c->seq_len_in, &c->copy_num_in, &c->root, &c->ctg, &c->dist,
+                    &c->std_dev, &c->flags, &c->row_ptr, &c->dst, &c->edist, &c->estd, &c->eflags,
+                    &c->eid, &c->win_rec, &c->estate, &c->vstate, &c->rep_pred, &c->cnt, &c->bptr,
+                    &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
+                    &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
+                    &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
+                    &c->work_a, &c->work_b, &c->big_scratch};
+  for (DevBuf *b : bufs) release(*b);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (Timer *t : {&c->t_build, &c->t_rep, &c->t_filter}) {
+    if (t->a) cudaEventDestroy(t->a);
+    if (t->b) cudaEventDestroy(t->b);
+  }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *gtsb_error(const gtsb_context *c) { return c ? c->err.c_str() : "null context"; }
+
+int gtsb_set_stream(gtsb_context *c, void *stream) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = static_cast<cudaStream_t>(stream);
+  c->own_stream = false;
+  return 0;
+}
+
+int gtsb_want_win_rec(gtsb_context *c, int on) {
+  if (c == nullptr) return -1;
+  c->want_win = on != 0;
+  return 0;
+}
+
+int gtsb_set_vertices_host(gtsb_context *c, uint64_t V, const uint32_t *seq_len, const float *astat,
+                           const float *copy_num) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (!c->seq_len_in.owned) c->seq_len_in = DevBuf();
+  if (!c->copy_num_in.owned) c->copy_num_in = DevBuf();
+  if (!c->astat.owned) c->astat = DevBuf();
+  ENSURE(c->seq_len_in, V * 4);
+  ENSURE(c->copy_num_in, V * 4);
+  ENSURE(c->astat, V * 4);
+  if (V) {
+    CK(cudaMemcpyAsync(c->seq_len_in.p, seq_len, V * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->copy_num_in.p, copy_num, V * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->astat.p, astat, V * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  return vertices_common(c, V);
+}
+
+int gtsb_set_vertices_device(gtsb_context *c, uint64_t V, const uint32_t *seq_len, const float *astat,
+                             const float *copy_num) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  adopt(c->seq_len_in, seq_len);
+  adopt(c->copy_num_in, copy_num);
+  adopt(c->astat, astat);
+  return vertices_common(c, V);
+}
+
+int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, const uint32_t *ctg,
+                          const int32_t *dist, const float *std_dev, const uint8_t *flags) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  DevBuf *bs[] = {&c->root, &c->ctg, &c->dist, &c->std_dev, &c->flags};
+  for (DevBuf *b : bs)
+    if (!b->owned) *b = DevBuf();
+  ENSURE(c->root, R * 4);
+  ENSURE(c->ctg, R * 4);
+  ENSURE(c->dist, R * 4);
+  ENSURE(c->std_dev, R * 4);
+  ENSURE(c->flags, R);
+  if (R) {
+    CK(cudaMemcpyAsync(c->root.p, root, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ctg.p, ctg, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->dist.p, dist, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->std_dev.p, std_dev, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->flags.p, flags, R, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->R = R;
+  c->have_records = true;
+  c->stats.nof_records = R;
+  return 0;
+}
+
+int gtsb_set_records_device(gtsb_context *c, uint64_t R, const uint32_t *root, const uint32_t *ctg,
+                            const int32_t *dist, const float *std_dev, const uint8_t *flags) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  adopt(c->root, root);
+  adopt(c->ctg, ctg);
+  adopt(c->dist, dist);
+  adopt(c->std_dev, std_dev);
+  adopt(c->flags, flags);
+  c->R = R;
+  c->have_records = true;
+  c->stats.nof_records = R;
+  return 0;
+}
+
+int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t *row_ptr,
+                        const uint32_t *dst, const int32_t *dist, const float *std_dev,
+                        const uint8_t *flags, const uint32_t *seq_len, const float *astat,
+                        const float *copy_num, const uint8_t *vstate, const uint8_t *estate) {
+  if (c == nullptr) return -1;
+  if (gtsb_set_vertices_host(c, V, seq_len, astat, copy_num) != 0) return -1;
+  if (E >= 0xFFFFFFF0ull) return fail(c, "too many edges");
+  cudaStream_t s = c->stream;
+  ENSURE(c->row_ptr, (V + 1) * 4);
+  ENSURE(c->dst, E * 4);
+  ENSURE(c->edist, E * 4);
+  ENSURE(c->estd, E * 4);
+  ENSURE(c->eflags, E);
+  ENSURE(c->estate, E);
+  ENSURE(c->big_rows, (V + 1) * 4);
+  CK(cudaMemcpyAsync(c->row_ptr.p, row_ptr, (V + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (E) {
+    CK(cudaMemcpyAsync(c->dst.p, dst, E * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->edist.p, dist, E * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->estd.p, std_dev, E * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->eflags.p, flags, E, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->estate.p, estate, E, cudaMemcpyHostToDevice, s));
+  }
+  if (V) CK(cudaMemcpyAsync(c->vstate.p, vstate, V, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
+  if (V) {
+    k_classify_rows<<<(uint32_t) ((V + 255) / 256), 256, 0, s>>>((uint32_t) V, c->row_ptr.as<uint32_t>(),
+                                                                  c->big_rows.as<uint32_t>(),
+                                                                  c->counters.as<uint32_t>());
+    c->stats.kernel_launches++;
+  }
+  if (read_counters(c) != 0) return -1;
+  c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
+  c->max_deg = c->h_counters[CNT_MAX_DEG];
+  c->E = E;
+  c->R = 0;
+  c->have_graph = true;
+  c->stats.nof_edges = E;
+  c->stats.big_rows = c->n_big_rows;
+  c->stats.max_degree = c->max_deg;
+  return 0;
+}
+
+int gtsb_build(gtsb_context *c) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (timer_begin(c, c->t_build) != 0) return -1;
+  if (do_build(c) != 0) return -1;
+  return timer_end(c, c->t_build, &c->stats.ms_build);
+}
+
+int gtsb_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (timer_begin(c, c->t_rep) != 0) return -1;
+  if (do_mark_repeats(c, cn_cutoff, astat_cutoff, use_cn) != 0) return -1;
+  return timer_end(c, c->t_rep, &c->stats.ms_mark_repeats);
+}
+
+int gtsb_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (timer_begin(c, c->t_filter) != 0) return -1;
+  if (do_filter(c, pcutoff, cncutoff, ocutoff) != 0) return -1;
+  return timer_end(c, c->t_filter, &c->stats.ms_filter);
+}
+
+int gtsb_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn, float pcutoff,
+                  float cncutoff, int64_t ocutoff) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (do_build(c) != 0) return -1;
+  if (do_mark_repeats(c, cn_cutoff, astat_cutoff, use_cn) != 0) return -1;
+  if (do_filter(c, pcutoff, cncutoff, ocutoff) != 0) return -1;
+  return 0;
+}
+
+uint64_t gtsb_nof_edges(const gtsb_context *c) { return c ? c->E : 0; }
+
+int gtsb_get_vertex_states(gtsb_context *c, uint8_t *vstate) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (c->V && vstate) CK(cudaMemcpyAsync(vstate, c->vstate.p, c->V, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dist, float *std_dev,
+                 uint8_t *flags, uint32_t *eid, uint32_t *win_rec, uint8_t *estate) {
+  if (c == nullptr) return -1;
+  if (!c->have_graph) return fail(c, "gtsb_get_csr: no graph");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const uint64_t V = c->V, E = c->E;
+  if (row_ptr) CK(cudaMemcpyAsync(row_ptr, c->row_ptr.p, (V + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (E) {
+    if (dst) CK(cudaMemcpyAsync(dst, c->dst.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (dist) CK(cudaMemcpyAsync(dist, c->edist.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (std_dev) CK(cudaMemcpyAsync(std_dev, c->estd.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (flags) CK(cudaMemcpyAsync(flags, c->eflags.p, E, cudaMemcpyDeviceToHost, s));
+    if (eid) {
+      if (c->eid.p == nullptr) return fail(c, "gtsb_get_csr: this graph has no eid (not built here)");
+      CK(cudaMemcpyAsync(eid, c->eid.p, E * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (win_rec) {
+      if (!c->want_win || c->win_rec.p == nullptr) return fail(c, "gtsb_get_csr: win_rec was not requested before gtsb_build");
+      CK(cudaMemcpyAsync(win_rec, c->win_rec.p, E * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (estate) CK(cudaMemcpyAsync(estate, c->estate.p, E, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int gtsb_device_pointers(gtsb_context *c, const uint32_t **row_ptr, const uint32_t **dst,
+                         const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate) {
+  if (c == nullptr) return -1;
+  if (row_ptr) *row_ptr = c->row_ptr.as<uint32_t>();
+  if (dst) *dst = c->dst.as<uint32_t>();
+  if (eid) *eid = c->eid.as<uint32_t>();
+  if (estate) *estate = c->estate.as<uint8_t>();
+  if (vstate) *vstate = c->vstate.as<uint8_t>();
+  return 0;
+}
+
+int gtsb_get_stats(gtsb_context *c, gtsb_stats *st) {
+  if (c == nullptr || st == nullptr) return -1;
+  c->stats.nof_vertices = c->V;
+  *st = c->stats;
+  return 0;
+}
+
+int gtsb_synchronize(gtsb_context *c) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+/* gtscaffold_b200.h -- C ABI of the B200-native scaffold-graph hot path.
+ *
+ * Array-level entry points: plain pointers and sizes, no GenomeTools and no
+ * torch types.  They are what the reference's three hot-path functions bind to
+ * (the binding itself is include/gtscaffold_dropin.h + INTEGRATION.md):
+ *
+ *   gtsb_build         <- the insert/dedup loop of
+ *                         gt_scaffolder_parser_read_distances
+ *                         (gt_scaffolder_parser.c:357-379) with
+ *                         gt_scaffolder_graph_add_edge / find_edge / alter_edge
+ *                         (gt_scaffolder_graph.c:137-184, 219-235)
+ *   gtsb_mark_repeats  <- the marking loop of gt_scaffolder_graph_mark_repeats
+ *                         (gt_scaffolder_algorithms.c:160-166, 61-87)
+ *   gtsb_filter        <- gt_scaffolder_graph_filter
+ *                         (gt_scaffolder_algorithms.c:261-343, 174-258)
+ *
+ * All functions return 0 on success and -1 on error (message: gtsb_error), the
+ * reference's own convention (gt_scaffolder_algorithms.c:112-113).  There is no
+ * CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Vertex ids are the reference's: rank of the contig header in strcmp order
+ * (gt_scaffolder_parser.c:172).  Records are in .de file order.
+ */
+#ifndef GTSCAFFOLD_B200_H
+#define GTSCAFFOLD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GraphItemState values (gt_scaffolder_graph.h:29-31) */
+enum { GTSB_UNVISITED = 0, GTSB_POLYMORPHIC = 1, GTSB_INCONSISTENT = 2, GTSB_REPEAT = 3,
+       GTSB_VISITED = 4, GTSB_PROCESSED = 5, GTSB_SCAFFOLD = 6, GTSB_CYCLIC = 7 };
+
+/* record / edge flag bits */
+#define GTSB_SENSE  1u   /* edge->sense  (record: before the ';', parser.c:382) */
+#define GTSB_SAME   2u   /* edge->same   (record: '+' suffix, parser.c:347)      */
+#define GTSB_RSENSE 4u   /* CSR slots only: sense of the reverse edge dst->src   */
+#define GTSB_RSAME  8u   /* CSR slots only: same of the reverse edge             */
+
+#define GTSB_WIN_SEEDED 0x80000000u  /* win_rec: attributes are the twin seed of that record */
+#define GTSB_MAX_VERTICES ((1u << 27) - 1u)
+
+typedef struct gtsb_context gtsb_context;
+
+typedef struct gtsb_stats {
+  uint64_t nof_vertices, nof_records, nof_edges;
+  uint32_t max_degree, big_rows, large_buckets;
+  uint32_t proposals, poly_sweeps, fire_rounds;
+  uint64_t kernel_launches;        /* kernels launched by this context so far */
+  float ms_build, ms_mark_repeats, ms_filter;   /* device time of the last call of each stage */
+} gtsb_stats;
+
+int gtsb_create(gtsb_context **ctx, int device);
+void gtsb_destroy(gtsb_context *ctx);
+const char *gtsb_error(const gtsb_context *ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own */
+int gtsb_set_stream(gtsb_context *ctx, void *cuda_stream);
+/* also record, per edge, which record's attributes it carries (needed to fill
+   GtScaffolderGraphEdge.num_pairs); costs 8 B/edge of extra traffic */
+int gtsb_want_win_rec(gtsb_context *ctx, int on);
+
+/* ---- inputs.  *_host variants copy from host memory (H2D on the context's
+   stream); *_device variants adopt device pointers that must stay valid. */
+int gtsb_set_vertices_host(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
+                           const float *astat, const float *copy_num);
+int gtsb_set_vertices_device(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
+                             const float *astat, const float *copy_num);
+int gtsb_set_records_host(gtsb_context *ctx, uint64_t nof_records, const uint32_t *root,
+                          const uint32_t *ctg, const int32_t *dist, const float *std_dev,
+                          const uint8_t *flags);
+int gtsb_set_records_device(gtsb_context *ctx, uint64_t nof_records, const uint32_t *root,
+                            const uint32_t *ctg, const int32_t *dist, const float *std_dev,
+                            const uint8_t *flags);
+/* an already-built graph (host CSR, flags incl. GTSB_RSENSE/RSAME, states);
+   used by the GtScaffolderGraph binding of mark_repeats / filter */
+int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_edges,
+                        const uint32_t *row_ptr, const uint32_t *dst, const int32_t *dist,
+                        const float *std_dev, const uint8_t *flags, const uint32_t *seq_len,
+                        const float *astat, const float *copy_num, const uint8_t *vstate,
+                        const uint8_t *estate);
+
+/* ---- the hot path */
+int gtsb_build(gtsb_context *ctx);
+int gtsb_mark_repeats(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff,
+                      int use_copy_num /* strlen(filename) != 0, algorithms.c:164 */);
+int gtsb_filter(gtsb_context *ctx, float pcutoff, float cncutoff, int64_t ocutoff);
+/* build + mark_repeats + filter back to back */
+int gtsb_pipeline(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff, int use_copy_num,
+                  float pcutoff, float cncutoff, int64_t ocutoff);
+
+/* ---- results (device-resident until fetched; NULL pointers are skipped) */
+uint64_t gtsb_nof_edges(const gtsb_context *ctx);
+int gtsb_get_vertex_states(gtsb_context *ctx, uint8_t *vstate);
+/* CSR in adjacency order; eid = index into the reference's graph->edges[] */
+int gtsb_get_csr(gtsb_context *ctx, uint32_t *row_ptr, uint32_t *dst, int32_t *dist,
+                 float *std_dev, uint8_t *flags, uint32_t *eid, uint32_t *win_rec,
+                 uint8_t *estate);
+/* device pointers of the resident result (for callers that keep it on the GPU) */
+int gtsb_device_pointers(gtsb_context *ctx, const uint32_t **row_ptr, const uint32_t **dst,
+                         const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate);
+int gtsb_get_stats(gtsb_context *ctx, gtsb_stats *stats);
+int gtsb_synchronize(gtsb_context *ctx);
+
+/* host helper: thresholds of the ambiguous-order test for a cutoff (exposed
+   for tests; see csrc/gtsb_threshold.c) */
+int gtsb_ambig_thresholds(float cutoff, float *t_pos, float *t_neg, int *inf_true);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracles
+(compiled reference when oracle/_ref is present, else the C restatement) and
+against the committed golden vectors.  Bit-exact: integer/byte/index work and
+IEEE-exact float decisions."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS = ("src", "dst", "dist", "std_dev", "flags", "row_ptr", "adj_eid", "vstate", "estate")
+DEFAULT = dict(cn_cut=0.3, a_cut=20.0, use_cn=True, pc=0.01, cnc=1.5, oc=400)
+
+
+def _cmp(got, exp, what=""):
+    for k in KEYS:
+        if not np.array_equal(got[k], exp[k]):
+            bad = np.nonzero(np.asarray(got[k]) != np.asarray(exp[k]))[0] if got[k].shape == exp[k].shape else []
+            raise AssertionError(f"{what}: {k} differs at {len(bad)} positions, first {bad[:8]}; "
+                                 f"got {np.asarray(got[k])[bad[:8]]} exp {np.asarray(exp[k])[bad[:8]]}")
+
+
+def _run_both(pkg, inp, cn_cut, a_cut, use_cn, pc, cnc, oc, stagewise=True):
+    g = pkg.ScaffoldGraphB200.new_from_records(inp)
+    ref = O.best_oracle().build(inp)
+    if stagewise:
+        _cmp(g.result(), ref.result(), "build")
+    g.mark_repeats(cn_cut, a_cut, use_cn)
+    ref.mark_repeats(cn_cut, a_cut, use_copy_num=use_cn)
+    if stagewise:
+        _cmp(g.result(), ref.result(), "mark_repeats")
+    g.filter(pc, cnc, oc)
+    ref.filter(pc, cnc, oc)
+    _cmp(g.result(), ref.result(), "filter")
+    st = g.stats()
+    g.close()
+    ref.close()
+    return st
+
+
+PARAMS = [(0.3, 20.0, True, 0.01, 1.5, 400), (0.3, 20.0, True, 0.01, 1.5, 0),
+          (0.3, 20.0, False, 0.01, 1.5, -1), (0.5, 19.5, True, 0.2, 2.5, 50),
+          (0.3, 20.0, True, 0.5, 1.5, 400), (0.0, -1e9, True, -0.5, 9.0, 3000)]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_tiny_adversarial(pkg, synth, seed):
+    inp = synth.tiny_dense(4 + seed % 13, 6 + 3 * (seed % 17), 3000 + seed, split_lines=bool(seed % 2))
+    _run_both(pkg, inp, *PARAMS[seed % len(PARAMS)])
+
+
+def test_empty_and_degenerate(pkg, synth):
+    # vertices without any record; a single pair; records only one-sided
+    inp = synth.tiny_dense(5, 1, 1)
+    empty = synth.ScaffoldInput(inp.seq_len, inp.astat, inp.copy_num, inp.root[:0], inp.ctg[:0],
+                                inp.dist[:0], inp.std_dev[:0], inp.num_pairs[:0], inp.flags[:0])
+    g = pkg.ScaffoldGraphB200.new_from_records(empty)
+    g.mark_repeats()
+    g.filter()
+    assert g.E == 0
+    ref = O.PortGraph(empty)
+    ref.mark_repeats(0.3, 20.0)
+    assert np.array_equal(g.vstate(), ref.vstate())
+    _run_both(pkg, inp, *PARAMS[0])
+
+
+def test_invalid_records_are_refused(pkg, synth):
+    inp = synth.tiny_dense(5, 4, 2)
+    bad = synth.ScaffoldInput(inp.seq_len, inp.astat, inp.copy_num, inp.root.copy(), inp.ctg.copy(),
+                              inp.dist, inp.std_dev, inp.num_pairs, inp.flags)
+    bad.ctg[0] = 99
+    with pytest.raises(RuntimeError):
+        pkg.ScaffoldGraphB200.new_from_records(bad)
+    bad.ctg[0] = bad.root[0]
+    with pytest.raises(RuntimeError):
+        pkg.ScaffoldGraphB200.new_from_records(bad)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "diff_*.npz"))))
+def test_committed_differential_vectors(pkg, synth, path):
+    z = np.load(path)
+    inp = synth.ScaffoldInput(**{k: z[k] for k in ["seq_len", "astat", "copy_num", "root", "ctg",
+                                                   "dist", "std_dev", "num_pairs", "flags"]})
+    pc, cnc, oc, cn_cut, a_cut, use_cn = z["params"]
+    g = pkg.ScaffoldGraphB200.new_from_records(inp)
+    r = g.result()
+    for k, zk in [("src", "e_src"), ("dst", "e_dst"), ("dist", "e_dist"), ("std_dev", "e_std"),
+                  ("flags", "e_flags"), ("row_ptr", "row_ptr"), ("adj_eid", "adj_eid")]:
+        assert np.array_equal(r[k], z[zk]), k
+    g.mark_repeats(float(cn_cut), float(a_cut), bool(use_cn))
+    r = g.result()
+    assert np.array_equal(r["vstate"], z["rep_vstate"]) and np.array_equal(r["estate"], z["rep_estate"])
+    g.filter(float(pc), float(cnc), int(oc))
+    r = g.result()
+    assert np.array_equal(r["vstate"], z["fin_vstate"]) and np.array_equal(r["estate"], z["fin_estate"])
+
+
+@pytest.mark.parametrize("name,V,kw", [
+    ("c2_bacterial", None, {}),
+    ("c2_bacterial", 30_000, dict(line_order="id", one_sided_frac=0.2)),
+    ("c3_human", 400_000, {}),
+    ("c4_repeat_hubs", 150_000, dict(max_deg=3000)),
+])
+def test_named_configs(pkg, synth, name, V, kw):
+    inp = synth.generate(name, V=V, **kw)
+    st = _run_both(pkg, inp, **{k: v for k, v in zip(
+        ["cn_cut", "a_cut", "use_cn", "pc", "cnc", "oc"], PARAMS[0])}, stagewise=False)
+    assert st["nof_edges"] > 0
+
+
+def test_win_rec_points_at_the_winning_record(pkg, synth):
+    inp = synth.tiny_dense(12, 60, 77)
+    g = pkg.ScaffoldGraphB200.new_from_records(inp, want_win_rec=True)
+    c = g.csr(win_rec=True)
+    ref = O.PortGraph(inp)
+    e = ref.edges()
+    order = np.argsort(c["eid"])
+    win = c["win_rec"][order]
+    assert np.array_equal((win & 0x7FFFFFFF).astype(np.int64), e["win_rec"])
+    # seeded <=> the edge carries the twin seed of a record of the other direction
+    seeded = (win >> 31).astype(bool)
+    rec_root = inp.root[(win & 0x7FFFFFFF)]
+    assert np.array_equal(seeded, rec_root != e["src"])
+
+
+def test_filter_on_uploaded_graph_with_arbitrary_states(pkg, synth):
+    """gtsb_set_graph_host path (what the GtScaffolderGraph binding uses)."""
+    rng = np.random.default_rng(11)
+    for seed in range(12):
+        inp = synth.tiny_dense(12, 50, 4000 + seed)
+        ref = O.best_oracle().build(inp)
+        res = ref.result()
+        E, V = len(res["src"]), len(res["vstate"])
+        vs = rng.choice([0, 0, 0, 1, 3, 7, 4], V).astype(np.uint8)
+        es = rng.choice([0, 0, 0, 1, 2, 3, 7, 6], E).astype(np.uint8)
+        # CSR in adjacency order with reverse-edge flags
+        eids = res["adj_eid"].astype(np.int64)
+        rev = {(int(s), int(d)): i for i, (s, d) in enumerate(zip(res["src"], res["dst"]))}
+        flags = np.zeros(E, np.uint8)
+        for slot, e in enumerate(eids):
+            r = rev[(int(res["dst"][e]), int(res["src"][e]))]
+            flags[slot] = res["flags"][e] | ((res["flags"][r] & 3) << 2)
+        g = pkg.ScaffoldGraphB200()
+        g.set_graph(res["row_ptr"].astype(np.uint32), res["dst"][eids], res["dist"][eids].astype(np.int32),
+                    res["std_dev"][eids], flags, inp.seq_len, inp.astat, inp.copy_num, vs, es[eids])
+        g.filter(0.01, 1.5, 400)
+        ref.set_states(vs, es)
+        ref.filter(0.01, 1.5, 400)
+        c = g.csr(eid=False)
+        assert np.array_equal(g.vstate(), ref.vstate()), seed
+        assert np.array_equal(c["estate"], ref.estate()[eids]), seed
