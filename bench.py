@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- scaffold-graph edges pushed through build + mark_repeats + filter
+per second (BASELINE.json's metric) on synthetic graphs of the named shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c3_human] [--vertices V] [--line-order shuffled|id]
+
+A "step" is one pass of the hot path (records -> CSR -> repeat marks ->
+polymorphic/inconsistent marks) over one synthetic graph.  `value` times it
+with inputs already resident in HBM; `e2e` times the same call through the
+C ABI with HOST buffers (H2D of records/vertices and D2H of vertex/edge states
+inside the timed region).  `--impl reference` times the reference's own
+single-threaded C (oracle/_ref, compiled from /root/reference) on a bounded
+sample of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "scaffold_graph_edges_filtered_per_sec"
+UNIT = "edges/s"
+PARAMS = dict(copy_num_cutoff=0.3, astat_cutoff=20.0, use_copy_num=True,     # test.c:35-42
+              pcutoff=0.01, cncutoff=1.5, ocutoff=400)
+B_E, B_V = 62, 19       # algorithmic bytes per directed edge / per vertex
+STAGE_BYTES = {"build": 34, "mark_repeats": 5, "filter": 23}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_reference_leg(pkg, workload, sample_vertices, line_order, steps=1, warmup=0):
+    """The reference's own C (oracle/_ref) -- or the C port when oracle/_ref is
+    absent -- single-threaded on one host core, on a bounded sample."""
+    import oracle_lib as O
+    import torch
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"     # input plumbing only
+    t = pkg.synth.generate_torch(workload, V=sample_vertices, device=gen_dev, line_order=line_order)
+    inp = pkg.synth.torch_to_input(t)
+    kind = "reference" if O.have_ref() else "port"
+    times = []
+    E = 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        g = O.best_oracle().build(inp)
+        g.mark_repeats(PARAMS["copy_num_cutoff"], PARAMS["astat_cutoff"], use_copy_num=PARAMS["use_copy_num"])
+        g.filter(PARAMS["pcutoff"], PARAMS["cncutoff"], PARAMS["ocutoff"])
+        dt = time.perf_counter() - t0
+        E = g.E
+        g.close()
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": E / sec, "unit": UNIT, "cores": 1, "kind": kind,
+            "host_cores": os.cpu_count(),
+            "sample": f"{workload} at V={sample_vertices} (E={E}), build+mark_repeats+filter, "
+                      f"{sec:.2f} s per pass, 1 thread"}, sec, E
+
+
+def run_reference_arm(args, pkg):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cb, sec, E = cpu_reference_leg(pkg, args.workload, args.cpu_sample_vertices, args.line_order,
+                                   steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(args.warmup, 1),
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64/f32/f64 (reference C)", "data": "synthetic",
+            "config": {"workload": args.workload, "sample_vertices": args.cpu_sample_vertices,
+                       "line_order": args.line_order, **{k: PARAMS[k] for k in ("pcutoff", "cncutoff", "ocutoff")}},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_arm(args, pkg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: weak scaling, every rank owns one graph of the named shape
+    V = args.vertices
+    t = pkg.synth.generate_torch(args.workload, V=V, device=dev, line_order=args.line_order,
+                                 seed=None if world == 1 else 0x5CAFF01D + 1000 * rank)
+    Vn, Rn = int(t["seq_len"].shape[0]), int(t["root"].shape[0])
+    stream = torch.cuda.current_stream(dev)
+    g = pkg.ScaffoldGraphB200(device=local, stream=stream.cuda_stream)
+    P = PARAMS
+
+    def set_device_inputs():
+        g.set_vertices_device(Vn, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
+        g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
+                             t["std_dev"].data_ptr(), t["flags"].data_ptr())
+
+    def step():
+        g.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
+                   P["cncutoff"], P["ocutoff"])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    set_device_inputs()
+    for _ in range(args.warmup):
+        step()
+    launches0 = g.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    st = g.stats()
+    launches = (st["kernel_launches"] - launches0) // max(1, args.steps)
+    E = st["nof_edges"]
+
+    # ---- per-kernel device time (CUDA events on the launching stream), 2 extra steps
+    g.set_profile(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step()
+    kern = {n: (m / prof_steps, c / prof_steps) for n, (m, c) in g.profile().items()}
+    g.set_profile(False)
+
+    # ---- e2e: the same call through the C ABI with host buffers
+    host = {k: t[k].cpu().pin_memory() for k in ("seq_len", "astat", "copy_num", "root", "ctg", "dist",
+                                                  "std_dev", "flags")}
+    vstate_h = torch.empty(Vn, dtype=torch.uint8).pin_memory()
+    estate_h = torch.empty(2 * Rn, dtype=torch.uint8).pin_memory()
+    eid_h = torch.empty(2 * Rn, dtype=torch.int32).pin_memory()
+    g2 = pkg.ScaffoldGraphB200(device=local, stream=stream.cuda_stream)
+
+    def e2e_step():
+        g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
+                                           host["copy_num"].data_ptr()))
+        g2.V = Vn
+        g2._ck(g2.L.gtsb_set_records_host(g2.h, Rn, host["root"].data_ptr(), host["ctg"].data_ptr(),
+                                          host["dist"].data_ptr(), host["std_dev"].data_ptr(),
+                                          host["flags"].data_ptr()))
+        g2.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
+                    P["cncutoff"], P["ocutoff"])
+        g2._ck(g2.L.gtsb_get_vertex_states(g2.h, vstate_h.data_ptr()))
+        g2._ck(g2.L.gtsb_get_csr(g2.h, None, None, None, None, None, eid_h.data_ptr(), None,
+                                 estate_h.data_ptr()))
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev3.record(stream)
+    barrier()
+    e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    h2d = Vn * 12 + Rn * 17
+    d2h = Vn + E * 5
+    g2.close()
+
+    # ---- max over ranks, whole-job aggregate
+    ms_step = ms_total / args.steps
+    vals = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(E), float(Vn)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms = float(vals[0]), float(vals[1])
+    E_all, V_all = float(tot[0]), float(tot[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    alg_bytes = B_E * E + B_V * Vn                     # per GPU
+    dom = max(kern.items(), key=lambda kv: kv[1][0]) if kern else ("n/a", (float("nan"), 0))
+    stage_of = lambda n: ("mark_repeats" if "repeat" in n else
+                          "filter" if any(x in n for x in ("pairs", "poly", "overlap", "fire", "finalize"))
+                          else "build")
+    dom_bytes = STAGE_BYTES[stage_of(dom[0])] * E      # the stage's compulsory bytes
+    dom_ms = dom[1][0]
+    roofline = {"bound": "hbm", "kernel": dom[0], "stage": stage_of(dom[0]),
+                "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms == dom_ms and dom_ms > 0 else None,
+                "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "kernel_ms_per_step": dom_ms,
+                "pipeline": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms_step * 1e-3) / 1e9,
+                             "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                "kernels_ms_per_step": {k: round(v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}}
+    roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
+
+    cb, _, _ = cpu_reference_leg(pkg, args.workload, args.cpu_sample_vertices, args.line_order)
+    line = {"metric": METRIC, "value": E_all / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32/i32/f32 (+i64,f64 in the exact slow path)", "data": "synthetic",
+            "config": {"workload": args.workload, "vertices_per_gpu": Vn, "records_per_gpu": Rn,
+                       "edges_per_gpu": int(E), "line_order": args.line_order,
+                       "l2": "inputs (%.2f GB) larger than L2; no flush" % ((Vn * 12 + Rn * 17) / 1e9),
+                       **{k: P[k] for k in ("pcutoff", "cncutoff", "ocutoff", "astat_cutoff", "copy_num_cutoff")}},
+            "e2e": {"value": E_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
+            "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds")}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_human")
+    ap.add_argument("--vertices", type=int, default=None, help="override the config's vertex count (per GPU)")
+    ap.add_argument("--line-order", default="shuffled", choices=["shuffled", "id"])
+    ap.add_argument("--cpu-sample-vertices", type=int, default=2_000_000)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    pkg = importlib.import_module("gt-scaffold_b200")
+    if args.impl == "reference":
+        run_reference_arm(args, pkg)
+    else:
+        run_b200_arm(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

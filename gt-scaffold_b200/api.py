@@ -32,6 +32,7 @@ EXPORTS = [
     "gtsb_set_records_device", "gtsb_set_graph_host", "gtsb_build", "gtsb_mark_repeats",
     "gtsb_filter", "gtsb_pipeline", "gtsb_nof_edges", "gtsb_get_vertex_states", "gtsb_get_csr",
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
+    "gtsb_set_profile", "gtsb_get_profile",
 ]
 
 
@@ -83,6 +84,9 @@ def load_library():
     L.gtsb_device_pointers.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.gtsb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.gtsb_synchronize.argtypes = [vp]
+    L.gtsb_set_profile.argtypes = [vp, i32]
+    L.gtsb_get_profile.argtypes = [vp, C.c_char_p, u64, C.POINTER(C.c_double), C.POINTER(C.c_uint32),
+                                   C.c_uint32]
     L.gtsb_ambig_thresholds.argtypes = [f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
     _lib = L
     return L
@@ -222,6 +226,21 @@ class ScaffoldGraphB200:
         ps = [C.c_void_p() for _ in range(5)]
         self._ck(self.L.gtsb_device_pointers(self.h, *[C.byref(p) for p in ps]))
         return dict(zip(["row_ptr", "dst", "eid", "estate", "vstate"], [p.value for p in ps]))
+
+    def set_profile(self, on: bool):
+        """Per-kernel device timing (CUDA events on the launching stream)."""
+        self._ck(self.L.gtsb_set_profile(self.h, int(on)))
+
+    def profile(self):
+        """{kernel name: (accumulated ms, launch groups)} since set_profile(True)."""
+        names = C.create_string_buffer(8192)
+        ms = (C.c_double * 64)()
+        calls = (C.c_uint32 * 64)()
+        n = self.L.gtsb_get_profile(self.h, names, 8192, ms, calls, 64)
+        if n < 0:
+            self._ck(-1)
+        ks = names.value.decode().split(";")[:n] if n else []
+        return {k: (ms[i], calls[i]) for i, k in enumerate(ks)}
 
     def stats(self):
         s = Stats()

@@ -14,6 +14,30 @@
 
 using namespace gtsb;
 
+namespace gtsb {
+struct Profiler {
+  struct Rec { const char *name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+static thread_local Profiler *g_prof = nullptr;
+KernelTimer::KernelTimer(const char *n, cudaStream_t s) : name(n), stream(s), slot(-1) {
+  if (g_prof == nullptr) return;
+  Profiler::Rec r{n, g_prof->get(), g_prof->get()};
+  cudaEventRecord(r.a, s);
+  slot = (int) g_prof->recs.size();
+  g_prof->recs.push_back(r);
+}
+KernelTimer::~KernelTimer() {
+  if (g_prof == nullptr || slot < 0) return;
+  cudaEventRecord(g_prof->recs[slot].b, stream);
+}
+}  // namespace gtsb
+
 namespace {
 
 struct DevBuf {
@@ -55,6 +79,12 @@ struct gtsb_context {
   uint32_t *h_counters = nullptr;   // pinned
   gtsb_stats stats{};
   Timer t_build, t_rep, t_filter;
+
+  bool profile = false;
+  gtsb::Profiler prof;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<uint32_t> prof_calls;
 
   // cached ambiguous-order thresholds
   bool ambig_valid = false;
@@ -211,7 +241,35 @@ int get_ambig(gtsb_context *c, float pcutoff) {
   return 0;
 }
 
+struct ProfScope {
+  gtsb_context *c;
+  explicit ProfScope(gtsb_context *ctx) : c(ctx) { gtsb::g_prof = c->profile ? &c->prof : nullptr; }
+  ~ProfScope() { gtsb::g_prof = nullptr; }
+};
+
+// fold finished event pairs into the per-kernel totals (stream must be idle)
+void prof_collect(gtsb_context *c) {
+  for (auto &r : c->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+    size_t k = 0;
+    for (; k < c->prof_names.size(); k++)
+      if (c->prof_names[k] == r.name) break;
+    if (k == c->prof_names.size()) {
+      c->prof_names.push_back(r.name);
+      c->prof_ms.push_back(0.0);
+      c->prof_calls.push_back(0);
+    }
+    c->prof_ms[k] += ms;
+    c->prof_calls[k] += 1;
+    c->prof.pool.push_back(r.a);
+    c->prof.pool.push_back(r.b);
+  }
+  c->prof.recs.clear();
+}
+
 int do_build(gtsb_context *c) {
+  ProfScope ps_(c);
   if (!c->have_vertices || !c->have_records) return fail(c, "gtsb_build: vertices and records must be set first");
   const uint64_t V = c->V, R = c->R;
   if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records");
@@ -312,6 +370,7 @@ int do_build(gtsb_context *c) {
 }
 
 int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
+  ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_mark_repeats: no graph (call gtsb_build or gtsb_set_graph_host)");
   launch_mark_repeats(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
   c->stats.kernel_launches += c->V ? 2 : 0;
@@ -320,6 +379,7 @@ int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int us
 }
 
 int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
+  ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
   if (get_ambig(c, pcutoff) != 0) return -1;
   const uint64_t V = c->V, E = c->E;
@@ -670,6 +730,39 @@ int gtsb_get_stats(gtsb_context *c, gtsb_stats *st) {
   c->stats.nof_vertices = c->V;
   *st = c->stats;
   return 0;
+}
+
+int gtsb_set_profile(gtsb_context *c, int on) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  prof_collect(c);
+  c->profile = on != 0;
+  c->prof_names.clear();
+  c->prof_ms.clear();
+  c->prof_calls.clear();
+  return 0;
+}
+
+int gtsb_get_profile(gtsb_context *c, char *names, uint64_t names_cap, double *ms, uint32_t *calls,
+                     uint32_t cap) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  prof_collect(c);
+  std::string joined;
+  uint32_t n = 0;
+  for (size_t k = 0; k < c->prof_names.size() && n < cap; k++, n++) {
+    if (k) joined += ";";
+    joined += c->prof_names[k];
+    if (ms) ms[n] = c->prof_ms[k];
+    if (calls) calls[n] = c->prof_calls[k];
+  }
+  if (names && names_cap) {
+    strncpy(names, joined.c_str(), names_cap - 1);
+    names[names_cap - 1] = 0;
+  }
+  return (int) n;
 }
 
 int gtsb_synchronize(gtsb_context *c) {

@@ -343,14 +343,17 @@ static inline uint32_t grid_for(uint64_t n, int threads, int max_blocks) {
 }
 
 void launch_build_count(const BuildArgs &a, cudaStream_t s) {
+  { KernelTimer t_("k_count_halfedges", s);
   k_count_halfedges<<<grid_for(a.R, 256, a.sm_count * 16), 256, 0, s>>>(a.R, a.V, a.root, a.ctg,
-                                                                         a.cnt, a.counters + CNT_ERROR);
+                                                                         a.cnt, a.counters + CNT_ERROR); }
   exclusive_scan<uint32_t>(a.cnt, a.V, a.bptr, a.scan_scratch, s);
 }
 
 void launch_build_scatter_resolve(const BuildArgs &a, cudaStream_t s) {
+  { KernelTimer t_("k_scatter_halfedges", s);
   k_scatter_halfedges<<<grid_for(a.R, 256, a.sm_count * 16), 256, 0, s>>>(
-      a.R, a.V, a.root, a.ctg, a.dist, a.std_dev, a.flags, a.bptr, a.cursor, a.entries);
+      a.R, a.V, a.root, a.ctg, a.dist, a.std_dev, a.flags, a.bptr, a.cursor, a.entries); }
+  KernelTimer t2_("k_resolve_small", s);
   if (a.V)
     k_resolve_small<<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
                                                       a.creator_flag, a.large_list, a.counters);
@@ -360,6 +363,7 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
                                 uint32_t nlarge, cudaStream_t s) {
   if (nlarge == 0) return;
   uint32_t blocks = nlarge < (uint32_t) a.sm_count * 8 ? nlarge : (uint32_t) a.sm_count * 8;
+  KernelTimer t_("k_resolve_large", s);
   k_resolve_large<<<blocks, 256, 0, s>>>(a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
                                          a.large_list, a.counters, scratch, scratch_tag);
 }
@@ -367,6 +371,7 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
 void launch_build_emit(const BuildArgs &a, cudaStream_t s) {
   exclusive_scan<uint32_t>(a.deg, a.V, a.row_ptr, a.scan_scratch, s);
   exclusive_scan<uint8_t>(a.creator_flag, a.R, a.krank, a.scan_scratch, s);
+  KernelTimer t_("k_emit_csr", s);
   if (a.V)
     k_emit_csr<<<(a.V + 255) / 256, 256, 0, s>>>(a.V, a.bptr, a.row_ptr, a.entries, a.bwin, a.krank,
                                                  a.dst, a.edist, a.win_rec, a.estd, a.eflags, a.eid,

@@ -81,8 +81,10 @@ void launch_mark_repeats(const GraphArgs &g, uint8_t *rep_pred, float copy_num_c
                          float astat_cutoff, int use_copy_num, cudaStream_t s) {
   if (g.V == 0) return;
   const uint32_t blocks = (g.V + 255) / 256;
+  { KernelTimer t_("k_repeat_vertices", s);
   k_repeat_vertices<<<blocks, 256, 0, s>>>(g.V, g.astat, g.vattr, copy_num_cutoff, astat_cutoff,
-                                           use_copy_num, rep_pred, g.vstate);
+                                           use_copy_num, rep_pred, g.vstate); }
+  KernelTimer t2_("k_repeat_edges", s);
   k_repeat_edges<<<blocks, 256, 0, s>>>(g.V, g.row_ptr, g.dst, rep_pred, g.estate);
 }
 
@@ -176,8 +178,9 @@ __global__ void __launch_bounds__(512) k_pairs_big(FilterArgs a) {
 
 void launch_filter_pairs(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
-  k_pairs_small<<<(a.g.V + 127) / 128, 128, 0, s>>>(a);
-  if (a.g.n_big_rows) k_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
+  { KernelTimer t_("k_pairs_small", s);
+  k_pairs_small<<<(a.g.V + 127) / 128, 128, 0, s>>>(a); }
+  if (a.g.n_big_rows) { KernelTimer t_("k_pairs_big", s); k_pairs_big<<<a.big_blocks, 512, 0, s>>>(a); }
 }
 
 // ------------------------------------------------------------------ polyTime fixpoint
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(256) k_poly_commit(const uint2 *__restrict__ p
 void launch_poly_sweep(const FilterArgs &a, uint32_t n, cudaStream_t s) {
   if (n == 0) return;
   const uint32_t blocks = (n + 255) / 256;
+  KernelTimer t_("k_poly_sweep(3 kernels)", s);
   k_poly_reset<<<blocks, 256, 0, s>>>(a.proposals, n, a.poly_new);
   k_poly_propose<<<blocks, 256, 0, s>>>(a.proposals, n, a.poly_cur, a.poly_new);
   k_poly_commit<<<blocks, 256, 0, s>>>(a.proposals, n, a.poly_cur, a.poly_new, a.g.counters);
@@ -322,8 +326,9 @@ __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
 
 void launch_filter_overlap(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
-  k_overlap_small<<<(a.g.V + 127) / 128, 128, 0, s>>>(a);
-  if (a.g.n_big_rows) k_overlap_big<<<a.big_blocks, 512, 0, s>>>(a);
+  { KernelTimer t_("k_overlap_small", s);
+  k_overlap_small<<<(a.g.V + 127) / 128, 128, 0, s>>>(a); }
+  if (a.g.n_big_rows) { KernelTimer t_("k_overlap_big", s); k_overlap_big<<<a.big_blocks, 512, 0, s>>>(a); }
 }
 
 // ------------------------------------------------------------------ fire fixpoint
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s) {
   if (n_in == 0) return;
+  KernelTimer t_("k_fire_round", s);
   k_fire_round<<<(n_in + 127) / 128, 128, 0, s>>>(a, work_in, n_in, work_out, n_out);
 }
 
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(256) k_finalize(FilterArgs a) {
 
 void launch_filter_finalize(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
+  KernelTimer t_("k_finalize", s);
   k_finalize<<<(a.g.V + 255) / 256, 256, 0, s>>>(a);
 }
 

@@ -7,6 +7,17 @@
 
 namespace gtsb {
 
+// Optional per-kernel device timing (CUDA events on the launching stream),
+// switched on by gtsb_set_profile; a no-op otherwise.
+struct KernelTimer {
+  const char *name;
+  cudaStream_t stream;
+  int slot;
+  explicit KernelTimer(const char *n, cudaStream_t s);
+  ~KernelTimer();
+};
+#define GTSB_TIMED(name, stream) ::gtsb::KernelTimer gtsb_timer_##__LINE__(name, stream)
+
 constexpr uint32_t BIG_ROW = 32;    // rows above this take the block-per-row path
 
 // device counter block (uint32 each)

@@ -3,6 +3,7 @@
 // (one block), tile scan with carry-in.  out[n] receives the grand total.
 #pragma once
 #include "gtsb_common.cuh"
+#include "gtsb_kernels.h"
 
 namespace gtsb {
 
@@ -106,6 +107,7 @@ inline void exclusive_scan(const T *in, uint64_t n, uint32_t *out, uint32_t *til
     return;
   }
   const uint32_t ntiles = (uint32_t) ((n + SCAN_TILE - 1) / SCAN_TILE);
+  KernelTimer timer_(sizeof(T) == 1 ? "scan_u8(3 kernels)" : "scan_u32(3 kernels)", stream);
   k_scan_tile_sums<T><<<ntiles, SCAN_THREADS, 0, stream>>>(in, n, tile_scratch);
   k_scan_tile_offsets<<<1, 1024, 0, stream>>>(tile_scratch, ntiles, out + n);
   k_scan_tiles<T><<<ntiles, SCAN_THREADS, 0, stream>>>(in, n, tile_scratch, out);

@@ -262,3 +262,139 @@ def tiny_dense(V: int, n_pairs: int, seed: int, *, repeats: float = 0.12,
         dist=np.array(arr[2], np.int32), std_dev=np.array(arr[3], np.float32),
         num_pairs=rng.integers(10, 801, R).astype(np.uint32), flags=flags,
         name="tiny_dense", meta={"V": V, "records": R, "seed": seed})
+
+
+# --------------------------------------------------------------------------
+# torch version of generate(): same distributions, runs on the GPU so that the
+# 10^7..10^8-vertex configs materialise in a second instead of minutes.  The
+# random streams differ from the numpy generator (and between devices); parity
+# tests always feed ONE set of arrays to both the CUDA path and the oracle.
+
+def generate_torch(name: str = "c3_human", V: int | None = None, *, device="cuda",
+                   mean_pairs: float | None = None, seed: int | None = None,
+                   line_order: str = "shuffled", one_sided_frac: float = 0.0,
+                   mirror_diff_frac: float = 0.01, dup_same_line_frac: float = 0.005,
+                   max_deg: int = 10_000, zipf_alpha: float = 2.1):
+    """Returns a dict of torch tensors on `device`: seq_len(i32) astat(f32)
+    copy_num(f32) root(i32) ctg(i32) dist(i32) std_dev(f32) num_pairs(i32)
+    flags(u8), plus 'meta'."""
+    import torch
+    config_id, V0, mp0, kind = CONFIGS[name]
+    V = V0 if V is None else int(V)
+    mp = mp0 if mean_pairs is None else mean_pairs
+    s = splitmix64(0x5CAFF01D ^ config_id) if seed is None else splitmix64(seed)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(s & ((1 << 63) - 1))
+    dev = torch.device(device)
+
+    def rand(n):
+        return torch.rand(n, generator=gen, device=dev, dtype=torch.float64)
+
+    def randint(lo, hi, n):
+        return torch.randint(lo, hi, (n,), generator=gen, device=dev, dtype=torch.int64)
+
+    def normal(n):
+        return torch.randn(n, generator=gen, device=dev, dtype=torch.float64)
+
+    # vertices
+    seq_len = torch.clamp(torch.round(torch.exp(7.6 + 1.1 * normal(V))), 201, 200000).to(torch.int32)
+    u = rand(V)
+    astat = 20.5 + (6000.0 - 20.5) * rand(V)
+    rep = u < 0.10
+    astat = torch.where(rep, 20.0 - 420.0 * rand(V), astat)
+    astat = torch.where((u >= 0.10) & (u < 0.12), torch.zeros_like(astat), astat).to(torch.float32)
+    if V:
+        astat[randint(0, V, max(1, V // 1000))] = 20.0
+    u = rand(V)
+    cn = 1.0 + 0.06 * normal(V)
+    cn = torch.where(u < 0.06, 0.05 + 0.70 * rand(V), cn)
+    cn = torch.where((u >= 0.06) & (u < 0.10), 1.6 + 4.4 * rand(V), cn).to(torch.float32)
+    if V > 1:
+        dup = torch.nonzero(rand(V) < 0.05).flatten()
+        dup = dup[dup > 0]
+        cn[dup] = cn[dup - 1]
+
+    # links
+    if kind == "uniform":
+        P = int(round(mp * V))
+        a = randint(0, V, P)
+    else:
+        # Zipf(alpha) degrees by inverse transform on a truncated support
+        k = torch.arange(1, max_deg + 1, device=dev, dtype=torch.float64)
+        cdf = torch.cumsum(k ** (-zipf_alpha), 0)
+        cdf = cdf / cdf[-1]
+        deg = torch.searchsorted(cdf, rand(V)).clamp(max=max_deg - 1) + 1
+        a = torch.repeat_interleave(torch.arange(V, device=dev, dtype=torch.int64), deg)
+        P = int(a.shape[0])
+    if V < 2:
+        P = 0
+        a = a[:0]
+    b = randint(0, max(V - 1, 1), P)
+    b = b + (b >= a).to(torch.int64)
+    lo, hi = torch.minimum(a, b), torch.maximum(a, b)
+    key = torch.unique(lo * V + hi)
+    key = key[torch.randperm(key.shape[0], generator=gen, device=dev)]
+    lo, hi = key // V, key % V
+    swap = rand(key.shape[0]) < 0.5
+    a, b = torch.where(swap, hi, lo), torch.where(swap, lo, hi)
+    P = int(a.shape[0])
+
+    sense_a = rand(P) < 0.5
+    same = rand(P) < 0.5
+    sense_b = torch.where(same, ~sense_a, sense_a)
+    dist = randint(-99, 3001, P)
+    std = torch.round((0.5 + 59.5 * rand(P)) * 10.0) / 10.0
+    std = torch.where(rand(P) < 0.005, torch.zeros_like(std), std)
+    npairs = randint(10, 801, P)
+    if P > 1:
+        order = torch.sort(a, stable=True).indices
+        prev = torch.empty(P, dtype=torch.int64, device=dev)
+        prev[order[1:]] = order[:-1]
+        prev[order[0]] = order[0]
+        has_sib = a[prev] == a
+        has_sib[order[0]] = False
+        pick = has_sib & (rand(P) < 0.30)
+        dist = torch.where(pick, dist[prev] + randint(-8, 9, P), dist)
+
+    keep_b = rand(P) >= one_sided_frac
+    md = keep_b & (rand(P) < mirror_diff_frac)
+    dist_b = torch.where(md, dist + randint(-40, 41, P), dist)
+    std_b = torch.where(md, torch.round((0.5 + 59.5 * rand(P)) * 10.0) / 10.0, std)
+    dupm = rand(P) < dup_same_line_frac
+    nd = int(dupm.sum())
+    root = torch.cat([a, b[keep_b], a[dupm]])
+    ctg = torch.cat([b, a[keep_b], b[dupm]])
+    sense = torch.cat([sense_a, sense_b[keep_b], sense_a[dupm]])
+    same_r = torch.cat([same, same[keep_b], same[dupm]])
+    dist_r = torch.cat([dist, dist_b[keep_b], dist[dupm] + randint(-40, 41, nd)])
+    std_r = torch.cat([std, std_b[keep_b], torch.round((0.5 + 59.5 * rand(nd)) * 10.0) / 10.0])
+    np_r = torch.cat([npairs, npairs[keep_b], randint(10, 801, nd)])
+
+    if line_order == "shuffled":
+        line_rank = torch.randperm(V, generator=gen, device=dev)
+    elif line_order == "id":
+        line_rank = torch.arange(V, device=dev, dtype=torch.int64)
+    else:
+        raise ValueError(line_order)
+    okey = line_rank[root] * 2 + (~sense).to(torch.int64)
+    order = torch.sort(okey, stable=True).indices
+    out = dict(
+        seq_len=seq_len, astat=astat, copy_num=cn,
+        root=root[order].to(torch.int32).contiguous(), ctg=ctg[order].to(torch.int32).contiguous(),
+        dist=dist_r[order].to(torch.int32).contiguous(),
+        std_dev=std_r[order].to(torch.float32).contiguous(),
+        num_pairs=np_r[order].to(torch.int32).contiguous(),
+        flags=(sense[order].to(torch.uint8) * SENSE + same_r[order].to(torch.uint8) * SAME).contiguous(),
+        meta={"config": name, "V": V, "pairs": P, "records": int(root.shape[0]), "seed": int(s),
+              "line_order": line_order, "generator": "torch:" + str(dev)})
+    return out
+
+
+def torch_to_input(t) -> ScaffoldInput:
+    """generate_torch() result -> host ScaffoldInput (numpy)."""
+    g = lambda k, dt: t[k].detach().cpu().numpy().astype(dt, copy=False)
+    return ScaffoldInput(seq_len=g("seq_len", np.uint32), astat=g("astat", np.float32),
+                         copy_num=g("copy_num", np.float32), root=g("root", np.uint32),
+                         ctg=g("ctg", np.uint32), dist=g("dist", np.int32),
+                         std_dev=g("std_dev", np.float32), num_pairs=g("num_pairs", np.uint32),
+                         flags=g("flags", np.uint8), name=t["meta"]["config"], meta=dict(t["meta"]))

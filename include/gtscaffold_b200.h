@@ -101,6 +101,12 @@ int gtsb_device_pointers(gtsb_context *ctx, const uint32_t **row_ptr, const uint
                          const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate);
 int gtsb_get_stats(gtsb_context *ctx, gtsb_stats *stats);
 int gtsb_synchronize(gtsb_context *ctx);
+/* per-kernel device time (CUDA events on the launching stream).  set_profile
+   resets the totals; get_profile returns the number of distinct kernels and
+   fills ';'-joined names, accumulated milliseconds and launch-group counts. */
+int gtsb_set_profile(gtsb_context *ctx, int on);
+int gtsb_get_profile(gtsb_context *ctx, char *names, uint64_t names_cap, double *ms,
+                     uint32_t *calls, uint32_t cap);
 
 /* host helper: thresholds of the ambiguous-order test for a cutoff (exposed
    for tests; see csrc/gtsb_threshold.c) */
