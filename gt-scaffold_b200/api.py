@@ -32,7 +32,7 @@ EXPORTS = [
     "gtsb_set_records_device", "gtsb_set_graph_host", "gtsb_build", "gtsb_mark_repeats",
     "gtsb_filter", "gtsb_pipeline", "gtsb_nof_edges", "gtsb_get_vertex_states", "gtsb_get_csr",
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
-    "gtsb_set_profile", "gtsb_get_profile",
+    "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
 ]
 
 
@@ -40,6 +40,7 @@ class Stats(C.Structure):
     _fields_ = [("nof_vertices", C.c_uint64), ("nof_records", C.c_uint64), ("nof_edges", C.c_uint64),
                 ("max_degree", C.c_uint32), ("big_rows", C.c_uint32), ("large_buckets", C.c_uint32),
                 ("proposals", C.c_uint32), ("poly_sweeps", C.c_uint32), ("fire_rounds", C.c_uint32),
+                ("line_ordered_build", C.c_uint32), ("fallback_reason", C.c_uint32),
                 ("kernel_launches", C.c_uint64), ("ms_build", C.c_float),
                 ("ms_mark_repeats", C.c_float), ("ms_filter", C.c_float)]
 
@@ -68,6 +69,7 @@ def load_library():
     L.gtsb_error.restype = C.c_char_p
     L.gtsb_set_stream.argtypes = [vp, vp]
     L.gtsb_want_win_rec.argtypes = [vp, i32]
+    L.gtsb_force_general_build.argtypes = [vp, i32]
     for n in ("gtsb_set_vertices_host", "gtsb_set_vertices_device"):
         getattr(L, n).argtypes = [vp, u64, vp, vp, vp]
     for n in ("gtsb_set_records_host", "gtsb_set_records_device"):
@@ -106,7 +108,8 @@ def _ptr(a):
 class ScaffoldGraphB200:
     """A scaffold graph resident in B200 HBM."""
 
-    def __init__(self, device: int = 0, want_win_rec: bool = False, stream: int | None = None):
+    def __init__(self, device: int = 0, want_win_rec: bool = False, stream: int | None = None,
+                 force_general: bool = False):
         self.L = load_library()
         h = C.c_void_p()
         if self.L.gtsb_create(C.byref(h), device) != 0:
@@ -116,6 +119,8 @@ class ScaffoldGraphB200:
         self._keep = []
         if want_win_rec:
             self._ck(self.L.gtsb_want_win_rec(self.h, 1))
+        if force_general:
+            self._ck(self.L.gtsb_force_general_build(self.h, 1))
         if stream is not None:
             self._ck(self.L.gtsb_set_stream(self.h, C.c_void_p(stream)))
 
@@ -154,10 +159,11 @@ class ScaffoldGraphB200:
         self._ck(self.L.gtsb_set_graph_host(self.h, self.V, a[1].shape[0], *[_ptr(x) for x in a]))
 
     @classmethod
-    def new_from_records(cls, inp, device: int = 0, want_win_rec: bool = False):
+    def new_from_records(cls, inp, device: int = 0, want_win_rec: bool = False,
+                         force_general: bool = False):
         """Vertices + file-ordered records -> device CSR (the record loop of
         gt_scaffolder_parser_read_distances, parser.c:357-379)."""
-        g = cls(device, want_win_rec)
+        g = cls(device, want_win_rec, force_general=force_general)
         g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
         g.set_records(inp.root, inp.ctg, inp.dist, inp.std_dev, inp.flags)
         g.build()

@@ -63,12 +63,20 @@ struct gtsb_context {
 
   uint64_t V = 0, R = 0, E = 0;
   bool have_vertices = false, have_records = false, have_graph = false;
+  bool line_layout = false;     // rows in .de line order (rs/re/vid/pos) instead of plain CSR
+  bool csr_exported = false;    // plain CSR copy of a line-layout graph is current
 
   // inputs
   DevBuf vattr, astat, seq_len_in, copy_num_in;
   DevBuf root, ctg, dist, std_dev, flags;
   // graph
   DevBuf row_ptr, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
+  DevBuf rs, re, vid, pos;      // line layout
+  DevBuf ls, tile_cnt, tile_off, rf, cnt_in, bptr2, cursor2, seg_creators, seg_k, tmp_ent, tmp_dest,
+      tmp_cursor, bucket, corrections, lineless_flag, lineless_rank;
+  DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
+  uint32_t fallback_reason = 0;
+  int force_general = 0;
   // build work
   DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
       big_rows, counters, lscratch, ltag;
@@ -211,7 +219,15 @@ GraphArgs graph_args(gtsb_context *c) {
   GraphArgs g{};
   g.V = (uint32_t) c->V;
   g.sm_count = c->sm_count;
-  g.row_ptr = c->row_ptr.as<uint32_t>();
+  if (c->line_layout) {
+    g.rs = c->rs.as<uint32_t>();
+    g.re = c->re.as<uint32_t>();
+    g.vid = c->vid.as<uint32_t>();
+  } else {
+    g.rs = c->row_ptr.as<uint32_t>();
+    g.re = c->row_ptr.as<uint32_t>() + 1;
+    g.vid = nullptr;
+  }
   g.dst = c->dst.as<uint32_t>();
   g.dist = c->edist.as<int32_t>();
   g.std_dev = c->estd.as<float>();
@@ -268,12 +284,133 @@ void prof_collect(gtsb_context *c) {
   c->prof.recs.clear();
 }
 
+int ensure_rows(gtsb_context *c, uint64_t R) {
+  ENSURE(c->dst, 2 * R * 4);
+  ENSURE(c->edist, 2 * R * 4);
+  ENSURE(c->estd, 2 * R * 4);
+  ENSURE(c->eflags, 2 * R);
+  ENSURE(c->eid, 2 * R * 4);
+  ENSURE(c->estate, 2 * R);
+  return 0;
+}
+
+// The line-ordered fast path (gtsb_build2.cu).  Returns 1 if the input is
+// outside its preconditions (caller runs the general path), 0 on success.
+int do_build_lines(gtsb_context *c) {
+  const uint64_t V = c->V, R = c->R;
+  cudaStream_t s = c->stream;
+  const uint32_t nseg = (uint32_t) ((V + SEG_LINES - 1) / SEG_LINES);
+  const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
+  ENSURE(c->pos, (V + 1) * 4);
+  ENSURE(c->vid, (V + 1) * 4);
+  ENSURE(c->ls, (V + 2) * 4);
+  ENSURE(c->rs, (V + 1) * 4);
+  ENSURE(c->re, (V + 1) * 4);
+  ENSURE(c->tile_cnt, (ntiles + 2) * 4);
+  ENSURE(c->tile_off, (ntiles + 2) * 4);
+  ENSURE(c->rf, R);
+  ENSURE(c->cnt_in, (V + 2) * 4);
+  ENSURE(c->bptr2, (V + 2) * 4);
+  ENSURE(c->cursor2, (V + 2) * 4);
+  ENSURE(c->seg_creators, (nseg + 2) * 4);
+  ENSURE(c->seg_k, (nseg + 2) * 4);
+  ENSURE(c->tmp_ent, R * sizeof(uint4));
+  ENSURE(c->tmp_dest, R * 4);
+  ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
+  ENSURE(c->bucket, R * sizeof(uint4));
+  const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
+  ENSURE(c->corrections, (size_t) corr_cap * sizeof(uint4));
+  ENSURE(c->lineless_flag, V + 1);
+  ENSURE(c->lineless_rank, (V + 2) * 4);
+  const uint64_t scan_n = V > R ? V : R;
+  ENSURE(c->scan_scratch, scan_scratch_elems(scan_n) * 4);
+  ENSURE(c->big_rows, (V + 1) * 4);
+  if (ensure_rows(c, R) != 0) return -1;
+
+  CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
+  CK(cudaMemsetAsync(c->pos.p, 0xFF, (V + 1) * 4, s));
+  CK(cudaMemsetAsync(c->cnt_in.p, 0, (V + 2) * 4, s));
+  CK(cudaMemsetAsync(c->cursor2.p, 0, (V + 2) * 4, s));
+  CK(cudaMemsetAsync(c->estate.p, 0, 2 * R ? 2 * R : 1, s));   // GIS_UNVISITED, graph.c:162
+  CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, s));
+
+  Build2Args a{};
+  a.R = R;
+  a.V = (uint32_t) V;
+  a.sm_count = c->sm_count;
+  uint32_t shift = 0;
+  while (((V ? V - 1 : 0) >> shift) >= (uint64_t) NB_COARSE) shift++;
+  a.coarse_shift = shift;
+  a.corrections_cap = corr_cap;
+  a.root = c->root.as<uint32_t>();
+  a.ctg = c->ctg.as<uint32_t>();
+  a.dist = c->dist.as<int32_t>();
+  a.std_dev = c->std_dev.as<float>();
+  a.flags = c->flags.as<uint8_t>();
+  a.pos = c->pos.as<uint32_t>();
+  a.vid = c->vid.as<uint32_t>();
+  a.ls = c->ls.as<uint32_t>();
+  a.tile_cnt = c->tile_cnt.as<uint32_t>();
+  a.tile_off = c->tile_off.as<uint32_t>();
+  a.rf = c->rf.as<uint8_t>();
+  a.cnt_in = c->cnt_in.as<uint32_t>();
+  a.bptr = c->bptr2.as<uint32_t>();
+  a.cursor = c->cursor2.as<uint32_t>();
+  a.seg_creators = c->seg_creators.as<uint32_t>();
+  a.seg_k = c->seg_k.as<uint32_t>();
+  a.tmp_ent = c->tmp_ent.as<uint4>();
+  a.bucket = c->bucket.as<uint4>();
+  a.corrections = c->corrections.as<uint4>();
+  a.tmp_dest = c->tmp_dest.as<uint32_t>();
+  a.tmp_cursor = c->tmp_cursor.as<uint32_t>();
+  a.lineless_flag = c->lineless_flag.as<uint8_t>();
+  a.lineless_rank = c->lineless_rank.as<uint32_t>();
+  a.scan_scratch = c->scan_scratch.as<uint32_t>();
+  a.counters = c->counters.as<uint32_t>();
+  a.big_rows = c->big_rows.as<uint32_t>();
+  a.rs = c->rs.as<uint32_t>();
+  a.re = c->re.as<uint32_t>();
+  a.dst = c->dst.as<uint32_t>();
+  a.eid = c->eid.as<uint32_t>();
+  a.edist = c->edist.as<int32_t>();
+  a.estd = c->estd.as<float>();
+  a.eflags = c->eflags.as<uint8_t>();
+
+  c->stats.kernel_launches += launch_build2_lines(a, s);
+  c->stats.kernel_launches += launch_build2_rows(a, s);
+  if (read_counters(c) != 0) return -1;
+  if (c->h_counters[CNT_ERROR] & 1u) return fail(c, "gtsb_build: a record names a vertex id >= nof_vertices");
+  if (c->h_counters[CNT_ERROR] & 2u)
+    return fail(c, "gtsb_build: self link (root == ctg) is not supported (the reference would "
+                   "create two parallel self edges, parser.c:374-377)");
+  c->fallback_reason = c->h_counters[CNT_FALLBACK];
+  if (c->fallback_reason) return 1;
+  c->E = c->h_counters[CNT_EDGES];
+  c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
+  c->max_deg = c->h_counters[CNT_MAX_DEG];
+  c->stats.nof_edges = c->E;
+  c->stats.big_rows = c->n_big_rows;
+  c->stats.max_degree = c->max_deg;
+  c->stats.large_buckets = 0;
+  c->line_layout = true;
+  c->csr_exported = false;
+  c->have_graph = true;
+  return 0;
+}
+
 int do_build(gtsb_context *c) {
   ProfScope ps_(c);
   if (!c->have_vertices || !c->have_records) return fail(c, "gtsb_build: vertices and records must be set first");
   const uint64_t V = c->V, R = c->R;
   if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records");
   cudaStream_t s = c->stream;
+  c->fallback_reason = 0;
+  if (!c->want_win && !c->force_general && R > 0 && V > 0) {
+    const int rc = do_build_lines(c);
+    if (rc <= 0) return rc;
+  }
+  c->line_layout = false;
+  c->csr_exported = false;
 
   ENSURE(c->cnt, (V + 1) * 4);
   ENSURE(c->bptr, (V + 1) * 4);
@@ -372,6 +509,7 @@ int do_build(gtsb_context *c) {
 int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_mark_repeats: no graph (call gtsb_build or gtsb_set_graph_host)");
+  c->csr_exported = false;
   launch_mark_repeats(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
   c->stats.kernel_launches += c->V ? 2 : 0;
   CK(cudaGetLastError());
@@ -382,6 +520,7 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
   if (get_ambig(c, pcutoff) != 0) return -1;
+  c->csr_exported = false;
   const uint64_t V = c->V, E = c->E;
   cudaStream_t s = c->stream;
   ENSURE(c->proposals, (E + 1) * sizeof(uint2));
@@ -461,6 +600,43 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
   return 0;
 }
 
+// plain CSR (vertex order) copy of a line-layout graph, made on demand
+int export_csr(gtsb_context *c) {
+  if (!c->line_layout || c->csr_exported) return 0;
+  const uint64_t V = c->V, E = c->E;
+  ENSURE(c->x_row_ptr, (V + 2) * 4);
+  ENSURE(c->x_deg, (V + 2) * 4);
+  ENSURE(c->x_dst, (E + 1) * 4);
+  ENSURE(c->x_dist, (E + 1) * 4);
+  ENSURE(c->x_std, (E + 1) * 4);
+  ENSURE(c->x_flags, E + 1);
+  ENSURE(c->x_eid, (E + 1) * 4);
+  ENSURE(c->x_estate, E + 1);
+  ENSURE(c->scan_scratch, scan_scratch_elems(V > c->R ? V : c->R) * 4);
+  ExportArgs x{};
+  x.V = (uint32_t) V;
+  x.pos = c->pos.as<uint32_t>();
+  x.rs = c->rs.as<uint32_t>();
+  x.re = c->re.as<uint32_t>();
+  x.dst = c->dst.as<uint32_t>();
+  x.eid = c->eid.as<uint32_t>();
+  x.dist = c->edist.as<int32_t>();
+  x.std_dev = c->estd.as<float>();
+  x.flags = c->eflags.as<uint8_t>();
+  x.estate = c->estate.as<uint8_t>();
+  x.row_ptr = c->x_row_ptr.as<uint32_t>();
+  x.dst_o = c->x_dst.as<uint32_t>();
+  x.eid_o = c->x_eid.as<uint32_t>();
+  x.dist_o = c->x_dist.as<int32_t>();
+  x.std_o = c->x_std.as<float>();
+  x.flags_o = c->x_flags.as<uint8_t>();
+  x.estate_o = c->x_estate.as<uint8_t>();
+  c->stats.kernel_launches += launch_export_csr(x, c->x_deg.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), c->stream);
+  CK(cudaGetLastError());
+  c->csr_exported = true;
+  return 0;
+}
+
 }  // namespace
 
 // =============================================================== C ABI
@@ -503,7 +679,11 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
                     &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
-                    &c->work_a, &c->work_b, &c->big_scratch};
+                    &c->work_a, &c->work_b, &c->big_scratch, &c->rs, &c->re, &c->vid, &c->pos, &c->ls,
+                    &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
+                    &c->seg_creators, &c->seg_k, &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
+                    &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
+                    &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg};
   for (DevBuf *b : bufs) release(*b);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (Timer *t : {&c->t_build, &c->t_rep, &c->t_filter}) {
@@ -523,6 +703,12 @@ int gtsb_set_stream(gtsb_context *c, void *stream) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = static_cast<cudaStream_t>(stream);
   c->own_stream = false;
+  return 0;
+}
+
+int gtsb_force_general_build(gtsb_context *c, int on) {
+  if (c == nullptr) return -1;
+  c->force_general = on;
   return 0;
 }
 
@@ -637,6 +823,8 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
   c->E = E;
   c->R = 0;
   c->have_graph = true;
+  c->line_layout = false;
+  c->csr_exported = false;
   c->stats.nof_edges = E;
   c->stats.big_rows = c->n_big_rows;
   c->stats.max_degree = c->max_deg;
@@ -694,21 +882,23 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const uint64_t V = c->V, E = c->E;
-  if (row_ptr) CK(cudaMemcpyAsync(row_ptr, c->row_ptr.p, (V + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (export_csr(c) != 0) return -1;
+  const bool ll = c->line_layout;
+  if (row_ptr) CK(cudaMemcpyAsync(row_ptr, ll ? c->x_row_ptr.p : c->row_ptr.p, (V + 1) * 4, cudaMemcpyDeviceToHost, s));
   if (E) {
-    if (dst) CK(cudaMemcpyAsync(dst, c->dst.p, E * 4, cudaMemcpyDeviceToHost, s));
-    if (dist) CK(cudaMemcpyAsync(dist, c->edist.p, E * 4, cudaMemcpyDeviceToHost, s));
-    if (std_dev) CK(cudaMemcpyAsync(std_dev, c->estd.p, E * 4, cudaMemcpyDeviceToHost, s));
-    if (flags) CK(cudaMemcpyAsync(flags, c->eflags.p, E, cudaMemcpyDeviceToHost, s));
+    if (dst) CK(cudaMemcpyAsync(dst, ll ? c->x_dst.p : c->dst.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (dist) CK(cudaMemcpyAsync(dist, ll ? c->x_dist.p : c->edist.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (std_dev) CK(cudaMemcpyAsync(std_dev, ll ? c->x_std.p : c->estd.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (flags) CK(cudaMemcpyAsync(flags, ll ? c->x_flags.p : c->eflags.p, E, cudaMemcpyDeviceToHost, s));
     if (eid) {
       if (c->eid.p == nullptr) return fail(c, "gtsb_get_csr: this graph has no eid (not built here)");
-      CK(cudaMemcpyAsync(eid, c->eid.p, E * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(eid, ll ? c->x_eid.p : c->eid.p, E * 4, cudaMemcpyDeviceToHost, s));
     }
     if (win_rec) {
       if (!c->want_win || c->win_rec.p == nullptr) return fail(c, "gtsb_get_csr: win_rec was not requested before gtsb_build");
       CK(cudaMemcpyAsync(win_rec, c->win_rec.p, E * 4, cudaMemcpyDeviceToHost, s));
     }
-    if (estate) CK(cudaMemcpyAsync(estate, c->estate.p, E, cudaMemcpyDeviceToHost, s));
+    if (estate) CK(cudaMemcpyAsync(estate, ll ? c->x_estate.p : c->estate.p, E, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
   return 0;
@@ -717,10 +907,13 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
 int gtsb_device_pointers(gtsb_context *c, const uint32_t **row_ptr, const uint32_t **dst,
                          const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate) {
   if (c == nullptr) return -1;
-  if (row_ptr) *row_ptr = c->row_ptr.as<uint32_t>();
-  if (dst) *dst = c->dst.as<uint32_t>();
-  if (eid) *eid = c->eid.as<uint32_t>();
-  if (estate) *estate = c->estate.as<uint8_t>();
+  CK(cudaSetDevice(c->device));
+  if (export_csr(c) != 0) return -1;
+  const bool ll = c->line_layout;
+  if (row_ptr) *row_ptr = ll ? c->x_row_ptr.as<uint32_t>() : c->row_ptr.as<uint32_t>();
+  if (dst) *dst = ll ? c->x_dst.as<uint32_t>() : c->dst.as<uint32_t>();
+  if (eid) *eid = ll ? c->x_eid.as<uint32_t>() : c->eid.as<uint32_t>();
+  if (estate) *estate = ll ? c->x_estate.as<uint8_t>() : c->estate.as<uint8_t>();
   if (vstate) *vstate = c->vstate.as<uint8_t>();
   return 0;
 }
@@ -728,6 +921,8 @@ int gtsb_device_pointers(gtsb_context *c, const uint32_t **row_ptr, const uint32
 int gtsb_get_stats(gtsb_context *c, gtsb_stats *st) {
   if (c == nullptr || st == nullptr) return -1;
   c->stats.nof_vertices = c->V;
+  c->stats.line_ordered_build = c->line_layout ? 1u : 0u;
+  c->stats.fallback_reason = c->fallback_reason;
   *st = c->stats;
   return 0;
 }

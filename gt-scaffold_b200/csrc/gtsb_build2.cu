@@ -1,0 +1,541 @@
+// gtsb_build2.cu -- line-ordered CSR build (the fast path of gtsb_build).
+//
+// Same construction semantics as gtsb_build.cu (reference
+// gt_scaffolder_parser.c:357-379, gt_scaffolder_graph.c:137-184, 219-235), but
+// organised around what a .de file is: one LINE per root contig, each link
+// normally listed on both contigs' lines.  Measured B200 primitives
+// (profiles/r01_microbench_mem.txt) forbid per-record random DRAM traffic
+// (42 G sectors/s random vs 6.2 TB/s streaming), so every pass streams and the
+// only data that has to cross between lines goes through a two-level counting
+// sort whose second level is L2-local:
+//
+//   positions   p = index of a vertex's line in file order (vertices without a
+//               line follow in id order); every array of this build is laid out
+//               by position, so line p, its mailbox and its CSR row all stream.
+//   "up" record (root r -> ctg c) with pos[r] < pos[c]: the first such record of
+//               a line is the CREATOR of the pair (no earlier record can exist:
+//               c's line comes later), edge ids 2k / 2k+1 with k = its rank
+//               among creators in file order.  It mails {k, seed attributes,
+//               final flags of r->c} to c's mailbox.
+//   "down" record (pos[c] < pos[r]): competes for edge r->c against the twin seed
+//               found in r's mailbox (strict std_dev maximum, parser.c:362).
+//   row of p    = [twin-created slots, by k] ++ [own creators, in line order]
+//               = adjacency (creation) order, graph.c:166-167.
+//   reverse flags of an up slot are the twin seed's unless c's own records beat
+//               the seed with different flags; the down side detects that and
+//               posts a correction (rare), applied by a fix-up kernel.
+//
+// Anything outside the fast path's preconditions -- a root on several lines, a
+// link listed only on the LATER line, very long lines, oversized segments --
+// raises a flag and gtsb_build reruns the general path of gtsb_build.cu.
+#include "gtsb_common.cuh"
+#include "gtsb_scan.cuh"
+#include "gtsb_kernels.h"
+
+namespace gtsb {
+
+constexpr uint32_t UNSET = 0xFFFFFFFFu;
+constexpr int HEAD_TILE = 4096;             // records per block in the head passes
+constexpr uint32_t RF_UP = 1, RF_FIRST = 2; // per-record flag byte
+
+// mailbox entry (uint4): x = k of the creator, y = src vertex | M_* bits,
+// z = seed dist, w = seed std_dev
+constexpr uint32_t M_SEED_SENSE = 1u << 27, M_SEED_SAME = 1u << 28;
+constexpr uint32_t M_FWD_SENSE = 1u << 29, M_FWD_SAME = 1u << 30;
+
+__device__ __forceinline__ void raise(uint32_t *counters, uint32_t why) {
+  atomicOr(&counters[CNT_FALLBACK], why);
+}
+
+// block-uniform "an earlier kernel gave up" test (safe before __syncthreads)
+__device__ __forceinline__ bool block_abort(const uint32_t *counters) {
+  __shared__ uint32_t s_abort;
+  if (threadIdx.x == 0) s_abort = counters[CNT_FALLBACK] | counters[CNT_ERROR];
+  __syncthreads();
+  return s_abort != 0;
+}
+
+// ------------------------------------------------------------------ lines
+
+__global__ void __launch_bounds__(256) k2_head_counts(uint64_t R, const uint32_t *__restrict__ root,
+                                                       uint32_t *__restrict__ tile_cnt) {
+  const uint64_t base = (uint64_t) blockIdx.x * HEAD_TILE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < HEAD_TILE / 256; k++) {
+    const uint64_t i = base + (uint64_t) k * 256 + threadIdx.x;
+    if (i < R) c += (i == 0 || root[i] != root[i - 1]) ? 1u : 0u;
+  }
+  uint32_t total;
+  block_excl_scan(c, &total);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V,
+                                                      const uint32_t *__restrict__ root,
+                                                      const uint32_t *__restrict__ tile_off,
+                                                      uint32_t *__restrict__ ls, uint32_t *__restrict__ vid,
+                                                      uint32_t *__restrict__ pos,
+                                                      uint32_t *__restrict__ counters) {
+  constexpr int ITEMS = HEAD_TILE / 256;
+  const uint64_t base = (uint64_t) blockIdx.x * HEAD_TILE + (uint64_t) threadIdx.x * ITEMS;
+  uint32_t heads = 0, c = 0;
+  uint32_t prev = (base > 0 && base <= R) ? root[base - 1] : UNSET;
+  uint32_t mine[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint64_t i = base + k;
+    mine[k] = i < R ? root[i] : UNSET;
+    if (i < R && (i == 0 || mine[k] != prev)) {
+      heads |= 1u << k;
+      c++;
+    }
+    prev = mine[k];
+  }
+  uint32_t total;
+  uint32_t l = tile_off[blockIdx.x] + block_excl_scan(c, &total);
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    if (!((heads >> k) & 1u)) continue;
+    const uint32_t r = mine[k];
+    if (r >= V) {
+      atomicOr(&counters[CNT_ERROR], 1u);
+    } else if (l < V) {
+      ls[l] = (uint32_t) (base + k);
+      vid[l] = r;
+      if (atomicExch(&pos[r], l) != UNSET) raise(counters, FB_MULTIRUN);
+    } else {
+      raise(counters, FB_MULTIRUN);     // more lines than vertices
+    }
+    l++;
+  }
+}
+
+__global__ void __launch_bounds__(256) k2_lineless_flags(uint32_t V, const uint32_t *__restrict__ pos,
+                                                          uint8_t *__restrict__ flag) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) flag[v] = pos[v] == UNSET ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k2_lineless_assign(uint32_t V, uint64_t R,
+                                                           const uint32_t *__restrict__ nlines,
+                                                           const uint8_t *__restrict__ flag,
+                                                           const uint32_t *__restrict__ rank,
+                                                           uint32_t *__restrict__ pos, uint32_t *__restrict__ vid,
+                                                           uint32_t *__restrict__ ls,
+                                                           const uint32_t *__restrict__ counters) {
+  if (counters[CNT_FALLBACK] | counters[CNT_ERROR]) return;
+  const uint32_t L = *nlines;
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > V) return;
+  if (v >= L) ls[v] = (uint32_t) R;                  // positions without records (and ls[V])
+  if (v < V && flag[v]) {
+    const uint32_t p = L + rank[v];
+    if (p < V) {
+      pos[v] = p;
+      vid[p] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ segments
+
+struct Seg {
+  uint32_t p0, nlines, rec0, n;
+};
+
+// load the segment's line starts; false (block-uniform) if it cannot be staged
+__device__ __forceinline__ bool seg_open(const Build2Args &a, uint32_t s, Seg &g, uint32_t *s_ls) {
+  g.p0 = s * SEG_LINES;
+  g.nlines = min((uint32_t) SEG_LINES, a.V - g.p0);
+  for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) s_ls[j] = a.ls[g.p0 + j];
+  __syncthreads();
+  g.rec0 = s_ls[0];
+  g.n = s_ls[g.nlines] - g.rec0;
+  if (g.n > SEG_REC_CAP) {
+    if (threadIdx.x == 0) raise(a.counters, FB_SEGMENT);
+    return false;
+  }
+  return true;
+}
+
+// s_line[r] = line (within the segment) of staged record r
+__device__ __forceinline__ void seg_lines(const Build2Args &a, const Seg &g, const uint32_t *s_ls,
+                                          uint8_t *s_line) {
+  for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) {
+    const uint32_t b = s_ls[j] - g.rec0, e = s_ls[j + 1] - g.rec0;
+    if (e - b > MAX_LINE_RECS) raise(a.counters, FB_LONGLINE);
+    for (uint32_t r = b; r < e; r++) s_line[r] = (uint8_t) j;
+  }
+}
+
+// pass C: classify every record (up / first of its neighbour in the line),
+// count creators per segment and mail per destination position
+__global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (block_abort(a.counters)) return;
+  uint32_t *s_ls = reinterpret_cast<uint32_t *>(smem);
+  uint32_t *s_ctg = s_ls + SEG_LINES + 4;
+  uint8_t *s_line = reinterpret_cast<uint8_t *>(s_ctg + SEG_REC_CAP);
+  Seg g;
+  const bool ok = seg_open(a, blockIdx.x, g, s_ls);
+  uint32_t creators = 0;
+  if (ok) {
+    seg_lines(a, g, s_ls, s_line);
+    for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) s_ctg[r] = a.ctg[g.rec0 + r];
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
+      const uint32_t j = s_line[r], c = s_ctg[r];
+      const uint32_t p = g.p0 + j;
+      uint8_t rf = 0;
+      if (c >= a.V) {
+        atomicOr(&a.counters[CNT_ERROR], 1u);
+      } else if (c == a.vid[p]) {
+        atomicOr(&a.counters[CNT_ERROR], 2u);
+      } else {
+        const uint32_t pc = a.pos[c];
+        bool first = true;
+        for (uint32_t t = s_ls[j] - g.rec0; t < r; t++) first &= s_ctg[t] != c;
+        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u));
+        if (rf == (RF_UP | RF_FIRST)) {
+          atomicAdd(&a.cnt_in[pc], 1u);
+          creators++;
+        }
+      }
+      a.rf[g.rec0 + r] = rf;
+    }
+  }
+  uint32_t total;
+  block_excl_scan(creators, &total);
+  if (threadIdx.x == 0) a.seg_creators[blockIdx.x] = total;
+}
+
+__global__ void k2_init_cursors(Build2Args a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > NB_COARSE) return;
+  const uint64_t p = (uint64_t) b << a.coarse_shift;
+  a.tmp_cursor[b] = a.bptr[p < a.V ? p : a.V];
+}
+
+// pass D-A: creators build their mailbox entry and drop it into the coarse bin
+// of the destination position (bins are contiguous ranges of the final mailbox
+// array, so bin b starts at bptr[b << shift])
+__global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (block_abort(a.counters)) return;
+  uint32_t *s_ls = reinterpret_cast<uint32_t *>(smem);
+  uint32_t *s_ctg = s_ls + SEG_LINES + 4;
+  uint32_t *s_pc = s_ctg + SEG_REC_CAP;
+  float *s_std = reinterpret_cast<float *>(s_pc + SEG_REC_CAP);
+  uint32_t *s_bin = reinterpret_cast<uint32_t *>(s_std + SEG_REC_CAP);   // [3][NB_COARSE]
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_bin + 3 * NB_COARSE);
+  uint8_t *s_rf = s_fl + SEG_REC_CAP;
+  uint8_t *s_line = s_rf + SEG_REC_CAP;
+  Seg g;
+  if (!seg_open(a, blockIdx.x, g, s_ls)) return;
+  seg_lines(a, g, s_ls, s_line);
+  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
+    s_ctg[r] = a.ctg[g.rec0 + r];
+    s_std[r] = a.std_dev[g.rec0 + r];
+    s_fl[r] = a.flags[g.rec0 + r];
+    s_rf[r] = a.rf[g.rec0 + r];
+  }
+  for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
+  __syncthreads();
+  // creators: destination position and bin histogram
+  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
+    if (s_rf[r] != (RF_UP | RF_FIRST)) continue;
+    const uint32_t pc = a.pos[s_ctg[r]];
+    s_pc[r] = pc;
+    atomicAdd(&s_bin[pc >> a.coarse_shift], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
+    if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
+  // creator ranks in record order: blocked chunks + block scan
+  const uint32_t chunk = (g.n + blockDim.x - 1) / blockDim.x;
+  const uint32_t r0 = min(g.n, threadIdx.x * chunk), r1 = min(g.n, r0 + chunk);
+  uint32_t mine = 0;
+  for (uint32_t r = r0; r < r1; r++) mine += s_rf[r] == (RF_UP | RF_FIRST);
+  uint32_t total;
+  uint32_t k = a.seg_k[blockIdx.x] + block_excl_scan(mine, &total);   // syncs: bin bases visible
+  for (uint32_t r = r0; r < r1; r++) {
+    if (s_rf[r] != (RF_UP | RF_FIRST)) continue;
+    const uint32_t j = s_line[r], c = s_ctg[r];
+    // final flags of edge root->c: strict running maximum over the line's records
+    float best = s_std[r];
+    uint32_t bf = s_fl[r];
+    for (uint32_t t = r + 1; t < s_ls[j + 1] - g.rec0; t++)
+      if (s_ctg[t] == c && best < s_std[t]) {
+        best = s_std[t];
+        bf = s_fl[t];
+      }
+    const uint32_t sf = s_fl[r];
+    uint4 e;
+    e.x = k++;
+    e.y = a.vid[g.p0 + j] | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
+          ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u);
+    e.z = (uint32_t) a.dist[g.rec0 + r];
+    e.w = __float_as_uint(s_std[r]);
+    const uint32_t pc = s_pc[r], b = pc >> a.coarse_shift;
+    const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
+    a.tmp_ent[at] = e;
+    a.tmp_dest[at] = pc;
+  }
+}
+
+// pass D-B: stream the coarsely sorted entries into their mailboxes; the
+// targets of concurrently running blocks stay inside one or two coarse bins
+__global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
+  if (a.counters[CNT_FALLBACK] | a.counters[CNT_ERROR]) return;
+  const uint32_t n = a.bptr[a.V];
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t pc = a.tmp_dest[e];
+    a.bucket[a.bptr[pc] + atomicAdd(&a.cursor[pc], 1u)] = a.tmp_ent[e];
+  }
+}
+
+// pass R: one thread per line resolves the line's records against its mailbox
+// and writes the CSR row
+__global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (block_abort(a.counters)) return;
+  uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
+  uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + SEG_ENT_CAP);
+  uint32_t *s_bp = s_ls + SEG_LINES + 4;
+  uint32_t *s_ctg = s_bp + SEG_LINES + 4;
+  int32_t *s_dist = reinterpret_cast<int32_t *>(s_ctg + SEG_REC_CAP);
+  float *s_std = reinterpret_cast<float *>(s_dist + SEG_REC_CAP);
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_std + SEG_REC_CAP);
+  uint8_t *s_rf = s_fl + SEG_REC_CAP;
+  Seg g;
+  if (!seg_open(a, blockIdx.x, g, s_ls)) return;
+  for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) s_bp[j] = a.bptr[g.p0 + j];
+  __syncthreads();
+  const uint32_t ent0 = s_bp[0], nent = s_bp[g.nlines] - ent0;
+  if (nent > SEG_ENT_CAP) {
+    if (threadIdx.x == 0) raise(a.counters, FB_SEGMENT);
+    return;
+  }
+  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
+    s_ctg[r] = a.ctg[g.rec0 + r];
+    s_dist[r] = a.dist[g.rec0 + r];
+    s_std[r] = a.std_dev[g.rec0 + r];
+    s_fl[r] = a.flags[g.rec0 + r];
+    s_rf[r] = a.rf[g.rec0 + r];
+  }
+  for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) s_ent[e] = a.bucket[ent0 + e];
+  __syncthreads();
+
+  const uint32_t j = threadIdx.x;
+  uint32_t ra = 0, rb = 0, ea = 0, eb = 0, nown = 0;
+  if (j < g.nlines) {
+    ra = s_ls[j] - g.rec0;
+    rb = s_ls[j + 1] - g.rec0;
+    ea = s_bp[j] - ent0;
+    eb = s_bp[j + 1] - ent0;
+    for (uint32_t t = ra; t < rb; t++) {
+      const uint32_t rf = s_rf[t];
+      if (rf == (RF_UP | RF_FIRST)) nown++;
+      if (rf == RF_FIRST) {                       // down: the creator's mail must be here
+        bool found = false;
+        for (uint32_t e = ea; e < eb; e++) found |= (s_ent[e].y & E_OTHER_MASK) == s_ctg[t];
+        if (!found) raise(a.counters, FB_DOWN_ORPHAN);
+      }
+    }
+  }
+  const uint32_t deg = (eb - ea) + nown;
+  uint32_t total;
+  const uint32_t ex = block_excl_scan(deg | (nown << 16), &total);
+  if (j >= g.nlines) return;
+  const uint32_t p = g.p0 + j, v = a.vid[p];
+  const uint32_t row0 = g.rec0 + ent0 + (ex & 0xFFFFu);    // capacity prefix: own records + mail
+  a.rs[p] = row0;
+  a.re[p] = row0 + deg;
+  if (j == 0) atomicAdd(&a.counters[CNT_EDGES], total & 0xFFFFu);
+  if (deg > BIG_ROW) {
+    atomicMax(&a.counters[CNT_MAX_DEG], deg);
+    a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
+  }
+  // twin-created slots, ordered by the creator's k
+  for (uint32_t e = ea; e < eb; e++) {
+    const uint4 m = s_ent[e];
+    const uint32_t u = m.y & E_OTHER_MASK;
+    uint32_t rank = 0;
+    for (uint32_t e2 = ea; e2 < eb; e2++) rank += s_ent[e2].x < m.x;
+    const bool seed_same = (m.y & M_SEED_SAME) != 0;
+    const bool seed_sense = twin_dir((m.y & M_SEED_SENSE) != 0, seed_same);   // parser.c:369-372
+    float best = __uint_as_float(m.w);
+    int32_t bdist = (int32_t) m.z;
+    uint32_t bf = (seed_sense ? F_SENSE : 0u) | (seed_same ? F_SAME : 0u);
+    for (uint32_t t = ra; t < rb; t++)
+      if (s_ctg[t] == u && best < s_std[t]) {                                  // parser.c:362
+        best = s_std[t];
+        bdist = s_dist[t];
+        bf = s_fl[t] & (F_SENSE | F_SAME);
+      }
+    const uint32_t slot = row0 + rank;
+    a.dst[slot] = u;
+    a.edist[slot] = bdist;
+    a.estd[slot] = best;
+    a.eflags[slot] = (uint8_t) (bf | ((m.y & M_FWD_SENSE) ? F_RSENSE : 0u) | ((m.y & M_FWD_SAME) ? F_RSAME : 0u));
+    a.eid[slot] = 2u * m.x + 1u;
+    if (bf != ((seed_sense ? F_SENSE : 0u) | (seed_same ? F_SAME : 0u))) {
+      // the creator assumed its twin keeps the seed's flags: tell it otherwise
+      const uint32_t at = atomicAdd(&a.counters[CNT_CORRECTIONS], 1u);
+      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, v, bf, 0u);
+      else raise(a.counters, FB_SEGMENT);
+    }
+  }
+  // own creators in line order
+  uint32_t q = 0;
+  const uint32_t k0 = a.seg_k[blockIdx.x] + (ex >> 16);
+  for (uint32_t t = ra; t < rb; t++) {
+    if (s_rf[t] != (RF_UP | RF_FIRST)) continue;
+    const uint32_t c = s_ctg[t];
+    float best = s_std[t];
+    int32_t bdist = s_dist[t];
+    uint32_t bf = s_fl[t] & (F_SENSE | F_SAME);
+    for (uint32_t t2 = t + 1; t2 < rb; t2++)
+      if (s_ctg[t2] == c && best < s_std[t2]) {
+        best = s_std[t2];
+        bdist = s_dist[t2];
+        bf = s_fl[t2] & (F_SENSE | F_SAME);
+      }
+    const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
+    const uint32_t slot = row0 + (eb - ea) + q;
+    a.dst[slot] = c;
+    a.edist[slot] = bdist;
+    a.estd[slot] = best;
+    a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u));
+    a.eid[slot] = 2u * (k0 + q);
+    q++;
+  }
+}
+
+// fix-up: reverse flags of creator-side slots whose twin did not keep the seed
+__global__ void __launch_bounds__(128) k2_corrections(Build2Args a) {
+  if (a.counters[CNT_FALLBACK] | a.counters[CNT_ERROR]) return;
+  const uint32_t n = min(a.counters[CNT_CORRECTIONS], a.corrections_cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 c = a.corrections[i];
+    const uint32_t p = a.pos[c.x];
+    for (uint32_t s = a.rs[p]; s < a.re[p]; s++)
+      if (a.dst[s] == c.y)
+        a.eflags[s] = (uint8_t) ((a.eflags[s] & (F_SENSE | F_SAME)) | ((c.z & F_SENSE) ? F_RSENSE : 0u) |
+                                 ((c.z & F_SAME) ? F_RSAME : 0u));
+  }
+}
+
+// ------------------------------------------------------------------ export to plain CSR
+
+__global__ void __launch_bounds__(256) k2_export_deg(uint32_t V, const uint32_t *__restrict__ pos,
+                                                      const uint32_t *__restrict__ rs,
+                                                      const uint32_t *__restrict__ re,
+                                                      uint32_t *__restrict__ deg) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) deg[v] = re[pos[v]] - rs[pos[v]];
+}
+
+__global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t from = 0, to = 0, d = 0;
+  if (v < x.V) {
+    const uint32_t p = x.pos[v];
+    from = x.rs[p];
+    d = x.re[p] - from;
+    to = x.row_ptr[v];
+  }
+  const bool big = d > BIG_ROW;
+  if (!big)
+    for (uint32_t k = 0; k < d; k++) {
+      x.dst_o[to + k] = x.dst[from + k];
+      x.dist_o[to + k] = x.dist[from + k];
+      x.std_o[to + k] = x.std_dev[from + k];
+      x.flags_o[to + k] = x.flags[from + k];
+      x.eid_o[to + k] = x.eid[from + k];
+      x.estate_o[to + k] = x.estate[from + k];
+    }
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int l = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t ff = __shfl_sync(0xffffffffu, from, l), tt = __shfl_sync(0xffffffffu, to, l),
+                   dd = __shfl_sync(0xffffffffu, d, l);
+    for (uint32_t k = lane_id(); k < dd; k += 32) {
+      x.dst_o[tt + k] = x.dst[ff + k];
+      x.dist_o[tt + k] = x.dist[ff + k];
+      x.std_o[tt + k] = x.std_dev[ff + k];
+      x.flags_o[tt + k] = x.flags[ff + k];
+      x.eid_o[tt + k] = x.eid[ff + k];
+      x.estate_o[tt + k] = x.estate[ff + k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host driver
+
+size_t build2_smem_classify() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
+size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 3 * NB_COARSE * 4 + 16; }
+size_t build2_smem_resolve() { return SEG_ENT_CAP * 16 + 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 14 + 16; }
+
+int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
+  const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
+  {
+    KernelTimer t_("k2_heads(2 kernels+scan)", s);
+    k2_head_counts<<<ntiles, 256, 0, s>>>(a.R, a.root, a.tile_cnt);
+    exclusive_scan<uint32_t>(a.tile_cnt, ntiles, a.tile_off, a.scan_scratch, s);
+    k2_head_write<<<ntiles, 256, 0, s>>>(a.R, a.V, a.root, a.tile_off, a.ls, a.vid, a.pos, a.counters);
+  }
+  KernelTimer t_("k2_lineless(2 kernels+scan)", s);
+  const uint32_t vb = (a.V + 256) / 256;
+  k2_lineless_flags<<<vb, 256, 0, s>>>(a.V, a.pos, a.lineless_flag);
+  exclusive_scan<uint8_t>(a.lineless_flag, a.V, a.lineless_rank, a.scan_scratch, s);
+  k2_lineless_assign<<<vb, 256, 0, s>>>(a.V, a.R, a.tile_off + ntiles, a.lineless_flag, a.lineless_rank,
+                                        a.pos, a.vid, a.ls, a.counters);
+  return 2 + 3 + 2 + 3;
+}
+
+int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k2_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_classify());
+    cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
+    cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
+    attr_done = true;
+  }
+  const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  {
+    KernelTimer t_("k2_classify", s);
+    k2_classify<<<nseg, SEG_THREADS, build2_smem_classify(), s>>>(a);
+  }
+  exclusive_scan<uint32_t>(a.cnt_in, a.V, a.bptr, a.scan_scratch, s);
+  exclusive_scan<uint32_t>(a.seg_creators, nseg, a.seg_k, a.scan_scratch, s);
+  {
+    KernelTimer t_("k2_partition", s);
+    k2_init_cursors<<<1, 128, 0, s>>>(a);
+    k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
+  }
+  {
+    KernelTimer t_("k2_deliver", s);
+    k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
+  }
+  {
+    KernelTimer t_("k2_resolve", s);
+    k2_resolve<<<nseg, SEG_THREADS, build2_smem_resolve(), s>>>(a);
+  }
+  KernelTimer t_("k2_corrections", s);
+  k2_corrections<<<64, 128, 0, s>>>(a);
+  return 1 + 6 + 2 + 1 + 1 + 1;
+}
+
+int launch_export_csr(const ExportArgs &x, uint32_t *deg_tmp, uint32_t *scan_scratch, cudaStream_t s) {
+  const uint32_t vb = (x.V + 255) / 256;
+  if (x.V == 0) return 0;
+  k2_export_deg<<<vb, 256, 0, s>>>(x.V, x.pos, x.rs, x.re, deg_tmp);
+  exclusive_scan<uint32_t>(deg_tmp, x.V, x.row_ptr, scan_scratch, s);
+  k2_export_rows<<<vb, 256, 0, s>>>(x);
+  return 5;
+}
+
+}  // namespace gtsb

@@ -34,6 +34,10 @@
 
 namespace gtsb {
 
+__device__ __forceinline__ uint32_t vertex_at(const GraphArgs &g, uint32_t p) {
+  return g.vid != nullptr ? g.vid[p] : p;
+}
+
 // ------------------------------------------------------------------ mark_repeats
 
 __global__ void __launch_bounds__(256) k_repeat_vertices(uint32_t V, const float *__restrict__ astat,
@@ -50,17 +54,16 @@ __global__ void __launch_bounds__(256) k_repeat_vertices(uint32_t V, const float
   if (pred) vstate[v] = GIS_REPEAT;
 }
 
-__global__ void __launch_bounds__(256) k_repeat_edges(uint32_t V, const uint32_t *__restrict__ row_ptr,
-                                                       const uint32_t *__restrict__ dst,
-                                                       const uint8_t *__restrict__ rep_pred,
-                                                       uint8_t *__restrict__ estate) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_repeat_edges(GraphArgs g, const uint8_t *__restrict__ rep_pred) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t *__restrict__ dst = g.dst;
+  uint8_t *__restrict__ estate = g.estate;
   uint32_t r0 = 0, d = 0;
   bool pv = false;
-  if (v < V) {
-    r0 = row_ptr[v];
-    d = row_ptr[v + 1] - r0;
-    pv = rep_pred[v] != 0;
+  if (p < g.V) {
+    r0 = g.rs[p];
+    d = g.re[p] - r0;
+    pv = rep_pred[vertex_at(g, p)] != 0;
   }
   const bool big = d > BIG_ROW;
   if (!big)
@@ -85,7 +88,7 @@ void launch_mark_repeats(const GraphArgs &g, uint8_t *rep_pred, float copy_num_c
   k_repeat_vertices<<<blocks, 256, 0, s>>>(g.V, g.astat, g.vattr, copy_num_cutoff, astat_cutoff,
                                            use_copy_num, rep_pred, g.vstate); }
   KernelTimer t2_("k_repeat_edges", s);
-  k_repeat_edges<<<blocks, 256, 0, s>>>(g.V, g.row_ptr, g.dst, rep_pred, g.estate);
+  k_repeat_edges<<<blocks, 256, 0, s>>>(g, rep_pred);
 }
 
 // ------------------------------------------------------------------ filter, phase 1
@@ -104,10 +107,11 @@ __device__ __forceinline__ void append_proposals(uint32_t t, uint32_t n, const u
 // thread per vertex, rows <= BIG_ROW: all same-sense pairs (i<j) of the row
 __global__ void __launch_bounds__(128) k_pairs_small(FilterArgs a) {
   const GraphArgs &g = a.g;
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= g.V) return;
-  const uint32_t r0 = g.row_ptr[v], d = g.row_ptr[v + 1] - r0;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.V) return;
+  const uint32_t r0 = g.rs[p], d = g.re[p] - r0;
   if (d < 2 || d > BIG_ROW) return;
+  const uint32_t v = vertex_at(g, p);
   if (vertex_state_marked(g.vstate[v])) return;                    // algorithms.c:279
   int32_t dist[BIG_ROW];
   float sd[BIG_ROW], cn[BIG_ROW];
@@ -144,9 +148,10 @@ __global__ void __launch_bounds__(512) k_pairs_big(FilterArgs a) {
   float *cn = reinterpret_cast<float *>(a.big_scratch + (size_t) blockIdx.x * g.max_deg * BIG_SCRATCH_STRIDE);
   uint8_t *mark = reinterpret_cast<uint8_t *>(cn + 2 * (size_t) g.max_deg);
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
-    const uint32_t v = g.big_rows[li];
+    const uint32_t p = g.big_rows[li];
+    const uint32_t v = vertex_at(g, p);
     if (vertex_state_marked(g.vstate[v])) continue;
-    const uint32_t r0 = g.row_ptr[v], d = g.row_ptr[v + 1] - r0;
+    const uint32_t r0 = g.rs[p], d = g.re[p] - r0;
     for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
       cn[k] = g.vattr[g.dst[r0 + k]].copy_num;
       mark[k] = 0;
@@ -230,10 +235,11 @@ constexpr uint8_t FS_DECIDED_ALL = 0x0C;
 // reached, not yet counting the fires of smaller neighbours (algorithms.c:301-320)
 __global__ void __launch_bounds__(128) k_overlap_small(FilterArgs a) {
   const GraphArgs &g = a.g;
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   bool queue = false;
-  if (v < g.V) {
-    const uint32_t r0 = g.row_ptr[v], d = g.row_ptr[v + 1] - r0;
+  if (p < g.V) {
+    const uint32_t r0 = g.rs[p], d = g.re[p] - r0;
+    const uint32_t v = vertex_at(g, p);
     if (d <= BIG_ROW) {
       const bool active = !vertex_state_marked(g.vstate[v]) && !(a.poly_cur[v] < v);
       uint8_t gb = 0;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(128) k_overlap_small(FilterArgs a) {
       }
     }
   }
-  warp_append(queue, v, a.work_a, &g.counters[CNT_WORK_A]);
+  warp_append(queue, p, a.work_a, &g.counters[CNT_WORK_A]);
 }
 
 __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
@@ -280,8 +286,9 @@ __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
   uint32_t *len = reinterpret_cast<uint32_t *>(a.big_scratch + (size_t) blockIdx.x * g.max_deg * BIG_SCRATCH_STRIDE);
   uint8_t *ok = reinterpret_cast<uint8_t *>(len + 2 * (size_t) g.max_deg);
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
-    const uint32_t v = g.big_rows[li];
-    const uint32_t r0 = g.row_ptr[v], d = g.row_ptr[v + 1] - r0;
+    const uint32_t p = g.big_rows[li];
+    const uint32_t v = vertex_at(g, p);
+    const uint32_t r0 = g.rs[p], d = g.re[p] - r0;
     const bool active = !vertex_state_marked(g.vstate[v]) && !(a.poly_cur[v] < v);
     uint8_t gb = 0;
     if (active && a.ocutoff < 0) {
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
         a.fstat[v] = FS_DECIDED_ALL | gb;
       } else {
         a.fstat[v] = (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
-        if (gb) a.work_a[atomicAdd(&g.counters[CNT_WORK_A], 1u)] = v;
+        if (gb) a.work_a[atomicAdd(&g.counters[CNT_WORK_A], 1u)] = p;
       }
     }
     __syncthreads();
@@ -343,13 +350,14 @@ __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t
   const GraphArgs &g = a.g;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   bool again = false;
-  uint32_t v = 0;
+  uint32_t p = 0;
   if (idx < n_in) {
-    v = work_in[idx];
+    p = work_in[idx];
+    const uint32_t v = vertex_at(g, p);
     const volatile uint8_t *fstat = a.fstat;
     uint8_t st = fstat[v];
     const uint32_t und = (~(uint32_t) st >> 2) & 3u;
-    const uint32_t r0 = g.row_ptr[v], d = g.row_ptr[v + 1] - r0;
+    const uint32_t r0 = g.rs[p], d = g.re[p] - r0;
     uint32_t out = 0, pend = 0;
     for (uint32_t k = 0; k < d; k++) {
       const uint32_t u = g.dst[r0 + k];
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t
     a.fstat[v] = st;
     again = (st & FS_DECIDED_ALL) != FS_DECIDED_ALL;
   }
-  warp_append(again, v, work_out, n_out);
+  warp_append(again, p, work_out, n_out);
 }
 
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
@@ -405,12 +413,13 @@ __device__ __forceinline__ void finalize_row(const FilterArgs &a, uint32_t v, ui
 
 __global__ void __launch_bounds__(256) k_finalize(FilterArgs a) {
   const GraphArgs &g = a.g;
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t r0 = 0, d = 0, fv = 0;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t r0 = 0, d = 0, fv = 0, v = 0;
   int pv = -1;
-  if (v < g.V) {
-    r0 = g.row_ptr[v];
-    d = g.row_ptr[v + 1] - r0;
+  if (p < g.V) {
+    v = vertex_at(g, p);
+    r0 = g.rs[p];
+    d = g.re[p] - r0;
     const uint32_t pt = a.poly_cur[v];
     if (pt != NO_TIME) {
       pv = (int) pt;

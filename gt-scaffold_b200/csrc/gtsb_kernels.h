@@ -32,8 +32,65 @@ enum {
   CNT_WORK_B,
   CNT_OVERFLOW,           // a list ran out of capacity
   CNT_MAX_DEG,
+  CNT_FALLBACK,           // FB_* bits: the line-ordered build cannot handle this input
+  CNT_EDGES,              // slots written by the line-ordered build
+  CNT_CORRECTIONS,        // reverse-flag corrections posted by k2_resolve
   CNT_NUM
 };
+
+// why the line-ordered build gave up (gtsb_build then runs the general path)
+enum : uint32_t {
+  FB_MULTIRUN = 1,        // a root contig heads more than one line
+  FB_LONGLINE = 2,        // a line longer than MAX_LINE_RECS records
+  FB_SEGMENT = 4,         // a segment does not fit the staging buffers
+  FB_DOWN_ORPHAN = 8      // a link listed only on the later of the two lines
+};
+
+constexpr int SEG_LINES = 256;            // lines (positions) per block
+constexpr int SEG_THREADS = 256;
+constexpr uint32_t SEG_REC_CAP = 4096;    // staged records per segment
+constexpr uint32_t SEG_ENT_CAP = 3072;    // staged mailbox entries per segment
+constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread scans accept
+constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
+
+struct Build2Args {
+  uint64_t R;
+  uint32_t V;
+  int sm_count;
+  uint32_t coarse_shift, corrections_cap;
+  const uint32_t *root, *ctg;
+  const int32_t *dist;
+  const float *std_dev;
+  const uint8_t *flags;
+  uint32_t *pos, *vid, *ls;                 // [V], [V], [V+1]
+  uint32_t *tile_cnt, *tile_off;            // head tiles
+  uint8_t *rf;                              // [R] RF_UP | RF_FIRST
+  uint32_t *cnt_in, *bptr, *cursor;         // [V+1] mailbox sizes / offsets / fill
+  uint32_t *seg_creators, *seg_k;           // [nseg+1]
+  uint4 *tmp_ent, *bucket, *corrections;
+  uint32_t *tmp_dest, *tmp_cursor;
+  uint8_t *lineless_flag;
+  uint32_t *lineless_rank, *scan_scratch, *counters, *big_rows;
+  uint32_t *rs, *re, *dst, *eid;            // rows
+  int32_t *edist;
+  float *estd;
+  uint8_t *eflags;
+};
+int launch_build2_lines(const Build2Args &a, cudaStream_t s);
+int launch_build2_rows(const Build2Args &a, cudaStream_t s);
+
+struct ExportArgs {        // line layout -> plain CSR in vertex order
+  uint32_t V;
+  const uint32_t *pos, *rs, *re, *dst, *eid;
+  const int32_t *dist;
+  const float *std_dev;
+  const uint8_t *flags, *estate;
+  uint32_t *row_ptr, *dst_o, *eid_o;
+  int32_t *dist_o;
+  float *std_o;
+  uint8_t *flags_o, *estate_o;
+};
+int launch_export_csr(const ExportArgs &x, uint32_t *deg_tmp, uint32_t *scan_scratch, cudaStream_t s);
 
 struct BuildArgs {
   uint64_t R;
@@ -65,10 +122,16 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
                                 uint32_t nlarge, cudaStream_t s);
 void launch_build_emit(const BuildArgs &a, cudaStream_t s);
 
-struct GraphArgs {          // a device-resident CSR graph + vertex attributes
+// A device-resident graph.  Rows are addressed by POSITION p in [0,V): row p
+// occupies slots [rs[p], re[p]) and belongs to vertex vid[p] (vid == nullptr:
+// identity).  The plain CSR of the general build is rs = row_ptr,
+// re = row_ptr + 1; the line-ordered build stores rows in .de line order.
+// Everything indexed by a vertex (states, attributes, polyTime, fire bits, the
+// dst column) uses the reference's vertex ids.
+struct GraphArgs {
   uint32_t V;
   int sm_count;
-  const uint32_t *row_ptr, *dst;
+  const uint32_t *rs, *re, *vid, *dst;
   const int32_t *dist;
   const float *std_dev;
   const uint8_t *flags;

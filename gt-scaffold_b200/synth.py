@@ -118,8 +118,11 @@ def generate(name: str = "c2_bacterial", V: int | None = None, *,
              mean_pairs: float | None = None, seed: int | None = None,
              line_order: str = "shuffled", one_sided_frac: float = 0.0,
              mirror_diff_frac: float = 0.01, dup_same_line_frac: float = 0.005,
-             max_deg: int = 10_000, zipf_alpha: float = 2.1) -> ScaffoldInput:
-    """Generate one of the named configs (optionally at a reduced V)."""
+             max_deg: int = 10_000, zipf_alpha: float = 2.1,
+             one_sided_up: bool = False) -> ScaffoldInput:
+    """Generate one of the named configs (optionally at a reduced V).
+    one_sided_up: links listed on one line only are listed on the EARLIER of the
+    two lines (the only one-sided case the line-ordered build handles itself)."""
     config_id, V0, mp0, kind = CONFIGS[name]
     V = V0 if V is None else int(V)
     mp = mp0 if mean_pairs is None else mean_pairs
@@ -138,6 +141,17 @@ def generate(name: str = "c2_bacterial", V: int | None = None, *,
     first.sort()
     a, b = a[first], b[first]
     P = a.shape[0]
+
+    if line_order == "shuffled":
+        line_rank = rng.permutation(V).astype(np.int64)
+    elif line_order == "id":
+        line_rank = np.arange(V, dtype=np.int64)
+    else:
+        raise ValueError(line_order)
+    keep_b = rng.random(P) >= one_sided_frac
+    if one_sided_up:
+        sw = (~keep_b) & (line_rank[a] > line_rank[b])
+        a, b = np.where(sw, b, a), np.where(sw, a, b)
 
     sense_a = rng.random(P) < 0.5
     same = rng.random(P) < 0.5
@@ -161,7 +175,6 @@ def generate(name: str = "c2_bacterial", V: int | None = None, *,
         dist[pick] = base[prev[pick]] + jitter[pick]
 
     # records: one on a's line, one on b's line
-    keep_b = rng.random(P) >= one_sided_frac
     r_root = [a, b[keep_b]]
     r_ctg = [b, a[keep_b]]
     r_sense = [sense_a, sense_b[keep_b]]
@@ -194,12 +207,6 @@ def generate(name: str = "c2_bacterial", V: int | None = None, *,
 
     # file order: lines (roots) in `line_order`, sense records first in a line,
     # then generation order
-    if line_order == "shuffled":
-        line_rank = rng.permutation(V).astype(np.int64)
-    elif line_order == "id":
-        line_rank = np.arange(V, dtype=np.int64)
-    else:
-        raise ValueError(line_order)
     key = line_rank[root] * 2 + (~sense).astype(np.int64)
     order = np.argsort(key, kind="stable")
 

@@ -47,6 +47,8 @@ typedef struct gtsb_stats {
   uint64_t nof_vertices, nof_records, nof_edges;
   uint32_t max_degree, big_rows, large_buckets;
   uint32_t proposals, poly_sweeps, fire_rounds;
+  uint32_t line_ordered_build;     /* 1: last gtsb_build took the line-ordered fast path */
+  uint32_t fallback_reason;        /* why not (bit mask, csrc/gtsb_kernels.h FB_*), else 0 */
   uint64_t kernel_launches;        /* kernels launched by this context so far */
   float ms_build, ms_mark_repeats, ms_filter;   /* device time of the last call of each stage */
 } gtsb_stats;
@@ -59,6 +61,8 @@ int gtsb_set_stream(gtsb_context *ctx, void *cuda_stream);
 /* also record, per edge, which record's attributes it carries (needed to fill
    GtScaffolderGraphEdge.num_pairs); costs 8 B/edge of extra traffic */
 int gtsb_want_win_rec(gtsb_context *ctx, int on);
+/* testing aid: always take the general (any-input) build path */
+int gtsb_force_general_build(gtsb_context *ctx, int on);
 
 /* ---- inputs.  *_host variants copy from host memory (H2D on the context's
    stream); *_device variants adopt device pointers that must stay valid. */

@@ -30,11 +30,11 @@ def diff(got, exp, tag):
     return ok
 
 
-def case(inp, tag, params=(0.3, 20.0, True, 0.01, 1.5, 400)):
+def case(inp, tag, params=(0.3, 20.0, True, 0.01, 1.5, 400), force_general=False):
     cn_cut, a_cut, use_cn, pc, cnc, oc = params
     t0 = time.time()
     try:
-        g = pkg.ScaffoldGraphB200.new_from_records(inp)
+        g = pkg.ScaffoldGraphB200.new_from_records(inp, force_general=force_general)
         ref = O.best_oracle().build(inp)
         ok = diff(g.result(), ref.result(), tag + "/build")
         g.mark_repeats(cn_cut, a_cut, use_cn)
@@ -53,9 +53,14 @@ def case(inp, tag, params=(0.3, 20.0, True, 0.01, 1.5, 400)):
 
 if __name__ == "__main__":
     print("oracle:", O.best_oracle().__name__)
-    for seed in range(8):
+    for seed in range(6):
+        case(pkg.synth.generate("c2_bacterial", V=6 + 5 * seed, seed=900 + seed, mean_pairs=1.0 + seed % 4,
+                                line_order="id" if seed % 2 else "shuffled", one_sided_frac=0.25 * (seed % 2),
+                                one_sided_up=True, mirror_diff_frac=0.3, dup_same_line_frac=0.2), f"line{seed}")
+    for seed in range(3):
         case(pkg.synth.tiny_dense(4 + seed, 6 + 5 * seed, 3000 + seed), f"tiny{seed}")
     case(pkg.synth.generate("c2_bacterial", V=2000), "c2_2k")
+    case(pkg.synth.generate("c2_bacterial", V=2000, line_order="id"), "c2_2k_id")
     case(pkg.synth.generate("c2_bacterial"), "c2_full")
     case(pkg.synth.generate("c4_repeat_hubs", V=50000, max_deg=2000), "c4_50k")
     case(pkg.synth.generate("c3_human", V=1_000_000), "c3_1M")

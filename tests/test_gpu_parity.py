@@ -24,8 +24,8 @@ def _cmp(got, exp, what=""):
                                  f"got {np.asarray(got[k])[bad[:8]]} exp {np.asarray(exp[k])[bad[:8]]}")
 
 
-def _run_both(pkg, inp, cn_cut, a_cut, use_cn, pc, cnc, oc, stagewise=True):
-    g = pkg.ScaffoldGraphB200.new_from_records(inp)
+def _run_both(pkg, inp, cn_cut, a_cut, use_cn, pc, cnc, oc, stagewise=True, force_general=False):
+    g = pkg.ScaffoldGraphB200.new_from_records(inp, force_general=force_general)
     ref = O.best_oracle().build(inp)
     if stagewise:
         _cmp(g.result(), ref.result(), "build")
@@ -49,8 +49,40 @@ PARAMS = [(0.3, 20.0, True, 0.01, 1.5, 400), (0.3, 20.0, True, 0.01, 1.5, 0),
 
 @pytest.mark.parametrize("seed", range(60))
 def test_tiny_adversarial(pkg, synth, seed):
+    """Shuffled records / one-sided links: mostly the general build path."""
     inp = synth.tiny_dense(4 + seed % 13, 6 + 3 * (seed % 17), 3000 + seed, split_lines=bool(seed % 2))
     _run_both(pkg, inp, *PARAMS[seed % len(PARAMS)])
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_small_line_ordered(pkg, synth, seed):
+    """Small .de-shaped inputs that stay on the line-ordered build: shuffled or
+    id-ordered lines, repeated estimates on either line, links listed only on
+    the earlier line, vertices without a line."""
+    V = 6 + 7 * (seed % 9)
+    inp = synth.generate("c2_bacterial", V=V, seed=900 + seed, mean_pairs=1.0 + (seed % 5),
+                         line_order="id" if seed % 2 else "shuffled",
+                         one_sided_frac=0.25 if seed % 3 == 0 else 0.0, one_sided_up=True,
+                         mirror_diff_frac=0.3, dup_same_line_frac=0.2)
+    st = _run_both(pkg, inp, *PARAMS[seed % len(PARAMS)])
+    assert st["line_ordered_build"] == 1, st
+    _run_both(pkg, inp, *PARAMS[seed % len(PARAMS)], force_general=True)
+
+
+def test_fallback_reasons(pkg, synth):
+    """Inputs outside the fast path's preconditions must be detected, not guessed."""
+    # a link listed only on the later line
+    inp = synth.generate("c2_bacterial", V=3000, one_sided_frac=0.3)
+    st = _run_both(pkg, inp, *PARAMS[0], stagewise=False)
+    assert st["line_ordered_build"] == 0 and st["fallback_reason"] & 8
+    # hubs: lines longer than the per-thread scans accept
+    inp = synth.generate("c4_repeat_hubs", V=20000, max_deg=500)
+    st = _run_both(pkg, inp, *PARAMS[0], stagewise=False)
+    assert st["line_ordered_build"] == 0 and st["fallback_reason"] & (2 | 4)
+    # records not grouped by root
+    inp = synth.tiny_dense(12, 60, 5)
+    st = _run_both(pkg, inp, *PARAMS[0], stagewise=False)
+    assert st["line_ordered_build"] == 0 and st["fallback_reason"] & 1
 
 
 def test_empty_and_degenerate(pkg, synth):
@@ -107,9 +139,13 @@ def test_committed_differential_vectors(pkg, synth, path):
 ])
 def test_named_configs(pkg, synth, name, V, kw):
     inp = synth.generate(name, V=V, **kw)
-    st = _run_both(pkg, inp, **{k: v for k, v in zip(
-        ["cn_cut", "a_cut", "use_cn", "pc", "cnc", "oc"], PARAMS[0])}, stagewise=False)
-    assert st["nof_edges"] > 0
+    for force in (False, True):
+        st = _run_both(pkg, inp, **{k: v for k, v in zip(
+            ["cn_cut", "a_cut", "use_cn", "pc", "cnc", "oc"], PARAMS[0])}, stagewise=False,
+            force_general=force)
+        assert st["nof_edges"] > 0
+        if not force and not kw and name != "c4_repeat_hubs":
+            assert st["line_ordered_build"] == 1, st
 
 
 def test_win_rec_points_at_the_winning_record(pkg, synth):
