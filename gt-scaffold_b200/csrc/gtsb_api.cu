@@ -81,7 +81,7 @@ struct gtsb_context {
   DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
       big_rows, counters, lscratch, ltag;
   // filter work
-  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch;
+  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, dirty;
   uint32_t n_big_rows = 0, max_deg = 0;
 
   uint32_t *h_counters = nullptr;   // pinned
@@ -223,7 +223,9 @@ GraphArgs graph_args(gtsb_context *c) {
     g.rs = c->rs.as<uint32_t>();
     g.re = c->re.as<uint32_t>();
     g.vid = c->vid.as<uint32_t>();
+    g.pos = c->pos.as<uint32_t>();
   } else {
+    g.pos = nullptr;
     g.rs = c->row_ptr.as<uint32_t>();
     g.re = c->row_ptr.as<uint32_t>() + 1;
     g.vid = nullptr;
@@ -516,7 +518,7 @@ int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int us
   return 0;
 }
 
-int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
+int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, bool fused_repeats = false) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
   if (get_ambig(c, pcutoff) != 0) return -1;
@@ -530,6 +532,9 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
   ENSURE(c->fstat, V + 1);
   ENSURE(c->work_a, (V + 1) * 4);
   ENSURE(c->work_b, (V + 1) * 4);
+  ENSURE(c->vinfo, (V + 1) * sizeof(uint2));
+  ENSURE(c->vres, (V + 1) * 4);
+  ENSURE(c->dirty, V + 1);
   FilterArgs a{};
   a.big_blocks = (uint32_t) c->sm_count * 2;
   if (c->n_big_rows) {
@@ -549,16 +554,24 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
   a.work_a = c->work_a.as<uint32_t>();
   a.work_b = c->work_b.as<uint32_t>();
   a.big_scratch = c->big_scratch.as<uint8_t>();
+  a.vinfo = c->vinfo.as<uint2>();
+  a.vres = c->vres.as<uint32_t>();
+  a.dirty = c->dirty.as<uint8_t>();
+  a.fused_repeats = fused_repeats ? 1 : 0;
 
   uint32_t *cnt = c->counters.as<uint32_t>();
   CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
   CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (V + 1) * 4, s));
   CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (V + 1) * 4, s));
 
-  // phase 1: who proposes whom
-  launch_filter_pairs(a, s);
-  c->stats.kernel_launches += (V ? 1 : 0) + (c->n_big_rows ? 1 : 0);
+  CK(cudaMemsetAsync(c->dirty.p, 0, V + 1, s));
+  // phase 1: who proposes whom (+ the static overlap answer of every small row)
+  launch_vinfo(a, s);
+  launch_pairs2(a, s);
+  launch_pairs_big(a, s);
+  c->stats.kernel_launches += (V ? 2 : 0) + (c->n_big_rows ? 1 : 0);
   if (read_counters(c) != 0) return -1;
+  if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
   if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
   const uint32_t nprop = c->h_counters[CNT_PROPOSALS];
   c->stats.proposals = nprop;
@@ -573,15 +586,25 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
       if (!c->h_counters[CNT_POLY_CHANGED]) break;
       if (c->stats.poly_sweeps > V + 2) return fail(c, "gtsb_filter: polyTime sweeps did not converge");
     }
+    launch_dirty(a, nprop, s);
+    c->stats.kernel_launches += 1;
   }
-  // phase 2: overlap candidates, then the order-respecting fire fixpoint
+  // phase 2: fire candidates (static answer, recomputed next to polymorphic
+  // vertices), then the order-respecting fire fixpoint
   launch_filter_overlap(a, s);
   c->stats.kernel_launches += (V ? 1 : 0) + (c->n_big_rows ? 1 : 0);
   c->stats.fire_rounds = 0;
-  if (read_counters(c) != 0) return -1;
-  uint32_t n_in = c->h_counters[CNT_WORK_A];
-  uint32_t *win = a.work_a, *wout = a.work_b;
-  int in_idx = CNT_WORK_A, out_idx = CNT_WORK_B;
+  uint32_t *win = a.work_b, *wout = a.work_a;
+  int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
+  uint32_t n_in = 0;
+  if (ocutoff >= 0 && V) {
+    CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
+    launch_fire_dense(a, a.work_b, cnt + CNT_WORK_B, s);
+    c->stats.kernel_launches += 1;
+    c->stats.fire_rounds++;
+    if (read_counters(c) != 0) return -1;
+    n_in = c->h_counters[CNT_WORK_B];
+  }
   while (n_in) {
     CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
     launch_fire_round(a, win, n_in, wout, cnt + out_idx, s);
@@ -594,8 +617,8 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
     uint32_t *t = win; win = wout; wout = t;
     int ti = in_idx; in_idx = out_idx; out_idx = ti;
   }
-  launch_filter_finalize(a, s);
-  c->stats.kernel_launches += V ? 1 : 0;
+  launch_finalize2(a, fused_repeats ? c->rep_pred.as<uint8_t>() : nullptr, s);
+  c->stats.kernel_launches += V ? 2 : 0;
   CK(cudaGetLastError());
   return 0;
 }
@@ -679,7 +702,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
                     &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
-                    &c->work_a, &c->work_b, &c->big_scratch, &c->rs, &c->re, &c->vid, &c->pos, &c->ls,
+                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->rs, &c->re, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
                     &c->seg_creators, &c->seg_k, &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
@@ -860,8 +883,16 @@ int gtsb_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
   if (do_build(c) != 0) return -1;
-  if (do_mark_repeats(c, cn_cutoff, astat_cutoff, use_cn) != 0) return -1;
-  if (do_filter(c, pcutoff, cncutoff, ocutoff) != 0) return -1;
+  {
+    // fresh graph: every edge state is UNVISITED, so the REPEAT edge marks of
+    // mark_repeats (pred(v) || pred(w)) need not be stored before the filter
+    // overwrites most of them; the final pass derives them
+    ProfScope ps_(c);
+    c->csr_exported = false;
+    launch_repeat_vertices(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
+    c->stats.kernel_launches += c->V ? 1 : 0;
+  }
+  if (do_filter(c, pcutoff, cncutoff, ocutoff, true) != 0) return -1;
   return 0;
 }
 

@@ -219,7 +219,7 @@ __global__ void k2_init_cursors(Build2Args a) {
 
 // pass D-A: creators build their mailbox entry and drop it into the coarse bin
 // of the destination position (bins are contiguous ranges of the final mailbox
-// array, so bin b starts at bptr[b << shift])
+// array, so bin b starts at bptr[b << shift]).  Thread per record.
 __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
@@ -238,41 +238,39 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     s_ctg[r] = a.ctg[g.rec0 + r];
     s_std[r] = a.std_dev[g.rec0 + r];
     s_fl[r] = a.flags[g.rec0 + r];
-    s_rf[r] = a.rf[g.rec0 + r];
+    const uint8_t rf = a.rf[g.rec0 + r];
+    s_rf[r] = rf;
+    s_pc[r] = rf == (RF_UP | RF_FIRST) ? a.pos[s_ctg[r]] : UNSET;   // destination position
   }
   for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
   __syncthreads();
-  // creators: destination position and bin histogram
-  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
-    if (s_rf[r] != (RF_UP | RF_FIRST)) continue;
-    const uint32_t pc = a.pos[s_ctg[r]];
-    s_pc[r] = pc;
-    atomicAdd(&s_bin[pc >> a.coarse_shift], 1u);
-  }
+  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
+    if (s_pc[r] != UNSET) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
     if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
-  // creator ranks in record order: blocked chunks + block scan
-  const uint32_t chunk = (g.n + blockDim.x - 1) / blockDim.x;
-  const uint32_t r0 = min(g.n, threadIdx.x * chunk), r1 = min(g.n, r0 + chunk);
-  uint32_t mine = 0;
-  for (uint32_t r = r0; r < r1; r++) mine += s_rf[r] == (RF_UP | RF_FIRST);
-  uint32_t total;
-  uint32_t k = a.seg_k[blockIdx.x] + block_excl_scan(mine, &total);   // syncs: bin bases visible
-  for (uint32_t r = r0; r < r1; r++) {
-    if (s_rf[r] != (RF_UP | RF_FIRST)) continue;
+  // creator rank in record order = k - seg_k: one block scan per 256 records
+  uint32_t carry = a.seg_k[blockIdx.x];
+  for (uint32_t base = 0; base < g.n; base += blockDim.x) {
+    const uint32_t r = base + threadIdx.x;
+    const bool creator = r < g.n && s_pc[r] != UNSET;
+    uint32_t total;
+    const uint32_t k = carry + block_excl_scan(creator ? 1u : 0u, &total);   // syncs: bin bases visible
+    carry += total;
+    if (!creator) continue;
     const uint32_t j = s_line[r], c = s_ctg[r];
     // final flags of edge root->c: strict running maximum over the line's records
     float best = s_std[r];
     uint32_t bf = s_fl[r];
-    for (uint32_t t = r + 1; t < s_ls[j + 1] - g.rec0; t++)
+    const uint32_t rb = s_ls[j + 1] - g.rec0;
+    for (uint32_t t = r + 1; t < rb; t++)
       if (s_ctg[t] == c && best < s_std[t]) {
         best = s_std[t];
         bf = s_fl[t];
       }
     const uint32_t sf = s_fl[r];
     uint4 e;
-    e.x = k++;
+    e.x = k;
     e.y = a.vid[g.p0 + j] | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
           ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u);
     e.z = (uint32_t) a.dist[g.rec0 + r];
@@ -285,38 +283,65 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
 }
 
 // pass D-B: stream the coarsely sorted entries into their mailboxes; the
-// targets of concurrently running blocks stay inside one or two coarse bins
+// targets of concurrently running blocks stay inside one or two coarse bins,
+// i.e. inside L2.  Four independent chains per thread hide the atomic latency.
 __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
   if (a.counters[CNT_FALLBACK] | a.counters[CNT_ERROR]) return;
+  constexpr int ILP = 4;
   const uint32_t n = a.bptr[a.V];
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const uint32_t pc = a.tmp_dest[e];
-    a.bucket[a.bptr[pc] + atomicAdd(&a.cursor[pc], 1u)] = a.tmp_ent[e];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += stride * ILP) {
+    uint32_t pc[ILP], at[ILP];
+    uint4 ent[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+      const uint32_t e = e0 + k * stride;
+      pc[k] = e < n ? a.tmp_dest[e] : UNSET;
+      if (e < n) ent[k] = a.tmp_ent[e];
+    }
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+      if (pc[k] != UNSET) at[k] = a.bptr[pc[k]] + atomicAdd(&a.cursor[pc[k]], 1u);
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+      if (pc[k] != UNSET) a.bucket[at[k]] = ent[k];
   }
 }
 
-// pass R: one thread per line resolves the line's records against its mailbox
-// and writes the CSR row
+// pass R: resolve every line against its mailbox and write the CSR rows.
+// Thread per mailbox entry (twin-created slots) and per record (own slots), so
+// that neighbouring threads write neighbouring slots.
 __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + SEG_ENT_CAP);
   uint32_t *s_bp = s_ls + SEG_LINES + 4;
-  uint32_t *s_ctg = s_bp + SEG_LINES + 4;
+  uint32_t *s_row0 = s_bp + SEG_LINES + 4;          // first slot of each row
+  uint32_t *s_k0 = s_row0 + SEG_LINES + 4;          // creators before each line (in the segment)
+  uint32_t *s_nown = s_k0 + SEG_LINES + 4;          // creators of each line
+  uint32_t *s_ctg = s_nown + SEG_LINES + 4;
   int32_t *s_dist = reinterpret_cast<int32_t *>(s_ctg + SEG_REC_CAP);
   float *s_std = reinterpret_cast<float *>(s_dist + SEG_REC_CAP);
   uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_std + SEG_REC_CAP);
   uint8_t *s_rf = s_fl + SEG_REC_CAP;
+  uint8_t *s_line = s_rf + SEG_REC_CAP;
+  uint8_t *s_eline = s_line + SEG_REC_CAP;
   Seg g;
   if (!seg_open(a, blockIdx.x, g, s_ls)) return;
-  for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) s_bp[j] = a.bptr[g.p0 + j];
+  for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) {
+    s_bp[j] = a.bptr[g.p0 + j];
+    s_nown[j] = 0;
+  }
   __syncthreads();
   const uint32_t ent0 = s_bp[0], nent = s_bp[g.nlines] - ent0;
   if (nent > SEG_ENT_CAP) {
     if (threadIdx.x == 0) raise(a.counters, FB_SEGMENT);
     return;
   }
+  seg_lines(a, g, s_ls, s_line);
+  for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x)
+    for (uint32_t e = s_bp[j] - ent0; e < s_bp[j + 1] - ent0; e++) s_eline[e] = (uint8_t) j;
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
     s_ctg[r] = a.ctg[g.rec0 + r];
     s_dist[r] = a.dist[g.rec0 + r];
@@ -326,73 +351,83 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   }
   for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) s_ent[e] = a.bucket[ent0 + e];
   __syncthreads();
-
-  const uint32_t j = threadIdx.x;
-  uint32_t ra = 0, rb = 0, ea = 0, eb = 0, nown = 0;
-  if (j < g.nlines) {
-    ra = s_ls[j] - g.rec0;
-    rb = s_ls[j + 1] - g.rec0;
-    ea = s_bp[j] - ent0;
-    eb = s_bp[j + 1] - ent0;
-    for (uint32_t t = ra; t < rb; t++) {
-      const uint32_t rf = s_rf[t];
-      if (rf == (RF_UP | RF_FIRST)) nown++;
-      if (rf == RF_FIRST) {                       // down: the creator's mail must be here
-        bool found = false;
-        for (uint32_t e = ea; e < eb; e++) found |= (s_ent[e].y & E_OTHER_MASK) == s_ctg[t];
-        if (!found) raise(a.counters, FB_DOWN_ORPHAN);
+  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
+    if (s_rf[r] == (RF_UP | RF_FIRST)) atomicAdd(&s_nown[s_line[r]], 1u);
+  __syncthreads();
+  // row offsets: capacity prefix of the segment + exclusive scan of the degrees
+  {
+    const uint32_t j = threadIdx.x;              // SEG_LINES <= SEG_THREADS
+    uint32_t deg = 0, nown = 0;
+    if (j < g.nlines) {
+      nown = s_nown[j];
+      deg = (s_bp[j + 1] - s_bp[j]) + nown;
+    }
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(deg | (nown << 16), &total);
+    if (j < g.nlines) {
+      const uint32_t p = g.p0 + j;
+      const uint32_t row0 = g.rec0 + ent0 + (ex & 0xFFFFu);
+      s_row0[j] = row0;
+      s_k0[j] = a.seg_k[blockIdx.x] + (ex >> 16);
+      a.rs[p] = row0;
+      a.re[p] = row0 + deg;
+      if (j == 0) atomicAdd(&a.counters[CNT_EDGES], total & 0xFFFFu);
+      if (deg > BIG_ROW) {
+        atomicMax(&a.counters[CNT_MAX_DEG], deg);
+        a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
       }
     }
   }
-  const uint32_t deg = (eb - ea) + nown;
-  uint32_t total;
-  const uint32_t ex = block_excl_scan(deg | (nown << 16), &total);
-  if (j >= g.nlines) return;
-  const uint32_t p = g.p0 + j, v = a.vid[p];
-  const uint32_t row0 = g.rec0 + ent0 + (ex & 0xFFFFu);    // capacity prefix: own records + mail
-  a.rs[p] = row0;
-  a.re[p] = row0 + deg;
-  if (j == 0) atomicAdd(&a.counters[CNT_EDGES], total & 0xFFFFu);
-  if (deg > BIG_ROW) {
-    atomicMax(&a.counters[CNT_MAX_DEG], deg);
-    a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
-  }
+  __syncthreads();
   // twin-created slots, ordered by the creator's k
-  for (uint32_t e = ea; e < eb; e++) {
+  for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) {
+    const uint32_t j = s_eline[e];
+    const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
+    const uint32_t ra = s_ls[j] - g.rec0, rb = s_ls[j + 1] - g.rec0;
     const uint4 m = s_ent[e];
     const uint32_t u = m.y & E_OTHER_MASK;
     uint32_t rank = 0;
     for (uint32_t e2 = ea; e2 < eb; e2++) rank += s_ent[e2].x < m.x;
     const bool seed_same = (m.y & M_SEED_SAME) != 0;
     const bool seed_sense = twin_dir((m.y & M_SEED_SENSE) != 0, seed_same);   // parser.c:369-372
+    const uint32_t seedf = (seed_sense ? F_SENSE : 0u) | (seed_same ? F_SAME : 0u);
     float best = __uint_as_float(m.w);
     int32_t bdist = (int32_t) m.z;
-    uint32_t bf = (seed_sense ? F_SENSE : 0u) | (seed_same ? F_SAME : 0u);
+    uint32_t bf = seedf;
     for (uint32_t t = ra; t < rb; t++)
       if (s_ctg[t] == u && best < s_std[t]) {                                  // parser.c:362
         best = s_std[t];
         bdist = s_dist[t];
         bf = s_fl[t] & (F_SENSE | F_SAME);
       }
-    const uint32_t slot = row0 + rank;
+    const uint32_t slot = s_row0[j] + rank;
     a.dst[slot] = u;
     a.edist[slot] = bdist;
     a.estd[slot] = best;
     a.eflags[slot] = (uint8_t) (bf | ((m.y & M_FWD_SENSE) ? F_RSENSE : 0u) | ((m.y & M_FWD_SAME) ? F_RSAME : 0u));
     a.eid[slot] = 2u * m.x + 1u;
-    if (bf != ((seed_sense ? F_SENSE : 0u) | (seed_same ? F_SAME : 0u))) {
+    if (bf != seedf) {
       // the creator assumed its twin keeps the seed's flags: tell it otherwise
       const uint32_t at = atomicAdd(&a.counters[CNT_CORRECTIONS], 1u);
-      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, v, bf, 0u);
+      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, a.vid[g.p0 + j], bf, 0u);
       else raise(a.counters, FB_SEGMENT);
     }
   }
-  // own creators in line order
-  uint32_t q = 0;
-  const uint32_t k0 = a.seg_k[blockIdx.x] + (ex >> 16);
-  for (uint32_t t = ra; t < rb; t++) {
-    if (s_rf[t] != (RF_UP | RF_FIRST)) continue;
-    const uint32_t c = s_ctg[t];
+  // own records: creators write their slot, down records check their mail
+  for (uint32_t t = threadIdx.x; t < g.n; t += blockDim.x) {
+    const uint32_t rf = s_rf[t];
+    if (!(rf & RF_FIRST)) continue;
+    const uint32_t j = s_line[t], c = s_ctg[t];
+    const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
+    const uint32_t ra = s_ls[j] - g.rec0, rb = s_ls[j + 1] - g.rec0;
+    if (!(rf & RF_UP)) {                          // down: the creator's mail must be here
+      bool found = false;
+      for (uint32_t e = ea; e < eb; e++) found |= (s_ent[e].y & E_OTHER_MASK) == c;
+      if (!found) raise(a.counters, FB_DOWN_ORPHAN);
+      continue;
+    }
+    uint32_t q = 0;
+    for (uint32_t t2 = ra; t2 < t; t2++) q += s_rf[t2] == (RF_UP | RF_FIRST);
     float best = s_std[t];
     int32_t bdist = s_dist[t];
     uint32_t bf = s_fl[t] & (F_SENSE | F_SAME);
@@ -403,13 +438,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
         bf = s_fl[t2] & (F_SENSE | F_SAME);
       }
     const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
-    const uint32_t slot = row0 + (eb - ea) + q;
+    const uint32_t slot = s_row0[j] + (eb - ea) + q;
     a.dst[slot] = c;
     a.edist[slot] = bdist;
     a.estd[slot] = best;
     a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u));
-    a.eid[slot] = 2u * (k0 + q);
-    q++;
+    a.eid[slot] = 2u * (s_k0[j] + q);
   }
 }
 
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
 
 size_t build2_smem_classify() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
 size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 3 * NB_COARSE * 4 + 16; }
-size_t build2_smem_resolve() { return SEG_ENT_CAP * 16 + 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 14 + 16; }
+size_t build2_smem_resolve() { return SEG_ENT_CAP * 17 + 5 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 16; }
 
 int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);

@@ -91,6 +91,14 @@ void launch_mark_repeats(const GraphArgs &g, uint8_t *rep_pred, float copy_num_c
   k_repeat_edges<<<blocks, 256, 0, s>>>(g, rep_pred);
 }
 
+void launch_repeat_vertices(const GraphArgs &g, uint8_t *rep_pred, float copy_num_cutoff,
+                            float astat_cutoff, int use_copy_num, cudaStream_t s) {
+  if (g.V == 0) return;
+  KernelTimer t_("k_repeat_vertices", s);
+  k_repeat_vertices<<<(g.V + 255) / 256, 256, 0, s>>>(g.V, g.astat, g.vattr, copy_num_cutoff, astat_cutoff,
+                                                      use_copy_num, rep_pred, g.vstate);
+}
+
 // ------------------------------------------------------------------ filter, phase 1
 
 __device__ __forceinline__ void append_proposals(uint32_t t, uint32_t n, const uint32_t *targets,
@@ -181,6 +189,12 @@ __global__ void __launch_bounds__(512) k_pairs_big(FilterArgs a) {
   }
 }
 
+void launch_pairs_big(const FilterArgs &a, cudaStream_t s) {
+  if (a.g.n_big_rows == 0) return;
+  KernelTimer t_("k_pairs_big", s);
+  k_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
+}
+
 void launch_filter_pairs(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
   { KernelTimer t_("k_pairs_small", s);
@@ -245,6 +259,8 @@ __global__ void __launch_bounds__(128) k_overlap_small(FilterArgs a) {
       uint8_t gb = 0;
       if (active && a.ocutoff < 0) {
         gb = 3;            // 0 > ocutoff: both directions fire whatever the pairs (:301-324)
+      } else if (active && a.dirty != nullptr && !a.dirty[v]) {
+        gb = a.gbits[v];   // k3_pairs' static answer stands: no polymorphic vertex nearby
       } else if (active && d >= 2) {
         int32_t dist[BIG_ROW];
         uint32_t len[BIG_ROW];
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(128) k_overlap_small(FilterArgs a) {
         a.fstat[v] = FS_DECIDED_ALL | gb;          // no dependence on neighbours
       } else {
         a.fstat[v] = (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
-        queue = gb != 0;
+        queue = gb != 0 && a.dirty == nullptr;     // the dense first round needs no worklist
       }
     }
   }
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
         a.fstat[v] = FS_DECIDED_ALL | gb;
       } else {
         a.fstat[v] = (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
-        if (gb) a.work_a[atomicAdd(&g.counters[CNT_WORK_A], 1u)] = p;
+        if (gb && a.dirty == nullptr) a.work_a[atomicAdd(&g.counters[CNT_WORK_A], 1u)] = p;
       }
     }
     __syncthreads();
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(512) k_overlap_big(FilterArgs a) {
 
 void launch_filter_overlap(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
-  { KernelTimer t_("k_overlap_small", s);
+  { KernelTimer t_("k_fire_init", s);
   k_overlap_small<<<(a.g.V + 127) / 128, 128, 0, s>>>(a); }
   if (a.g.n_big_rows) { KernelTimer t_("k_overlap_big", s); k_overlap_big<<<a.big_blocks, 512, 0, s>>>(a); }
 }

@@ -46,10 +46,10 @@ enum : uint32_t {
   FB_DOWN_ORPHAN = 8      // a link listed only on the later of the two lines
 };
 
-constexpr int SEG_LINES = 256;            // lines (positions) per block
+constexpr int SEG_LINES = 128;            // lines (positions) per block
 constexpr int SEG_THREADS = 256;
-constexpr uint32_t SEG_REC_CAP = 4096;    // staged records per segment
-constexpr uint32_t SEG_ENT_CAP = 3072;    // staged mailbox entries per segment
+constexpr uint32_t SEG_REC_CAP = 2048;    // staged records per segment
+constexpr uint32_t SEG_ENT_CAP = 1536;    // staged mailbox entries per segment
 constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread scans accept
 constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
 
@@ -131,7 +131,7 @@ void launch_build_emit(const BuildArgs &a, cudaStream_t s);
 struct GraphArgs {
   uint32_t V;
   int sm_count;
-  const uint32_t *rs, *re, *vid, *dst;
+  const uint32_t *rs, *re, *vid, *pos, *dst;   // pos: vertex -> position (nullptr: identity)
   const int32_t *dist;
   const float *std_dev;
   const uint8_t *flags;
@@ -156,7 +156,20 @@ struct FilterArgs {
   uint32_t *work_a, *work_b;
   uint8_t *big_scratch;      // per block: max_deg * BIG_SCRATCH_STRIDE bytes
   uint32_t big_blocks;
+  // bandwidth path (gtsb_filter2.cu)
+  uint2 *vinfo;              // [V] {copy_num, seq_len | marked-on-entry << 31}
+  uint32_t *vres;            // [V] polyTime | fire bits | repeat predicate
+  uint8_t *dirty;            // [V] static overlap answer must be recomputed (nullptr: always recompute)
+  int fused_repeats;         // fresh graph: edge REPEAT marks are derived, not stored (gtsb_pipeline)
 };
+void launch_vinfo(const FilterArgs &a, cudaStream_t s);
+void launch_pairs2(const FilterArgs &a, cudaStream_t s);
+void launch_pairs_big(const FilterArgs &a, cudaStream_t s);
+void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
+void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
+void launch_finalize2(const FilterArgs &a, const uint8_t *rep_pred, cudaStream_t s);
+void launch_repeat_vertices(const GraphArgs &g, uint8_t *rep_pred, float copy_num_cutoff,
+                            float astat_cutoff, int use_copy_num, cudaStream_t s);
 constexpr uint32_t BIG_SCRATCH_STRIDE = 12;   // cn f32, len u32, u8 marks (padded)
 
 void launch_mark_repeats(const GraphArgs &g, uint8_t *rep_pred, float copy_num_cutoff,
