@@ -1,0 +1,532 @@
+/* gt_scaffolder_b200.c -- the reference-side binding of the B200 hot path.
+ *
+ * A maintainer of gt Scaffolder drops this file into src/ next to the
+ * reference's own sources and links libgtscaffold_b200.so.  It defines the
+ * three hot-path entry points with their prototypes UNCHANGED
+ *
+ *   gt_scaffolder_graph_new_from_file   (gt_scaffolder_graph.h:158-163,  body graph.c:346-412)
+ *   gt_scaffolder_graph_mark_repeats    (gt_scaffolder_algorithms.h:36-40, body algorithms.c:90-170)
+ *   gt_scaffolder_graph_filter          (gt_scaffolder_algorithms.h:43-46, body algorithms.c:261-343)
+ *
+ * over the array-level C ABI of include/gtscaffold_b200.h.  GtScaffolderGraph
+ * keeps its layout; everything downstream (gt_scaffolder_graph_print,
+ * removecycles, makescaffold, write_scaffold) reads the `state` fields and
+ * adjacency lists this file fills, exactly as it reads the reference's.
+ *
+ * Host text handling stays host C: FASTA goes
+ * through the reference's own gt_scaffolder_parser_count_contigs /
+ * _read_contigs, `.de` validation through its _count_distances; the `.de`
+ * and `.astat` tokenisers below only turn text into integer records with the
+ * same tokenising rules (1024-byte fgets, last character dropped, ' ' tokens,
+ * "%[^>,],%ld,%ld,%f" records, ';' switches the direction: parser.c:323-388,
+ * algorithms.c:118-149).  All graph work happens on the GPU; there is no CPU
+ * fallback -- a missing device or a CUDA error is reported the reference's
+ * way (-1 + GtError) or, for the void filter, printed and aborted.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <stdbool.h>
+
+#include "core/error_api.h"
+#include "core/ma_api.h"
+#include "core/str_api.h"
+#include "core/types_api.h"
+#include "core/array_api.h"
+#include "gt_scaffolder_graph.h"
+#include "gt_scaffolder_parser.h"
+#include "gt_scaffolder_algorithms.h"
+
+#include "gtscaffold_b200.h"
+
+#define B200_LINE 1024            /* the reference's BUFSIZE, parser.c:30 */
+
+/* ------------------------------------------------------------------ context */
+
+static gtsb_context *b200_ctx = NULL;
+
+static void b200_release(void)
+{
+  gtsb_destroy(b200_ctx);
+  b200_ctx = NULL;
+}
+
+static gtsb_context *b200_context(void)
+{
+  if (b200_ctx == NULL) {
+    const char *dev = getenv("GTSB_DEVICE");
+    if (gtsb_create(&b200_ctx, dev != NULL ? atoi(dev) : 0) != 0) {
+      b200_ctx = NULL;
+      return NULL;
+    }
+    atexit(b200_release);
+  }
+  return b200_ctx;
+}
+
+static void b200_die(const char *where)
+{
+  fprintf(stderr, "gt_scaffolder (B200): %s: %s\n", where,
+          b200_ctx != NULL ? gtsb_error(b200_ctx) : "no CUDA device (there is no CPU fallback)");
+  exit(EXIT_FAILURE);
+}
+
+/* ------------------------------------------------------------------ records */
+
+typedef struct {
+  uint64_t n, cap;
+  uint32_t *root, *ctg;
+  int32_t *dist;
+  float *std_dev;
+  uint8_t *flags;
+  GtUword *num_pairs;
+} B200Records;
+
+static void records_push(B200Records *r, uint32_t root, uint32_t ctg, GtWord dist,
+                         GtUword num_pairs, float std_dev, bool sense, bool same)
+{
+  if (r->n == r->cap) {
+    r->cap = r->cap != 0 ? 2 * r->cap : 1024;
+    r->root = gt_realloc(r->root, r->cap * sizeof (*r->root));
+    r->ctg = gt_realloc(r->ctg, r->cap * sizeof (*r->ctg));
+    r->dist = gt_realloc(r->dist, r->cap * sizeof (*r->dist));
+    r->std_dev = gt_realloc(r->std_dev, r->cap * sizeof (*r->std_dev));
+    r->flags = gt_realloc(r->flags, r->cap * sizeof (*r->flags));
+    r->num_pairs = gt_realloc(r->num_pairs, r->cap * sizeof (*r->num_pairs));
+  }
+  r->root[r->n] = root;
+  r->ctg[r->n] = ctg;
+  r->dist[r->n] = (int32_t) dist;
+  r->std_dev[r->n] = std_dev;
+  r->flags[r->n] = (uint8_t) ((sense ? GTSB_SENSE : 0u) | (same ? GTSB_SAME : 0u));
+  r->num_pairs[r->n] = num_pairs;
+  r->n++;
+}
+
+static void records_free(B200Records *r)
+{
+  gt_free(r->root);
+  gt_free(r->ctg);
+  gt_free(r->dist);
+  gt_free(r->std_dev);
+  gt_free(r->flags);
+  gt_free(r->num_pairs);
+  memset(r, 0, sizeof (*r));
+}
+
+/* `.de` text -> integer records, in file order.  Which tokens count as
+   records, which lines and records are skipped (unknown root: whole line;
+   unknown partner: that record) and where the direction switches follow
+   parser.c:323-388 token for token. */
+static int read_de_records(const char *filename, const GtScaffolderGraph *graph,
+                           B200Records *recs, GtError *err)
+{
+  char line[B200_LINE + 1], hdr[B200_LINE + 1], *tok;
+  GtWord dist, num_pairs;
+  float std_dev;
+  GtScaffolderGraphVertex *root, *ctg;
+  GtStr *key;
+  FILE *fp = fopen(filename, "rb");
+
+  if (fp == NULL) {
+    gt_error_set(err, " can not read distance file %s ", filename);
+    return -1;
+  }
+  key = gt_str_new();
+  while (fgets(line, B200_LINE, fp) != NULL) {
+    bool sense = true;
+    line[strlen(line) - 1] = '\0';
+    tok = strtok(line, " ");
+    if (tok == NULL)
+      continue;
+    gt_str_set(key, tok);
+    if (!gt_scaffolder_graph_get_vertex(graph, &root, key))
+      continue;
+    for (; tok != NULL; tok = strtok(NULL, " ")) {
+      if (sscanf(tok, "%[^>,]," GT_WD "," GT_WD ",%f", hdr, &dist, &num_pairs, &std_dev) == 4) {
+        const size_t len = strlen(hdr);
+        const bool same = hdr[len - 1] == '+';
+        hdr[len - 1] = '\0';
+        gt_str_set(key, hdr);
+        if (!gt_scaffolder_graph_get_vertex(graph, &ctg, key))
+          continue;
+        if (dist > INT32_MAX || dist < INT32_MIN) {
+          gt_error_set(err, "distance " GT_WD " in %s does not fit the device's 32-bit distance column",
+                       dist, filename);
+          gt_str_delete(key);
+          fclose(fp);
+          return -1;
+        }
+        records_push(recs, (uint32_t) (root - graph->vertices), (uint32_t) (ctg - graph->vertices),
+                     dist, (GtUword) num_pairs, std_dev, sense, same);
+      } else if (*tok == ';') {
+        sense = !sense;
+      }
+    }
+  }
+  gt_str_delete(key);
+  fclose(fp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ vertices */
+
+typedef struct {
+  uint32_t *seq_len;
+  float *astat, *copy_num;
+  uint8_t *vstate;
+} B200Vertices;
+
+static int vertices_flatten(const GtScaffolderGraph *graph, B200Vertices *v, GtError *err)
+{
+  GtUword i;
+  const GtUword n = graph->nof_vertices;
+  v->seq_len = gt_malloc((n + 1) * sizeof (*v->seq_len));
+  v->astat = gt_malloc((n + 1) * sizeof (*v->astat));
+  v->copy_num = gt_malloc((n + 1) * sizeof (*v->copy_num));
+  v->vstate = gt_malloc(n + 1);
+  for (i = 0; i < n; i++) {
+    if (graph->vertices[i].seq_len > (GtUword) INT32_MAX) {
+      if (err != NULL)
+        gt_error_set(err, "contig longer than 2^31-1 is not supported by the device path");
+      return -1;
+    }
+    v->seq_len[i] = (uint32_t) graph->vertices[i].seq_len;
+    v->astat[i] = graph->vertices[i].astat;
+    v->copy_num[i] = graph->vertices[i].copy_num;
+    v->vstate[i] = (uint8_t) graph->vertices[i].state;
+  }
+  return 0;
+}
+
+static void vertices_free(B200Vertices *v)
+{
+  gt_free(v->seq_len);
+  gt_free(v->astat);
+  gt_free(v->copy_num);
+  gt_free(v->vstate);
+}
+
+/* ------------------------------------------------------------------ new_from_file */
+
+int gt_scaffolder_graph_new_from_file(GtScaffolderGraph **graph_par,
+                                      const char *ctg_filename,
+                                      GtUword min_ctg_len,
+                                      const char *dist_filename,
+                                      bool astat_is_annotated,
+                                      GtError *err)
+{
+  GtScaffolderGraph *graph = NULL;
+  GtUword nof_contigs = 0, upper_bound = 0;
+  B200Records recs;
+  B200Vertices vert;
+  int had_err;
+
+  memset(&recs, 0, sizeof recs);
+  memset(&vert, 0, sizeof vert);
+
+  /* host text: the reference's own FASTA passes and `.de` validation; the
+     latter also sorts the vertices (=> vertex ids) and sizes every vertex's
+     edge-pointer array (parser.c:172, 278-283) */
+  had_err = gt_scaffolder_parser_count_contigs(ctg_filename, min_ctg_len, &nof_contigs, err);
+  if (had_err == 0) {
+    gt_assert(nof_contigs > 0);                                     /* graph.c:37 */
+    graph = gt_malloc(sizeof (*graph));
+    graph->edges = NULL;
+    graph->nof_edges = graph->max_nof_edges = 0;
+    graph->vertices = gt_malloc(sizeof (*graph->vertices) * nof_contigs);
+    graph->nof_vertices = 0;
+    graph->max_nof_vertices = nof_contigs;
+    had_err = gt_scaffolder_parser_read_contigs(graph, ctg_filename, min_ctg_len,
+                                                astat_is_annotated, err);
+  }
+  if (had_err == 0)
+    had_err = gt_scaffolder_parser_count_distances(graph, dist_filename, &upper_bound, err);
+  if (had_err == 0) {
+    if (nof_contigs == 1 && upper_bound == 0) {                     /* graph.c:389-393 */
+      fprintf(stderr, "Graph only contains 1 vertex and no edges: "
+                      "Did not perform scaffolding!\n");
+      exit(0);
+    }
+    graph->edges = gt_malloc(sizeof (*graph->edges) * upper_bound);
+    graph->nof_edges = 0;
+    graph->max_nof_edges = upper_bound;
+    had_err = read_de_records(dist_filename, graph, &recs, err);
+  }
+  if (had_err == 0)
+    had_err = vertices_flatten(graph, &vert, err);
+
+  /* device: records -> edges in creation order + adjacency lists */
+  if (had_err == 0) {
+    gtsb_context *c = b200_context();
+    const GtUword V = graph->nof_vertices;
+    uint32_t *row_ptr = NULL, *dst = NULL, *eid = NULL, *win = NULL;
+    int32_t *dist = NULL;
+    float *std_dev = NULL;
+    uint8_t *flags = NULL;
+    uint64_t E = 0;
+    if (c == NULL) {
+      gt_error_set(err, "no CUDA device available (the B200 path has no CPU fallback)");
+      had_err = -1;
+    }
+    if (had_err == 0 &&
+        (gtsb_want_win_rec(c, 1) != 0 ||
+         gtsb_set_vertices_host(c, V, vert.seq_len, vert.astat, vert.copy_num) != 0 ||
+         gtsb_set_records_host(c, recs.n, recs.root, recs.ctg, recs.dist, recs.std_dev, recs.flags) != 0 ||
+         gtsb_build(c) != 0)) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      had_err = -1;
+    }
+    if (had_err == 0) {
+      E = gtsb_nof_edges(c);
+      if (E > graph->max_nof_edges) {
+        gt_error_set(err, "device built more edges than the reference's bound");
+        had_err = -1;
+      }
+    }
+    if (had_err == 0) {
+      row_ptr = gt_malloc((V + 1) * sizeof (*row_ptr));
+      dst = gt_malloc((E + 1) * sizeof (*dst));
+      eid = gt_malloc((E + 1) * sizeof (*eid));
+      win = gt_malloc((E + 1) * sizeof (*win));
+      dist = gt_malloc((E + 1) * sizeof (*dist));
+      std_dev = gt_malloc((E + 1) * sizeof (*std_dev));
+      flags = gt_malloc(E + 1);
+      if (gtsb_get_csr(c, row_ptr, dst, dist, std_dev, flags, eid, win, NULL) != 0) {
+        gt_error_set(err, "%s", gtsb_error(c));
+        had_err = -1;
+      }
+    }
+    if (had_err == 0) {
+      GtUword v;
+      for (v = 0; v < V; v++) {
+        GtScaffolderGraphVertex *vx = graph->vertices + v;
+        uint32_t s;
+        vx->nof_edges = 0;
+        for (s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
+          GtScaffolderGraphEdge *e = graph->edges + eid[s];
+          e->start = vx;
+          e->end = graph->vertices + dst[s];
+          e->dist = dist[s];
+          e->std_dev = std_dev[s];
+          e->num_pairs = recs.num_pairs[win[s] & ~GTSB_WIN_SEEDED];
+          e->state = GIS_UNVISITED;
+          e->sense = (flags[s] & GTSB_SENSE) != 0;
+          e->same = (flags[s] & GTSB_SAME) != 0;
+          vx->edges[vx->nof_edges++] = e;                           /* graph.c:166-167 */
+        }
+      }
+      graph->nof_edges = E;
+    }
+    gt_free(row_ptr);
+    gt_free(dst);
+    gt_free(eid);
+    gt_free(win);
+    gt_free(dist);
+    gt_free(std_dev);
+    gt_free(flags);
+  }
+
+  records_free(&recs);
+  vertices_free(&vert);
+  if (had_err != 0) {
+    gt_scaffolder_graph_delete(graph);
+    graph = NULL;
+  }
+  *graph_par = graph;
+  return had_err;
+}
+
+/* ------------------------------------------------------------------ graph <-> device */
+
+typedef struct {
+  uint64_t V, E;
+  uint32_t *row_ptr, *dst;
+  int32_t *dist;
+  float *std_dev;
+  uint8_t *flags, *estate;
+  GtScaffolderGraphEdge **slot_edge;
+  B200Vertices vert;
+} B200Flat;
+
+static void flat_free(B200Flat *f)
+{
+  gt_free(f->row_ptr);
+  gt_free(f->dst);
+  gt_free(f->dist);
+  gt_free(f->std_dev);
+  gt_free(f->flags);
+  gt_free(f->estate);
+  gt_free(f->slot_edge);
+  vertices_free(&f->vert);
+}
+
+/* reverse edge of e (end -> start): the constructor creates edges in mutual
+   pairs 2k / 2k+1 (parser.c:374-377); anything else is searched */
+static const GtScaffolderGraphEdge *reverse_edge(const GtScaffolderGraph *graph,
+                                                 const GtScaffolderGraphEdge *e)
+{
+  const GtUword i = (GtUword) (e - graph->edges);
+  const GtUword j = i ^ 1u;
+  GtUword k;
+  if (i < graph->nof_edges && j < graph->nof_edges &&
+      graph->edges[j].start == e->end && graph->edges[j].end == e->start)
+    return graph->edges + j;
+  for (k = 0; k < e->end->nof_edges; k++)
+    if (e->end->edges[k]->end == e->start)
+      return e->end->edges[k];
+  return NULL;
+}
+
+/* GtScaffolderGraph -> CSR in adjacency order + states; -1 with a message on
+   stderr if the graph is outside what the device path represents */
+static int graph_flatten(const GtScaffolderGraph *graph, B200Flat *f, const char *where)
+{
+  GtUword v, k;
+  uint64_t s = 0;
+  memset(f, 0, sizeof (*f));
+  f->V = graph->nof_vertices;
+  if (vertices_flatten(graph, &f->vert, NULL) != 0) {
+    fprintf(stderr, "gt_scaffolder (B200): %s: contig longer than 2^31-1\n", where);
+    return -1;
+  }
+  for (v = 0; v < graph->nof_vertices; v++)
+    f->E += graph->vertices[v].nof_edges;
+  f->row_ptr = gt_malloc((f->V + 1) * sizeof (*f->row_ptr));
+  f->dst = gt_malloc((f->E + 1) * sizeof (*f->dst));
+  f->dist = gt_malloc((f->E + 1) * sizeof (*f->dist));
+  f->std_dev = gt_malloc((f->E + 1) * sizeof (*f->std_dev));
+  f->flags = gt_malloc(f->E + 1);
+  f->estate = gt_malloc(f->E + 1);
+  f->slot_edge = gt_malloc((f->E + 1) * sizeof (*f->slot_edge));
+  for (v = 0; v < graph->nof_vertices; v++) {
+    const GtScaffolderGraphVertex *vx = graph->vertices + v;
+    f->row_ptr[v] = (uint32_t) s;
+    for (k = 0; k < vx->nof_edges; k++, s++) {
+      GtScaffolderGraphEdge *e = vx->edges[k];
+      const GtScaffolderGraphEdge *r = reverse_edge(graph, e);
+      if (r == NULL || e->start != vx) {
+        fprintf(stderr, "gt_scaffolder (B200): %s: edge without a reverse edge; the device path "
+                        "handles the graphs gt_scaffolder_graph_new_from_file builds\n", where);
+        return -1;
+      }
+      if (e->dist > INT32_MAX || e->dist < INT32_MIN) {
+        fprintf(stderr, "gt_scaffolder (B200): %s: distance outside 32 bits\n", where);
+        return -1;
+      }
+      f->dst[s] = (uint32_t) (e->end - graph->vertices);
+      f->dist[s] = (int32_t) e->dist;
+      f->std_dev[s] = e->std_dev;
+      f->flags[s] = (uint8_t) ((e->sense ? GTSB_SENSE : 0u) | (e->same ? GTSB_SAME : 0u) |
+                               (r->sense ? GTSB_RSENSE : 0u) | (r->same ? GTSB_RSAME : 0u));
+      f->estate[s] = (uint8_t) e->state;
+      f->slot_edge[s] = e;
+    }
+  }
+  f->row_ptr[f->V] = (uint32_t) s;
+  return 0;
+}
+
+static int graph_upload(gtsb_context *c, const B200Flat *f)
+{
+  return gtsb_set_graph_host(c, f->V, f->E, f->row_ptr, f->dst, f->dist, f->std_dev, f->flags,
+                             f->vert.seq_len, f->vert.astat, f->vert.copy_num, f->vert.vstate,
+                             f->estate);
+}
+
+/* device states -> graph->vertices[].state / edge->state */
+static int graph_fetch_states(gtsb_context *c, GtScaffolderGraph *graph, B200Flat *f)
+{
+  uint64_t s;
+  GtUword v;
+  if (gtsb_get_vertex_states(c, f->vert.vstate) != 0 ||
+      gtsb_get_csr(c, NULL, NULL, NULL, NULL, NULL, NULL, NULL, f->estate) != 0)
+    return -1;
+  for (v = 0; v < graph->nof_vertices; v++)
+    graph->vertices[v].state = (GraphItemState) f->vert.vstate[v];
+  for (s = 0; s < f->E; s++)
+    f->slot_edge[s]->state = (GraphItemState) f->estate[s];
+  return 0;
+}
+
+/* ------------------------------------------------------------------ mark_repeats */
+
+int gt_scaffolder_graph_mark_repeats(const char *filename,
+                                     GtScaffolderGraph *graph,
+                                     float copy_num_cutoff,
+                                     float astat_cutoff,
+                                     GtError *err)
+{
+  const bool have_file = strlen(filename) != 0;
+  int had_err = 0;
+
+  if (have_file) {
+    /* `.astat` text -> per-vertex attributes, algorithms.c:118-149 */
+    char line[B200_LINE + 1], hdr[B200_LINE + 1];
+    FILE *fp = fopen(filename, "rb");
+    if (fp == NULL) {
+      gt_error_set(err, "can not read A-statistic file %s", filename);
+      return -1;
+    }
+    GtStr *key = gt_str_new();
+    while (fgets(line, B200_LINE, fp) != NULL) {
+      GtWord n1 = 0, n2 = 0, n3 = 0;
+      float copy_num = 0.0, astat = 0.0;
+      GtScaffolderGraphVertex *ctg;
+      line[strlen(line) - 1] = '\0';
+      if (sscanf(line, "%s\t" GT_WD "\t" GT_WD "\t" GT_WD "\t%f\t%f", hdr, &n1, &n2, &n3,
+                 &copy_num, &astat) != 6) {
+        gt_error_set(err, "Invalid record in A-statistic file %s", filename);
+        had_err = -1;
+        break;
+      }
+      gt_str_set(key, hdr);
+      if (gt_scaffolder_graph_get_vertex(graph, &ctg, key)) {
+        ctg->astat = astat;
+        ctg->copy_num = copy_num;
+      }
+    }
+    gt_str_delete(key);
+    fclose(fp);
+  }
+
+  if (had_err == 0) {
+    B200Flat f;
+    gtsb_context *c = b200_context();
+    if (c == NULL) {
+      gt_error_set(err, "no CUDA device available (the B200 path has no CPU fallback)");
+      return -1;
+    }
+    if (graph_flatten(graph, &f, "mark_repeats") != 0) {
+      gt_error_set(err, "graph cannot be represented on the device");
+      had_err = -1;
+    } else if (graph_upload(c, &f) != 0 ||
+               gtsb_mark_repeats(c, copy_num_cutoff, astat_cutoff, have_file ? 1 : 0) != 0 ||
+               graph_fetch_states(c, graph, &f) != 0) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      had_err = -1;
+    }
+    flat_free(&f);
+  }
+  return had_err;
+}
+
+/* ------------------------------------------------------------------ filter */
+
+void gt_scaffolder_graph_filter(GtScaffolderGraph *graph,
+                                float pcutoff,
+                                float cncutoff,
+                                GtWord ocutoff)
+{
+  B200Flat f;
+  gtsb_context *c = b200_context();
+  if (c == NULL)
+    b200_die("gt_scaffolder_graph_filter");
+  if (graph_flatten(graph, &f, "filter") != 0)
+    exit(EXIT_FAILURE);
+  if (graph_upload(c, &f) != 0 || gtsb_filter(c, pcutoff, cncutoff, (int64_t) ocutoff) != 0 ||
+      graph_fetch_states(c, graph, &f) != 0)
+    b200_die("gt_scaffolder_graph_filter");
+  flat_free(&f);
+}
