@@ -70,9 +70,9 @@ struct gtsb_context {
   DevBuf vattr, astat, seq_len_in, copy_num_in;
   DevBuf root, ctg, dist, std_dev, flags;
   // graph
-  DevBuf row_ptr, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
-  DevBuf rs, re, vid, pos;      // line layout
-  DevBuf ls, tile_cnt, tile_off, rf, cnt_in, bptr2, cursor2, seg_creators, seg_k, tmp_ent, tmp_dest,
+  DevBuf row_ptr, srcp, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
+  DevBuf vid, pos;              // line layout
+  DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
       tmp_cursor, bucket, corrections, lineless_flag, lineless_rank;
   DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
   uint32_t fallback_reason = 0;
@@ -186,17 +186,6 @@ __global__ void k_pack_vattr(uint32_t V, const uint32_t *__restrict__ seq_len,
   }
 }
 
-// big-row list + max degree for a graph that did not come from gtsb_build
-__global__ void k_classify_rows(uint32_t V, const uint32_t *__restrict__ row_ptr,
-                                uint32_t *__restrict__ big_rows, uint32_t *__restrict__ counters) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t d = 0;
-  if (v < V) d = row_ptr[v + 1] - row_ptr[v];
-  const bool big = d > BIG_ROW;
-  if (big) atomicMax(&counters[CNT_MAX_DEG], d);
-  warp_append(big, v, big_rows, &counters[CNT_BIG_ROWS]);
-}
-
 int vertices_common(gtsb_context *c, uint64_t V) {
   if (V > GTSB_MAX_VERTICES) return fail(c, "too many vertices (%llu > %u)", (unsigned long long) V,
                                          GTSB_MAX_VERTICES);
@@ -218,18 +207,12 @@ int vertices_common(gtsb_context *c, uint64_t V) {
 GraphArgs graph_args(gtsb_context *c) {
   GraphArgs g{};
   g.V = (uint32_t) c->V;
+  g.E = (uint32_t) c->E;
   g.sm_count = c->sm_count;
-  if (c->line_layout) {
-    g.rs = c->rs.as<uint32_t>();
-    g.re = c->re.as<uint32_t>();
-    g.vid = c->vid.as<uint32_t>();
-    g.pos = c->pos.as<uint32_t>();
-  } else {
-    g.pos = nullptr;
-    g.rs = c->row_ptr.as<uint32_t>();
-    g.re = c->row_ptr.as<uint32_t>() + 1;
-    g.vid = nullptr;
-  }
+  g.row_ptr = c->row_ptr.as<uint32_t>();
+  g.vid = c->line_layout ? c->vid.as<uint32_t>() : nullptr;
+  g.pos = c->line_layout ? c->pos.as<uint32_t>() : nullptr;
+  g.srcp = c->srcp.as<uint32_t>();
   g.dst = c->dst.as<uint32_t>();
   g.dist = c->edist.as<int32_t>();
   g.std_dev = c->estd.as<float>();
@@ -287,6 +270,7 @@ void prof_collect(gtsb_context *c) {
 }
 
 int ensure_rows(gtsb_context *c, uint64_t R) {
+  ENSURE(c->srcp, 2 * R * 4 + 256);
   ENSURE(c->dst, 2 * R * 4);
   ENSURE(c->edist, 2 * R * 4);
   ENSURE(c->estd, 2 * R * 4);
@@ -301,21 +285,20 @@ int ensure_rows(gtsb_context *c, uint64_t R) {
 int do_build_lines(gtsb_context *c) {
   const uint64_t V = c->V, R = c->R;
   cudaStream_t s = c->stream;
-  const uint32_t nseg = (uint32_t) ((V + SEG_LINES - 1) / SEG_LINES);
   const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
   ENSURE(c->pos, (V + 1) * 4);
   ENSURE(c->vid, (V + 1) * 4);
   ENSURE(c->ls, (V + 2) * 4);
-  ENSURE(c->rs, (V + 1) * 4);
-  ENSURE(c->re, (V + 1) * 4);
+  ENSURE(c->row_ptr, (V + 2) * 4);
+  ENSURE(c->pc, R * 4);
+  ENSURE(c->nown, (V + 2) * 4);
+  ENSURE(c->k0, (V + 2) * 4);
   ENSURE(c->tile_cnt, (ntiles + 2) * 4);
   ENSURE(c->tile_off, (ntiles + 2) * 4);
   ENSURE(c->rf, R);
   ENSURE(c->cnt_in, (V + 2) * 4);
   ENSURE(c->bptr2, (V + 2) * 4);
   ENSURE(c->cursor2, (V + 2) * 4);
-  ENSURE(c->seg_creators, (nseg + 2) * 4);
-  ENSURE(c->seg_k, (nseg + 2) * 4);
   ENSURE(c->tmp_ent, R * sizeof(uint4));
   ENSURE(c->tmp_dest, R * 4);
   ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
@@ -332,6 +315,7 @@ int do_build_lines(gtsb_context *c) {
   CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
   CK(cudaMemsetAsync(c->pos.p, 0xFF, (V + 1) * 4, s));
   CK(cudaMemsetAsync(c->cnt_in.p, 0, (V + 2) * 4, s));
+  CK(cudaMemsetAsync(c->nown.p, 0, (V + 2) * 4, s));
   CK(cudaMemsetAsync(c->cursor2.p, 0, (V + 2) * 4, s));
   CK(cudaMemsetAsync(c->estate.p, 0, 2 * R ? 2 * R : 1, s));   // GIS_UNVISITED, graph.c:162
   CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, s));
@@ -358,8 +342,9 @@ int do_build_lines(gtsb_context *c) {
   a.cnt_in = c->cnt_in.as<uint32_t>();
   a.bptr = c->bptr2.as<uint32_t>();
   a.cursor = c->cursor2.as<uint32_t>();
-  a.seg_creators = c->seg_creators.as<uint32_t>();
-  a.seg_k = c->seg_k.as<uint32_t>();
+  a.pc = c->pc.as<uint32_t>();
+  a.nown = c->nown.as<uint32_t>();
+  a.k0 = c->k0.as<uint32_t>();
   a.tmp_ent = c->tmp_ent.as<uint4>();
   a.bucket = c->bucket.as<uint4>();
   a.corrections = c->corrections.as<uint4>();
@@ -370,8 +355,8 @@ int do_build_lines(gtsb_context *c) {
   a.scan_scratch = c->scan_scratch.as<uint32_t>();
   a.counters = c->counters.as<uint32_t>();
   a.big_rows = c->big_rows.as<uint32_t>();
-  a.rs = c->rs.as<uint32_t>();
-  a.re = c->re.as<uint32_t>();
+  a.row_ptr = c->row_ptr.as<uint32_t>();
+  a.srcp = c->srcp.as<uint32_t>();
   a.dst = c->dst.as<uint32_t>();
   a.eid = c->eid.as<uint32_t>();
   a.edist = c->edist.as<int32_t>();
@@ -427,12 +412,7 @@ int do_build(gtsb_context *c) {
   ENSURE(c->creator_flag, R);
   ENSURE(c->large_list, (V + 1) * sizeof(uint2));
   ENSURE(c->big_rows, (V + 1) * 4);
-  ENSURE(c->dst, 2 * R * 4);
-  ENSURE(c->edist, 2 * R * 4);
-  ENSURE(c->estd, 2 * R * 4);
-  ENSURE(c->eflags, 2 * R);
-  ENSURE(c->eid, 2 * R * 4);
-  ENSURE(c->estate, 2 * R);
+  if (ensure_rows(c, R) != 0) return -1;
   if (c->want_win) ENSURE(c->win_rec, 2 * R * 4);
 
   CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
@@ -505,6 +485,9 @@ int do_build(gtsb_context *c) {
   c->stats.big_rows = c->n_big_rows;
   c->stats.max_degree = c->max_deg;
   c->have_graph = true;
+  launch_fill_srcp(graph_args(c), c->srcp.as<uint32_t>(), nullptr, s);   // big rows: listed by the emit pass
+  c->stats.kernel_launches += V ? 1 : 0;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -512,13 +495,22 @@ int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int us
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_mark_repeats: no graph (call gtsb_build or gtsb_set_graph_host)");
   c->csr_exported = false;
-  launch_mark_repeats(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
-  c->stats.kernel_launches += c->V ? 2 : 0;
+  FilterArgs a{};
+  a.g = graph_args(c);
+  a.rep_pred = c->rep_pred.as<uint8_t>();
+  launch_vertex_facts(a, 1, cn_cutoff, astat_cutoff, use_cn, c->stream);
+  launch_repeat_edges(a.g, a.rep_pred, c->stream);
+  c->stats.kernel_launches += (c->V ? 1 : 0) + (c->E ? 1 : 0);
   CK(cudaGetLastError());
   return 0;
 }
 
-int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, bool fused_repeats = false) {
+// fused = the three stages back to back on a fresh graph (gtsb_pipeline): the
+// repeat predicate is evaluated inside the vertex-facts pass and the REPEAT edge
+// marks (pred(v) || pred(w)) are derived by the final pass instead of being
+// stored first and overwritten later
+int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, bool fused = false,
+              float cn_cutoff = 0.f, float astat_cutoff = 0.f, int use_cn = 0) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
   if (get_ambig(c, pcutoff) != 0) return -1;
@@ -551,25 +543,25 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   a.poly_new = c->poly_new.as<uint32_t>();
   a.gbits = c->gbits.as<uint8_t>();
   a.fstat = c->fstat.as<uint8_t>();
+  a.dirty = c->dirty.as<uint8_t>();
+  a.rep_pred = c->rep_pred.as<uint8_t>();
   a.work_a = c->work_a.as<uint32_t>();
   a.work_b = c->work_b.as<uint32_t>();
   a.big_scratch = c->big_scratch.as<uint8_t>();
   a.vinfo = c->vinfo.as<uint2>();
   a.vres = c->vres.as<uint32_t>();
-  a.dirty = c->dirty.as<uint8_t>();
-  a.fused_repeats = fused_repeats ? 1 : 0;
+  a.fused_repeats = fused ? 1 : 0;
 
   uint32_t *cnt = c->counters.as<uint32_t>();
   CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
   CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (V + 1) * 4, s));
   CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (V + 1) * 4, s));
-
   CK(cudaMemsetAsync(c->dirty.p, 0, V + 1, s));
+  CK(cudaMemsetAsync(c->gbits.p, 0, V + 1, s));
   // phase 1: who proposes whom (+ the static overlap answer of every small row)
-  launch_vinfo(a, s);
-  launch_pairs2(a, s);
-  launch_pairs_big(a, s);
-  c->stats.kernel_launches += (V ? 2 : 0) + (c->n_big_rows ? 1 : 0);
+  launch_vertex_facts(a, fused ? 1 : 0, cn_cutoff, astat_cutoff, use_cn, s);
+  launch_pairs(a, s);
+  c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   if (read_counters(c) != 0) return -1;
   if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
   if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
@@ -591,16 +583,16 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   }
   // phase 2: fire candidates (static answer, recomputed next to polymorphic
   // vertices), then the order-respecting fire fixpoint
-  launch_filter_overlap(a, s);
-  c->stats.kernel_launches += (V ? 1 : 0) + (c->n_big_rows ? 1 : 0);
+  CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
+  launch_fire_init(a, s);
+  c->stats.kernel_launches += (V ? 1 : 0) + (V && c->n_big_rows ? 1 : 0);
   c->stats.fire_rounds = 0;
   uint32_t *win = a.work_b, *wout = a.work_a;
   int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
   uint32_t n_in = 0;
   if (ocutoff >= 0 && V) {
-    CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
     launch_fire_dense(a, a.work_b, cnt + CNT_WORK_B, s);
-    c->stats.kernel_launches += 1;
+    c->stats.kernel_launches += E ? 1 : 0;
     c->stats.fire_rounds++;
     if (read_counters(c) != 0) return -1;
     n_in = c->h_counters[CNT_WORK_B];
@@ -617,8 +609,8 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
     uint32_t *t = win; win = wout; wout = t;
     int ti = in_idx; in_idx = out_idx; out_idx = ti;
   }
-  launch_finalize2(a, fused_repeats ? c->rep_pred.as<uint8_t>() : nullptr, s);
-  c->stats.kernel_launches += V ? 2 : 0;
+  launch_finalize(a, s);
+  c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   CK(cudaGetLastError());
   return 0;
 }
@@ -639,8 +631,8 @@ int export_csr(gtsb_context *c) {
   ExportArgs x{};
   x.V = (uint32_t) V;
   x.pos = c->pos.as<uint32_t>();
-  x.rs = c->rs.as<uint32_t>();
-  x.re = c->re.as<uint32_t>();
+  x.vid = c->vid.as<uint32_t>();
+  x.row_ptr_p = c->row_ptr.as<uint32_t>();
   x.dst = c->dst.as<uint32_t>();
   x.eid = c->eid.as<uint32_t>();
   x.dist = c->edist.as<int32_t>();
@@ -702,9 +694,9 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
                     &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
-                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->rs, &c->re, &c->vid, &c->pos, &c->ls,
+                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
-                    &c->seg_creators, &c->seg_k, &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
+                    &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
                     &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg};
   for (DevBuf *b : bufs) release(*b);
@@ -818,6 +810,7 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
   if (E >= 0xFFFFFFF0ull) return fail(c, "too many edges");
   cudaStream_t s = c->stream;
   ENSURE(c->row_ptr, (V + 1) * 4);
+  ENSURE(c->srcp, E * 4 + 256);
   ENSURE(c->dst, E * 4);
   ENSURE(c->edist, E * 4);
   ENSURE(c->estd, E * 4);
@@ -834,12 +827,10 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
   }
   if (V) CK(cudaMemcpyAsync(c->vstate.p, vstate, V, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
-  if (V) {
-    k_classify_rows<<<(uint32_t) ((V + 255) / 256), 256, 0, s>>>((uint32_t) V, c->row_ptr.as<uint32_t>(),
-                                                                  c->big_rows.as<uint32_t>(),
-                                                                  c->counters.as<uint32_t>());
-    c->stats.kernel_launches++;
-  }
+  c->E = E;
+  c->line_layout = false;
+  launch_fill_srcp(graph_args(c), c->srcp.as<uint32_t>(), c->big_rows.as<uint32_t>(), s);
+  c->stats.kernel_launches += V ? 1 : 0;
   if (read_counters(c) != 0) return -1;
   c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
   c->max_deg = c->h_counters[CNT_MAX_DEG];
@@ -883,17 +874,7 @@ int gtsb_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
   if (do_build(c) != 0) return -1;
-  {
-    // fresh graph: every edge state is UNVISITED, so the REPEAT edge marks of
-    // mark_repeats (pred(v) || pred(w)) need not be stored before the filter
-    // overwrites most of them; the final pass derives them
-    ProfScope ps_(c);
-    c->csr_exported = false;
-    launch_repeat_vertices(graph_args(c), c->rep_pred.as<uint8_t>(), cn_cutoff, astat_cutoff, use_cn, c->stream);
-    c->stats.kernel_launches += c->V ? 1 : 0;
-  }
-  if (do_filter(c, pcutoff, cncutoff, ocutoff, true) != 0) return -1;
-  return 0;
+  return do_filter(c, pcutoff, cncutoff, ocutoff, true, cn_cutoff, astat_cutoff, use_cn);
 }
 
 uint64_t gtsb_nof_edges(const gtsb_context *c) { return c ? c->E : 0; }
@@ -932,6 +913,8 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
     if (estate) CK(cudaMemcpyAsync(estate, ll ? c->x_estate.p : c->estate.p, E, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
+  if (!ll && flags != nullptr)
+    for (uint64_t i = 0; i < E; i++) flags[i] &= 0x0Fu;          // F_LT is device-only
   return 0;
 }
 

@@ -36,12 +36,14 @@ namespace gtsb {
 
 constexpr uint32_t UNSET = 0xFFFFFFFFu;
 constexpr int HEAD_TILE = 4096;             // records per block in the head passes
-constexpr uint32_t RF_UP = 1, RF_FIRST = 2; // per-record flag byte
+constexpr uint32_t RF_UP = 1, RF_FIRST = 2;  // per-record flag byte
+constexpr uint32_t RF_LT = 4;                // id(ctg) < id(root): F_LT of the record's own slot
 
-// mailbox entry (uint4): x = k of the creator, y = src vertex | M_* bits,
-// z = seed dist, w = seed std_dev
+// mailbox entry (uint4): x = k of the creator, y = position of the creator's
+// line | M_* bits, z = seed dist, w = seed std_dev
 constexpr uint32_t M_SEED_SENSE = 1u << 27, M_SEED_SAME = 1u << 28;
 constexpr uint32_t M_FWD_SENSE = 1u << 29, M_FWD_SAME = 1u << 30;
+constexpr uint32_t M_LT = 1u << 31;          // id(creator's root) < id(receiver): F_LT of the twin slot
 
 __device__ __forceinline__ void raise(uint32_t *counters, uint32_t why) {
   atomicOr(&counters[CNT_FALLBACK], why);
@@ -169,17 +171,19 @@ __device__ __forceinline__ void seg_lines(const Build2Args &a, const Seg &g, con
   }
 }
 
-// pass C: classify every record (up / first of its neighbour in the line),
-// count creators per segment and mail per destination position
+// pass C: classify every record (up / first of its neighbour in the line /
+// id order), remember the partner's position, count creators per line and
+// mail per destination position
 __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(smem);
-  uint32_t *s_ctg = s_ls + SEG_LINES + 4;
+  uint32_t *s_nown = s_ls + SEG_LINES + 4;
+  uint32_t *s_ctg = s_nown + SEG_LINES + 4;
   uint8_t *s_line = reinterpret_cast<uint8_t *>(s_ctg + SEG_REC_CAP);
   Seg g;
   const bool ok = seg_open(a, blockIdx.x, g, s_ls);
-  uint32_t creators = 0;
+  for (uint32_t j = threadIdx.x; j < SEG_LINES; j += blockDim.x) s_nown[j] = 0;
   if (ok) {
     seg_lines(a, g, s_ls, s_line);
     for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) s_ctg[r] = a.ctg[g.rec0 + r];
@@ -188,26 +192,28 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
       const uint32_t j = s_line[r], c = s_ctg[r];
       const uint32_t p = g.p0 + j;
       uint8_t rf = 0;
+      uint32_t pc = UNSET;
+      const uint32_t me = a.vid[p];
       if (c >= a.V) {
         atomicOr(&a.counters[CNT_ERROR], 1u);
-      } else if (c == a.vid[p]) {
+      } else if (c == me) {
         atomicOr(&a.counters[CNT_ERROR], 2u);
       } else {
-        const uint32_t pc = a.pos[c];
+        pc = a.pos[c];
         bool first = true;
         for (uint32_t t = s_ls[j] - g.rec0; t < r; t++) first &= s_ctg[t] != c;
-        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u));
-        if (rf == (RF_UP | RF_FIRST)) {
+        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u));
+        if ((rf & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST)) {
           atomicAdd(&a.cnt_in[pc], 1u);
-          creators++;
+          atomicAdd(&s_nown[j], 1u);
         }
       }
       a.rf[g.rec0 + r] = rf;
+      a.pc[g.rec0 + r] = pc;
     }
   }
-  uint32_t total;
-  block_excl_scan(creators, &total);
-  if (threadIdx.x == 0) a.seg_creators[blockIdx.x] = total;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) a.nown[g.p0 + j] = s_nown[j];
 }
 
 __global__ void k2_init_cursors(Build2Args a) {
@@ -224,8 +230,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(smem);
-  uint32_t *s_ctg = s_ls + SEG_LINES + 4;
-  uint32_t *s_pc = s_ctg + SEG_REC_CAP;
+  uint32_t *s_pc = s_ls + SEG_LINES + 4;
   float *s_std = reinterpret_cast<float *>(s_pc + SEG_REC_CAP);
   uint32_t *s_bin = reinterpret_cast<uint32_t *>(s_std + SEG_REC_CAP);   // [3][NB_COARSE]
   uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_bin + 3 * NB_COARSE);
@@ -235,47 +240,46 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   if (!seg_open(a, blockIdx.x, g, s_ls)) return;
   seg_lines(a, g, s_ls, s_line);
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
-    s_ctg[r] = a.ctg[g.rec0 + r];
+    s_pc[r] = a.pc[g.rec0 + r];
     s_std[r] = a.std_dev[g.rec0 + r];
     s_fl[r] = a.flags[g.rec0 + r];
-    const uint8_t rf = a.rf[g.rec0 + r];
-    s_rf[r] = rf;
-    s_pc[r] = rf == (RF_UP | RF_FIRST) ? a.pos[s_ctg[r]] : UNSET;   // destination position
+    s_rf[r] = a.rf[g.rec0 + r];
   }
   for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
   __syncthreads();
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
-    if (s_pc[r] != UNSET) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
+    if ((s_rf[r] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST)) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
     if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
-  // creator rank in record order = k - seg_k: one block scan per 256 records
-  uint32_t carry = a.seg_k[blockIdx.x];
+  // creator rank in record order = k - k0[first line]: one block scan per 256 records
+  uint32_t carry = a.k0[g.p0];
   for (uint32_t base = 0; base < g.n; base += blockDim.x) {
     const uint32_t r = base + threadIdx.x;
-    const bool creator = r < g.n && s_pc[r] != UNSET;
+    const bool creator = r < g.n && (s_rf[r] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST);
     uint32_t total;
     const uint32_t k = carry + block_excl_scan(creator ? 1u : 0u, &total);   // syncs: bin bases visible
     carry += total;
     if (!creator) continue;
-    const uint32_t j = s_line[r], c = s_ctg[r];
+    const uint32_t j = s_line[r], pc = s_pc[r];
     // final flags of edge root->c: strict running maximum over the line's records
     float best = s_std[r];
     uint32_t bf = s_fl[r];
     const uint32_t rb = s_ls[j + 1] - g.rec0;
     for (uint32_t t = r + 1; t < rb; t++)
-      if (s_ctg[t] == c && best < s_std[t]) {
+      if (s_pc[t] == pc && best < s_std[t]) {
         best = s_std[t];
         bf = s_fl[t];
       }
     const uint32_t sf = s_fl[r];
     uint4 e;
     e.x = k;
-    e.y = a.vid[g.p0 + j] | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
-          ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u);
+    e.y = (g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
+          ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u) |
+          ((s_rf[r] & RF_LT) ? 0u : M_LT);
     e.z = (uint32_t) a.dist[g.rec0 + r];
     e.w = __float_as_uint(s_std[r]);
-    const uint32_t pc = s_pc[r], b = pc >> a.coarse_shift;
+    const uint32_t b = pc >> a.coarse_shift;
     const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
     a.tmp_ent[at] = e;
     a.tmp_dest[at] = pc;
@@ -310,18 +314,17 @@ __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
 
 // pass R: resolve every line against its mailbox and write the CSR rows.
 // Thread per mailbox entry (twin-created slots) and per record (own slots), so
-// that neighbouring threads write neighbouring slots.
+// that neighbouring threads write neighbouring slots.  Rows are dense:
+// row_ptr[p] = (mail for positions < p) + (creators of lines < p).
 __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + SEG_ENT_CAP);
   uint32_t *s_bp = s_ls + SEG_LINES + 4;
-  uint32_t *s_row0 = s_bp + SEG_LINES + 4;          // first slot of each row
-  uint32_t *s_k0 = s_row0 + SEG_LINES + 4;          // creators before each line (in the segment)
-  uint32_t *s_nown = s_k0 + SEG_LINES + 4;          // creators of each line
-  uint32_t *s_ctg = s_nown + SEG_LINES + 4;
-  int32_t *s_dist = reinterpret_cast<int32_t *>(s_ctg + SEG_REC_CAP);
+  uint32_t *s_k0 = s_bp + SEG_LINES + 4;            // creators before each line
+  uint32_t *s_pc = s_k0 + SEG_LINES + 4;
+  int32_t *s_dist = reinterpret_cast<int32_t *>(s_pc + SEG_REC_CAP);
   float *s_std = reinterpret_cast<float *>(s_dist + SEG_REC_CAP);
   uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_std + SEG_REC_CAP);
   uint8_t *s_rf = s_fl + SEG_REC_CAP;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   if (!seg_open(a, blockIdx.x, g, s_ls)) return;
   for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) {
     s_bp[j] = a.bptr[g.p0 + j];
-    s_nown[j] = 0;
+    s_k0[j] = a.k0[g.p0 + j];
   }
   __syncthreads();
   const uint32_t ent0 = s_bp[0], nent = s_bp[g.nlines] - ent0;
@@ -343,39 +346,25 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x)
     for (uint32_t e = s_bp[j] - ent0; e < s_bp[j + 1] - ent0; e++) s_eline[e] = (uint8_t) j;
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
-    s_ctg[r] = a.ctg[g.rec0 + r];
+    s_pc[r] = a.pc[g.rec0 + r];
     s_dist[r] = a.dist[g.rec0 + r];
     s_std[r] = a.std_dev[g.rec0 + r];
     s_fl[r] = a.flags[g.rec0 + r];
     s_rf[r] = a.rf[g.rec0 + r];
   }
   for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) s_ent[e] = a.bucket[ent0 + e];
-  __syncthreads();
-  for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
-    if (s_rf[r] == (RF_UP | RF_FIRST)) atomicAdd(&s_nown[s_line[r]], 1u);
-  __syncthreads();
-  // row offsets: capacity prefix of the segment + exclusive scan of the degrees
-  {
-    const uint32_t j = threadIdx.x;              // SEG_LINES <= SEG_THREADS
-    uint32_t deg = 0, nown = 0;
-    if (j < g.nlines) {
-      nown = s_nown[j];
-      deg = (s_bp[j + 1] - s_bp[j]) + nown;
+  // row offsets
+  for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) {
+    const uint32_t p = g.p0 + j;
+    const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
+    a.row_ptr[p] = row0;
+    if (p + 1 == a.V) {
+      a.row_ptr[a.V] = row0 + deg;
+      a.counters[CNT_EDGES] = row0 + deg;
     }
-    uint32_t total;
-    const uint32_t ex = block_excl_scan(deg | (nown << 16), &total);
-    if (j < g.nlines) {
-      const uint32_t p = g.p0 + j;
-      const uint32_t row0 = g.rec0 + ent0 + (ex & 0xFFFFu);
-      s_row0[j] = row0;
-      s_k0[j] = a.seg_k[blockIdx.x] + (ex >> 16);
-      a.rs[p] = row0;
-      a.re[p] = row0 + deg;
-      if (j == 0) atomicAdd(&a.counters[CNT_EDGES], total & 0xFFFFu);
-      if (deg > BIG_ROW) {
-        atomicMax(&a.counters[CNT_MAX_DEG], deg);
-        a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
-      }
+    if (deg > BIG_ROW) {
+      atomicMax(&a.counters[CNT_MAX_DEG], deg);
+      a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
     }
   }
   __syncthreads();
@@ -395,21 +384,24 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     int32_t bdist = (int32_t) m.z;
     uint32_t bf = seedf;
     for (uint32_t t = ra; t < rb; t++)
-      if (s_ctg[t] == u && best < s_std[t]) {                                  // parser.c:362
+      if (s_pc[t] == u && best < s_std[t]) {                                   // parser.c:362
         best = s_std[t];
         bdist = s_dist[t];
         bf = s_fl[t] & (F_SENSE | F_SAME);
       }
-    const uint32_t slot = s_row0[j] + rank;
+    const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
+    const uint32_t slot = row0 + rank;
+    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
     a.dst[slot] = u;
     a.edist[slot] = bdist;
     a.estd[slot] = best;
-    a.eflags[slot] = (uint8_t) (bf | ((m.y & M_FWD_SENSE) ? F_RSENSE : 0u) | ((m.y & M_FWD_SAME) ? F_RSAME : 0u));
+    a.eflags[slot] = (uint8_t) (bf | ((m.y & M_FWD_SENSE) ? F_RSENSE : 0u) | ((m.y & M_FWD_SAME) ? F_RSAME : 0u) |
+                                ((m.y & M_LT) ? F_LT : 0u));
     a.eid[slot] = 2u * m.x + 1u;
     if (bf != seedf) {
       // the creator assumed its twin keeps the seed's flags: tell it otherwise
       const uint32_t at = atomicAdd(&a.counters[CNT_CORRECTIONS], 1u);
-      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, a.vid[g.p0 + j], bf, 0u);
+      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, g.p0 + j, bf, 0u);
       else raise(a.counters, FB_SEGMENT);
     }
   }
@@ -417,7 +409,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   for (uint32_t t = threadIdx.x; t < g.n; t += blockDim.x) {
     const uint32_t rf = s_rf[t];
     if (!(rf & RF_FIRST)) continue;
-    const uint32_t j = s_line[t], c = s_ctg[t];
+    const uint32_t j = s_line[t], c = s_pc[t];
     const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
     const uint32_t ra = s_ls[j] - g.rec0, rb = s_ls[j + 1] - g.rec0;
     if (!(rf & RF_UP)) {                          // down: the creator's mail must be here
@@ -427,22 +419,24 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
       continue;
     }
     uint32_t q = 0;
-    for (uint32_t t2 = ra; t2 < t; t2++) q += s_rf[t2] == (RF_UP | RF_FIRST);
+    for (uint32_t t2 = ra; t2 < t; t2++) q += (s_rf[t2] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST);
     float best = s_std[t];
     int32_t bdist = s_dist[t];
     uint32_t bf = s_fl[t] & (F_SENSE | F_SAME);
     for (uint32_t t2 = t + 1; t2 < rb; t2++)
-      if (s_ctg[t2] == c && best < s_std[t2]) {
+      if (s_pc[t2] == c && best < s_std[t2]) {
         best = s_std[t2];
         bdist = s_dist[t2];
         bf = s_fl[t2] & (F_SENSE | F_SAME);
       }
     const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
-    const uint32_t slot = s_row0[j] + (eb - ea) + q;
+    const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
+    const uint32_t slot = row0 + (eb - ea) + q;
+    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
     a.dst[slot] = c;
     a.edist[slot] = bdist;
     a.estd[slot] = best;
-    a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u));
+    a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u) | ((rf & RF_LT) ? F_LT : 0u));
     a.eid[slot] = 2u * (s_k0[j] + q);
   }
 }
@@ -453,10 +447,9 @@ __global__ void __launch_bounds__(128) k2_corrections(Build2Args a) {
   const uint32_t n = min(a.counters[CNT_CORRECTIONS], a.corrections_cap);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint4 c = a.corrections[i];
-    const uint32_t p = a.pos[c.x];
-    for (uint32_t s = a.rs[p]; s < a.re[p]; s++)
+    for (uint32_t s = a.row_ptr[c.x]; s < a.row_ptr[c.x + 1]; s++)
       if (a.dst[s] == c.y)
-        a.eflags[s] = (uint8_t) ((a.eflags[s] & (F_SENSE | F_SAME)) | ((c.z & F_SENSE) ? F_RSENSE : 0u) |
+        a.eflags[s] = (uint8_t) ((a.eflags[s] & (F_SENSE | F_SAME | F_LT)) | ((c.z & F_SENSE) ? F_RSENSE : 0u) |
                                  ((c.z & F_SAME) ? F_RSAME : 0u));
   }
 }
@@ -464,11 +457,19 @@ __global__ void __launch_bounds__(128) k2_corrections(Build2Args a) {
 // ------------------------------------------------------------------ export to plain CSR
 
 __global__ void __launch_bounds__(256) k2_export_deg(uint32_t V, const uint32_t *__restrict__ pos,
-                                                      const uint32_t *__restrict__ rs,
-                                                      const uint32_t *__restrict__ re,
+                                                      const uint32_t *__restrict__ row_ptr_p,
                                                       uint32_t *__restrict__ deg) {
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < V) deg[v] = re[pos[v]] - rs[pos[v]];
+  if (v < V) deg[v] = row_ptr_p[pos[v] + 1] - row_ptr_p[pos[v]];
+}
+
+__device__ __forceinline__ void export_slot(const ExportArgs &x, uint32_t to, uint32_t from) {
+  x.dst_o[to] = x.vid[x.dst[from]];
+  x.dist_o[to] = x.dist[from];
+  x.std_o[to] = x.std_dev[from];
+  x.flags_o[to] = x.flags[from] & 0x0Fu;
+  x.eid_o[to] = x.eid[from];
+  x.estate_o[to] = x.estate[from];
 }
 
 __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
@@ -476,42 +477,28 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
   uint32_t from = 0, to = 0, d = 0;
   if (v < x.V) {
     const uint32_t p = x.pos[v];
-    from = x.rs[p];
-    d = x.re[p] - from;
+    from = x.row_ptr_p[p];
+    d = x.row_ptr_p[p + 1] - from;
     to = x.row_ptr[v];
   }
   const bool big = d > BIG_ROW;
   if (!big)
-    for (uint32_t k = 0; k < d; k++) {
-      x.dst_o[to + k] = x.dst[from + k];
-      x.dist_o[to + k] = x.dist[from + k];
-      x.std_o[to + k] = x.std_dev[from + k];
-      x.flags_o[to + k] = x.flags[from + k];
-      x.eid_o[to + k] = x.eid[from + k];
-      x.estate_o[to + k] = x.estate[from + k];
-    }
+    for (uint32_t k = 0; k < d; k++) export_slot(x, to + k, from + k);
   unsigned todo = __ballot_sync(0xffffffffu, big);
   while (todo) {
     const int l = __ffs(todo) - 1;
     todo &= todo - 1;
     const uint32_t ff = __shfl_sync(0xffffffffu, from, l), tt = __shfl_sync(0xffffffffu, to, l),
                    dd = __shfl_sync(0xffffffffu, d, l);
-    for (uint32_t k = lane_id(); k < dd; k += 32) {
-      x.dst_o[tt + k] = x.dst[ff + k];
-      x.dist_o[tt + k] = x.dist[ff + k];
-      x.std_o[tt + k] = x.std_dev[ff + k];
-      x.flags_o[tt + k] = x.flags[ff + k];
-      x.eid_o[tt + k] = x.eid[ff + k];
-      x.estate_o[tt + k] = x.estate[ff + k];
-    }
+    for (uint32_t k = lane_id(); k < dd; k += 32) export_slot(x, tt + k, ff + k);
   }
 }
 
 // ------------------------------------------------------------------ host driver
 
-size_t build2_smem_classify() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
-size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 3 * NB_COARSE * 4 + 16; }
-size_t build2_smem_resolve() { return SEG_ENT_CAP * 17 + 5 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 16; }
+size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
+size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
+size_t build2_smem_resolve() { return SEG_ENT_CAP * 17 + 3 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 16; }
 
 int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
@@ -544,7 +531,7 @@ int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
     k2_classify<<<nseg, SEG_THREADS, build2_smem_classify(), s>>>(a);
   }
   exclusive_scan<uint32_t>(a.cnt_in, a.V, a.bptr, a.scan_scratch, s);
-  exclusive_scan<uint32_t>(a.seg_creators, nseg, a.seg_k, a.scan_scratch, s);
+  exclusive_scan<uint32_t>(a.nown, a.V, a.k0, a.scan_scratch, s);
   {
     KernelTimer t_("k2_partition", s);
     k2_init_cursors<<<1, 128, 0, s>>>(a);
@@ -566,7 +553,7 @@ int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
 int launch_export_csr(const ExportArgs &x, uint32_t *deg_tmp, uint32_t *scan_scratch, cudaStream_t s) {
   const uint32_t vb = (x.V + 255) / 256;
   if (x.V == 0) return 0;
-  k2_export_deg<<<vb, 256, 0, s>>>(x.V, x.pos, x.rs, x.re, deg_tmp);
+  k2_export_deg<<<vb, 256, 0, s>>>(x.V, x.pos, x.row_ptr_p, deg_tmp);
   exclusive_scan<uint32_t>(deg_tmp, x.V, x.row_ptr, scan_scratch, s);
   k2_export_rows<<<vb, 256, 0, s>>>(x);
   return 5;

@@ -18,6 +18,7 @@ constexpr uint32_t F_SENSE = 1u;    // edge->sense
 constexpr uint32_t F_SAME = 2u;     // edge->same
 constexpr uint32_t F_RSENSE = 4u;   // sense of the reverse edge (dst -> src)
 constexpr uint32_t F_RSAME = 8u;    // same of the reverse edge
+constexpr uint32_t F_LT = 16u;      // device only: id(dst) < id(src), the filter's time order
 
 // Half-edge entry used while bucketing records by vertex (uint4):
 //   x = record index (raw) / creating record index (resolved)

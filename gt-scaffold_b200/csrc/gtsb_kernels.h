@@ -66,12 +66,13 @@ struct Build2Args {
   uint32_t *tile_cnt, *tile_off;            // head tiles
   uint8_t *rf;                              // [R] RF_UP | RF_FIRST
   uint32_t *cnt_in, *bptr, *cursor;         // [V+1] mailbox sizes / offsets / fill
-  uint32_t *seg_creators, *seg_k;           // [nseg+1]
   uint4 *tmp_ent, *bucket, *corrections;
   uint32_t *tmp_dest, *tmp_cursor;
   uint8_t *lineless_flag;
   uint32_t *lineless_rank, *scan_scratch, *counters, *big_rows;
-  uint32_t *rs, *re, *dst, *eid;            // rows
+  uint32_t *pc;                             // [R] position of every record's partner
+  uint32_t *nown, *k0;                      // [V+1] creators per line / before each line
+  uint32_t *row_ptr, *srcp, *dst, *eid;     // rows (dense, by position)
   int32_t *edist;
   float *estd;
   uint8_t *eflags;
@@ -81,7 +82,7 @@ int launch_build2_rows(const Build2Args &a, cudaStream_t s);
 
 struct ExportArgs {        // line layout -> plain CSR in vertex order
   uint32_t V;
-  const uint32_t *pos, *rs, *re, *dst, *eid;
+  const uint32_t *pos, *vid, *row_ptr_p, *dst, *eid;
   const int32_t *dist;
   const float *std_dev;
   const uint8_t *flags, *estate;
@@ -123,18 +124,23 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
 void launch_build_emit(const BuildArgs &a, cudaStream_t s);
 
 // A device-resident graph.  Rows are addressed by POSITION p in [0,V): row p
-// occupies slots [rs[p], re[p]) and belongs to vertex vid[p] (vid == nullptr:
-// identity).  The plain CSR of the general build is rs = row_ptr,
-// re = row_ptr + 1; the line-ordered build stores rows in .de line order.
-// Everything indexed by a vertex (states, attributes, polyTime, fire bits, the
-// dst column) uses the reference's vertex ids.
+// occupies slots [row_ptr[p], row_ptr[p+1]) and belongs to vertex vid[p]
+// (vid == nullptr: identity, the plain CSR of the general build).  The
+// line-ordered build lays rows out in .de line order.  Positions are the
+// device's vertex names: the dst column, the per-slot source column srcp and
+// every per-vertex work array of the filter are position-indexed, so that all
+// passes stream.  Only the caller-facing arrays (seq_len/astat/copy_num in,
+// vstate in/out) are indexed by the reference's vertex ids, and the only
+// id-order fact the filter needs per slot, id(dst) < id(src), is the F_LT flag.
+constexpr uint32_t S_BIG = 1u << 31;      // srcp: slot of a row with more than BIG_ROW slots
+constexpr uint32_t S_POS = (1u << 27) - 1u;
 struct GraphArgs {
-  uint32_t V;
+  uint32_t V, E;
   int sm_count;
-  const uint32_t *rs, *re, *vid, *pos, *dst;   // pos: vertex -> position (nullptr: identity)
+  const uint32_t *row_ptr, *vid, *pos, *srcp, *dst;
   const int32_t *dist;
   const float *std_dev;
-  const uint8_t *flags;
+  uint8_t *flags;
   const VAttr *vattr;
   const float *astat;
   uint8_t *vstate, *estate;
@@ -148,37 +154,34 @@ struct FilterArgs {
   AmbigParams ambig;
   float cncutoff;
   long long ocutoff;
-  // work arrays
-  uint2 *proposals;
+  // work arrays, all indexed by position
+  uint2 *proposals;          // {proposer position, target position}
   uint32_t proposals_cap;
-  uint32_t *poly_cur, *poly_new;
-  uint8_t *gbits, *fstat;
+  uint32_t *poly_cur, *poly_new;   // polyTime: vertex id of the winning proposer
+  uint8_t *gbits, *fstat, *dirty, *rep_pred;
   uint32_t *work_a, *work_b;
   uint8_t *big_scratch;      // per block: max_deg * BIG_SCRATCH_STRIDE bytes
   uint32_t big_blocks;
-  // bandwidth path (gtsb_filter2.cu)
-  uint2 *vinfo;              // [V] {copy_num, seq_len | marked-on-entry << 31}
-  uint32_t *vres;            // [V] polyTime | fire bits | repeat predicate
-  uint8_t *dirty;            // [V] static overlap answer must be recomputed (nullptr: always recompute)
+  uint2 *vinfo;              // {copy_num, seq_len | marked-on-entry << 31}
+  uint32_t *vres;            // polyTime | fire bits | repeat predicate
   int fused_repeats;         // fresh graph: edge REPEAT marks are derived, not stored (gtsb_pipeline)
 };
-void launch_vinfo(const FilterArgs &a, cudaStream_t s);
-void launch_pairs2(const FilterArgs &a, cudaStream_t s);
-void launch_pairs_big(const FilterArgs &a, cudaStream_t s);
-void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
-void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
-void launch_finalize2(const FilterArgs &a, const uint8_t *rep_pred, cudaStream_t s);
-void launch_repeat_vertices(const GraphArgs &g, uint8_t *rep_pred, float copy_num_cutoff,
-                            float astat_cutoff, int use_copy_num, cudaStream_t s);
 constexpr uint32_t BIG_SCRATCH_STRIDE = 12;   // cn f32, len u32, u8 marks (padded)
 
-void launch_mark_repeats(const GraphArgs &g, uint8_t *rep_pred, float copy_num_cutoff,
-                         float astat_cutoff, int use_copy_num, cudaStream_t s);
-void launch_filter_pairs(const FilterArgs &a, cudaStream_t s);
+// per-vertex facts by position; with do_repeats also the repeat predicate
+// (gt_scaffolder_graph_mark_repeats' vertex loop) and its vertex marks
+void launch_vertex_facts(const FilterArgs &a, int do_repeats, float copy_num_cutoff, float astat_cutoff,
+                         int use_copy_num, cudaStream_t s);
+void launch_repeat_edges(const GraphArgs &g, const uint8_t *rep_pred, cudaStream_t s);
+void launch_pairs(const FilterArgs &a, cudaStream_t s);
 void launch_poly_sweep(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
-void launch_filter_overlap(const FilterArgs &a, cudaStream_t s);
+void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
+void launch_fire_init(const FilterArgs &a, cudaStream_t s);
+void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
-void launch_filter_finalize(const FilterArgs &a, cudaStream_t s);
+void launch_finalize(const FilterArgs &a, cudaStream_t s);
+// srcp column, F_LT flags and the big-row list of a plain CSR that was uploaded
+void launch_fill_srcp(const GraphArgs &g, uint32_t *srcp, uint32_t *big_rows, cudaStream_t s);
 
 }  // namespace gtsb
