@@ -72,6 +72,8 @@ struct gtsb_context {
   // graph
   DevBuf row_ptr, srcp, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
   DevBuf vid, pos;              // line layout
+  DevBuf wcount, woff, win_start;
+  uint32_t n_windows = 0;
   DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
       tmp_cursor, bucket, corrections, lineless_flag, lineless_rank;
   DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
@@ -213,6 +215,8 @@ GraphArgs graph_args(gtsb_context *c) {
   g.vid = c->line_layout ? c->vid.as<uint32_t>() : nullptr;
   g.pos = c->line_layout ? c->pos.as<uint32_t>() : nullptr;
   g.srcp = c->srcp.as<uint32_t>();
+  g.win_start = c->win_start.as<uint32_t>();
+  g.n_windows = c->n_windows;
   g.dst = c->dst.as<uint32_t>();
   g.dist = c->edist.as<int32_t>();
   g.std_dev = c->estd.as<float>();
@@ -267,6 +271,16 @@ void prof_collect(gtsb_context *c) {
     c->prof.pool.push_back(r.b);
   }
   c->prof.recs.clear();
+}
+
+int ensure_windows(gtsb_context *c, uint64_t V, uint64_t max_edges) {
+  const uint64_t nthr = (V + 63) / 64 + 2;
+  ENSURE(c->wcount, nthr * 4);
+  ENSURE(c->woff, nthr * 4);
+  ENSURE(c->win_start, ((V < max_edges ? V : max_edges) + 2) * 4);
+  const uint64_t scan_n = V > c->R ? V : c->R;
+  ENSURE(c->scan_scratch, scan_scratch_elems(scan_n) * 4);
+  return 0;
 }
 
 int ensure_rows(gtsb_context *c, uint64_t R) {
@@ -363,8 +377,17 @@ int do_build_lines(gtsb_context *c) {
   a.estd = c->estd.as<float>();
   a.eflags = c->eflags.as<uint8_t>();
 
+  if (ensure_windows(c, V, 2 * R) != 0) return -1;
   c->stats.kernel_launches += launch_build2_lines(a, s);
   c->stats.kernel_launches += launch_build2_rows(a, s);
+  {
+    GraphArgs g{};
+    g.V = (uint32_t) V;
+    g.row_ptr = c->row_ptr.as<uint32_t>();
+    g.counters = c->counters.as<uint32_t>();
+    c->stats.kernel_launches += launch_pack_windows(g, c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
+                                                    c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
+  }
   if (read_counters(c) != 0) return -1;
   if (c->h_counters[CNT_ERROR] & 1u) return fail(c, "gtsb_build: a record names a vertex id >= nof_vertices");
   if (c->h_counters[CNT_ERROR] & 2u)
@@ -373,6 +396,7 @@ int do_build_lines(gtsb_context *c) {
   c->fallback_reason = c->h_counters[CNT_FALLBACK];
   if (c->fallback_reason) return 1;
   c->E = c->h_counters[CNT_EDGES];
+  c->n_windows = c->h_counters[CNT_WINDOWS];
   c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
   c->max_deg = c->h_counters[CNT_MAX_DEG];
   c->stats.nof_edges = c->E;
@@ -485,8 +509,13 @@ int do_build(gtsb_context *c) {
   c->stats.big_rows = c->n_big_rows;
   c->stats.max_degree = c->max_deg;
   c->have_graph = true;
+  if (ensure_windows(c, V, 2 * R) != 0) return -1;
   launch_fill_srcp(graph_args(c), c->srcp.as<uint32_t>(), nullptr, s);   // big rows: listed by the emit pass
   c->stats.kernel_launches += V ? 1 : 0;
+  c->stats.kernel_launches += launch_pack_windows(graph_args(c), c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
+                                                  c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
+  if (read_counters(c) != 0) return -1;
+  c->n_windows = V ? c->h_counters[CNT_WINDOWS] : 0;
   CK(cudaGetLastError());
   return 0;
 }
@@ -558,6 +587,7 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (V + 1) * 4, s));
   CK(cudaMemsetAsync(c->dirty.p, 0, V + 1, s));
   CK(cudaMemsetAsync(c->gbits.p, 0, V + 1, s));
+  CK(cudaMemsetAsync(c->fstat.p, 0x0C, V + 1, s));      // rows without slots: decided, nothing fires
   // phase 1: who proposes whom (+ the static overlap answer of every small row)
   launch_vertex_facts(a, fused ? 1 : 0, cn_cutoff, astat_cutoff, use_cn, s);
   launch_pairs(a, s);
@@ -585,7 +615,7 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   // vertices), then the order-respecting fire fixpoint
   CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
   launch_fire_init(a, s);
-  c->stats.kernel_launches += (V ? 1 : 0) + (V && c->n_big_rows ? 1 : 0);
+  c->stats.kernel_launches += (V ? 2 : 0) + (V && c->n_big_rows ? 1 : 0);
   c->stats.fire_rounds = 0;
   uint32_t *win = a.work_b, *wout = a.work_a;
   int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
@@ -694,7 +724,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
                     &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
-                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->vid, &c->pos, &c->ls,
+                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->wcount, &c->woff, &c->win_start, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
                     &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
@@ -829,11 +859,16 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
   CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
   c->E = E;
   c->line_layout = false;
+  c->R = 0;
+  if (ensure_windows(c, V, E) != 0) return -1;
   launch_fill_srcp(graph_args(c), c->srcp.as<uint32_t>(), c->big_rows.as<uint32_t>(), s);
   c->stats.kernel_launches += V ? 1 : 0;
+  c->stats.kernel_launches += launch_pack_windows(graph_args(c), c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
+                                                  c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
   if (read_counters(c) != 0) return -1;
   c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
   c->max_deg = c->h_counters[CNT_MAX_DEG];
+  c->n_windows = V ? c->h_counters[CNT_WINDOWS] : 0;
   c->E = E;
   c->R = 0;
   c->have_graph = true;

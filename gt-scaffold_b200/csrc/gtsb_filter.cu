@@ -29,17 +29,21 @@
 // parser.c:374-377); the build stores the reverse edge's sense/same per slot.
 //
 // Mapping to the machine.  Vertices are named by POSITION (gtsb_kernels.h), so
-// every per-vertex array streams.  The passes over edges are flat: a warp owns
-// a WINDOW of 32 consecutive slots plus the tail of the last row that starts in
-// it (rows of at most BIG_ROW slots; longer rows take block/warp-per-row
-// kernels), lanes are slots, row boundaries come from one ballot over the srcp
-// column, partners of a pair are fetched with shuffles and row-wide facts are
-// ballots.  No shared memory, no block barriers; per-neighbour facts are packed
-// so that each pass makes ONE gather per slot:
+// every per-vertex array streams.  The passes over edges are flat: the slots
+// are cut once per graph into WINDOWS of whole rows, at most 32 slots each
+// (k4_pack_windows; rows of more than BIG_ROW slots are windows of their own
+// and take block/warp-per-row kernels).  A warp walks a batch of 32 windows;
+// lanes are slots, row boundaries come from one ballot over the srcp column,
+// the same-direction pairs of all rows of a window are enumerated into one list
+// and dealt out to the lanes (every lane evaluates a real pair), operands move
+// by shuffle and row-wide results by redux/ballot.  No shared memory, no block
+// barriers; per-neighbour facts are packed so that each pass makes ONE gather
+// per slot:
 //   vinfo[p] = {copy_num, seq_len | marked-on-entry << 31}          (pairs pass)
 //   vres[p]  = polyTime (27 bits) | F[p,antisense] | F[p,sense] | repeat-pred
 //                                                                   (final pass)
 #include "gtsb_common.cuh"
+#include "gtsb_scan.cuh"
 #include "gtsb_kernels.h"
 
 namespace gtsb {
@@ -71,59 +75,218 @@ __device__ __forceinline__ void warp_append2(bool pred, uint2 value, uint2 *list
   }
 }
 
-// ------------------------------------------------------------------ windows
-
-// The rows a warp owns: those that START in slots [32w, 32w+32).  Lane l holds
-// slot 32w+l ("lo") and, if the last of those rows runs past the window, slot
-// 32(w+1)+l of that row ("hi").  Virtual index of lo = l, of hi = 32+l.
-struct Window {
-  uint32_t s_lo, s_hi;
-  uint32_t row, row_last;    // position of the lo slot's row / of the last row (the hi slots' row)
-  bool own_lo, own_hi, head, last;
-  uint32_t heads;            // lanes whose lo slot starts a row
-  uint32_t vb, ve;           // own lo lane: its row spans virtual indices [vb, ve)
-  uint32_t vb_last, nhi;
+// Worklist appends of one warp, staged in shared memory so that the global
+// counter sees one atomic per ~64 entries instead of one per window.
+struct WarpQueue {
+  uint32_t *buf;             // [QCAP] of this warp
+  uint32_t cnt;              // warp-uniform
+  static constexpr uint32_t QCAP = 96, QFLUSH = 64;
+  __device__ __forceinline__ void flush(uint32_t *list, uint32_t *count) {
+    if (cnt == 0) return;
+    uint32_t base = 0;
+    __syncwarp();
+    if (lane_id() == 0) base = atomicAdd(count, cnt);
+    base = __shfl_sync(FULL, base, 0);
+    for (uint32_t i = lane_id(); i < cnt; i += 32u) list[base + i] = buf[i];
+    __syncwarp();
+    cnt = 0;
+  }
+  __device__ __forceinline__ void push(bool pred, uint32_t value, uint32_t *list, uint32_t *count) {
+    const uint32_t mask = __ballot_sync(FULL, pred);
+    if (mask == 0) return;
+    if (pred) buf[cnt + __popc(mask & ((1u << lane_id()) - 1u))] = value;
+    cnt += __popc(mask);
+    if (cnt >= QFLUSH) flush(list, count);
+  }
 };
 
-__device__ __forceinline__ Window open_window(const GraphArgs &g, uint32_t w) {
+// maximum of v over the lanes of each row (rows of at most 32 lanes), valid in every lane of the row
+__device__ __forceinline__ int row_max(int v, uint32_t vb, uint32_t ve) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (uint32_t d = 1; d < 32u; d <<= 1) {
+    const int t = __shfl_down_sync(FULL, v, d);
+    if (lane + d < ve) v = max(v, t);
+  }
+  return __shfl_sync(FULL, v, vb);
+}
+
+// ------------------------------------------------------------------ windows
+
+constexpr int PACK_ROWS = 64;       // rows per thread of the packing pass
+
+// Greedy packing of consecutive rows into windows of at most 32 slots; a row of
+// more than BIG_ROW slots is a window of its own.  Windows never span two
+// threads' row ranges.  WRITE = false counts, WRITE = true writes the starts.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k4_pack_windows(uint32_t V, const uint32_t *__restrict__ row_ptr,
+                                                        uint32_t *__restrict__ count,
+                                                        const uint32_t *__restrict__ woff,
+                                                        uint32_t *__restrict__ win_start,
+                                                        uint32_t *__restrict__ counters) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t p0 = (uint64_t) t * PACK_ROWS;
+  if (p0 >= V) return;
+  if (counters[CNT_FALLBACK] | counters[CNT_ERROR]) return;     // no rows were built
+  const uint32_t p1 = (uint32_t) (p0 + PACK_ROWS < V ? p0 + PACK_ROWS : V);
+  uint32_t nw = 0, cur_start = 0, cur_len = 0;
+  uint32_t prev = row_ptr[p0];
+  const uint32_t base = WRITE ? woff[t] : 0u;
+  for (uint32_t p = (uint32_t) p0; p < p1; p++) {
+    const uint32_t nxt = row_ptr[p + 1], d = nxt - prev;
+    if (d > BIG_ROW || cur_len + d > 32u) {
+      if (cur_len) {
+        if (WRITE) win_start[base + nw] = cur_start;
+        nw++;
+      }
+      cur_len = 0;
+    }
+    if (d > BIG_ROW) {
+      if (WRITE) win_start[base + nw] = prev;
+      nw++;
+    } else if (d) {
+      if (cur_len == 0) cur_start = prev;
+      cur_len += d;
+    }
+    prev = nxt;
+  }
+  if (cur_len) {
+    if (WRITE) win_start[base + nw] = cur_start;
+    nw++;
+  }
+  if (!WRITE) count[t] = nw;
+  if (WRITE && p1 == V) {
+    win_start[base + nw] = prev;                 // = row_ptr[V]: end of the last window
+    counters[CNT_WINDOWS] = base + nw;
+  }
+}
+
+int launch_pack_windows(const GraphArgs &g, uint32_t *count, uint32_t *woff, uint32_t *win_start,
+                        uint32_t *scan_scratch, cudaStream_t s) {
+  if (g.V == 0) return 0;
+  KernelTimer t_("k4_pack_windows(2 kernels+scan)", s);
+  const uint32_t nthr = (uint32_t) (((uint64_t) g.V + PACK_ROWS - 1) / PACK_ROWS);
+  const uint32_t blocks = (nthr + 127) / 128;
+  k4_pack_windows<false><<<blocks, 128, 0, s>>>(g.V, g.row_ptr, count, nullptr, nullptr, g.counters);
+  exclusive_scan<uint32_t>(count, nthr, woff, scan_scratch, s);
+  k4_pack_windows<true><<<blocks, 128, 0, s>>>(g.V, g.row_ptr, nullptr, woff, win_start, g.counters);
+  return 5;
+}
+
+// One window: lanes are its slots.
+struct Window {
+  uint32_t s;                // this lane's slot
+  bool valid, head;
+  uint32_t row;              // position of the slot's row
+  uint32_t vb, ve, rowmask;  // the row's lanes [vb, ve)
+};
+
+__device__ __forceinline__ Window open_window(uint32_t start, uint32_t n, uint32_t sp) {
   Window W;
   const uint32_t lane = lane_id();
-  W.s_lo = w * 32u + lane;
-  W.s_hi = W.s_lo + 32u;
-  const bool valid_lo = W.s_lo < g.E;
-  const bool valid_hi = (uint64_t) W.s_lo + 32u < g.E;
-  const uint32_t sp = valid_lo ? g.srcp[W.s_lo] : NONE;
-  const uint32_t sph = valid_hi ? g.srcp[W.s_hi] : NONE;
-  uint32_t prev = __shfl_up_sync(FULL, sp, 1);
-  if (lane == 0) prev = w > 0 ? g.srcp[W.s_lo - 1] : NONE;
-  W.head = valid_lo && sp != prev;
-  W.heads = __ballot_sync(FULL, W.head);
-  const uint32_t upto = W.heads & (FULL >> (31u - lane));
-  const uint32_t above = lane == 31u ? 0u : (W.heads & (FULL << (lane + 1u)));
-  W.own_lo = valid_lo && upto != 0u && !(sp & S_BIG);
+  W.s = start + lane;
+  W.valid = lane < n;
+  const uint32_t prev = __shfl_up_sync(FULL, sp, 1);
+  W.head = W.valid && (lane == 0 || sp != prev);
+  const uint32_t heads = __ballot_sync(FULL, W.head);
+  const uint32_t upto = heads & (FULL >> (31u - lane));
+  const uint32_t above = lane == 31u ? 0u : (heads & (FULL << (lane + 1u)));
   W.row = sp & S_POS;
   W.vb = upto ? 31u - (uint32_t) __clz(upto) : 0u;
-  W.last = above == 0u;
-  const uint32_t sp31 = __shfl_sync(FULL, sp, 31);
-  W.own_hi = valid_hi && W.heads != 0u && sph == sp31 && !(sp31 & S_BIG);
-  W.nhi = (uint32_t) __popc(__ballot_sync(FULL, W.own_hi));
-  W.row_last = sp31 & S_POS;
-  W.vb_last = W.heads ? 31u - (uint32_t) __clz(W.heads) : 0u;
-  W.ve = W.last ? 32u + W.nhi : (uint32_t) __ffs(above) - 1u;
+  W.ve = above ? (uint32_t) __ffs(above) - 1u : n;
+  W.rowmask = (W.ve >= 32u ? FULL : ((1u << W.ve) - 1u)) & (FULL << W.vb);
   return W;
 }
 
-// OR of a per-slot predicate over the whole row; valid in own lo lanes
-__device__ __forceinline__ bool row_any(const Window &W, bool lo, bool hi) {
-  const uint32_t mlo = __ballot_sync(FULL, lo), mhi = __ballot_sync(FULL, hi);
-  const uint32_t lim = W.ve < 32u ? ((1u << W.ve) - 1u) : FULL;
-  return (mlo & lim & (FULL << W.vb)) != 0u || (W.last && mhi != 0u);
+// A warp's share of the windows: batches of 32 consecutive windows, U of them
+// in flight at a time so that the dependent memory round trips of different
+// windows overlap:  stageA(start, n) issues the slot loads and returns the
+// window's state, stageB(state) issues the gathers that need them,
+// stageC(state) computes and stores.  All three are called warp-uniformly, for
+// windows of at most 32 slots only.
+template <int U, typename StageA, typename StageB, typename StageC>
+__device__ __forceinline__ void for_each_window(const GraphArgs &g, StageA stageA, StageB stageB,
+                                                StageC stageC) {
+  const uint32_t lane = lane_id();
+  const uint32_t nwin = g.n_windows;
+  const uint32_t nbatch = (nwin + 31u) / 32u;
+  for (uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5); b < nbatch; b += gridDim.x * WARPS) {
+    const uint32_t w0 = b * 32u;
+    const uint32_t ws = w0 + lane <= nwin ? g.win_start[w0 + lane] : 0u;
+    const uint32_t wlast = w0 + 32u <= nwin ? g.win_start[w0 + 32u] : 0u;   // same address in every lane
+    const uint32_t cnt = nwin - w0 < 32u ? nwin - w0 : 32u;
+    for (uint32_t k = 0; k < cnt; k += U) {
+      decltype(stageA(0u, 0u)) st[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t kk = k + u;
+        const uint32_t start = __shfl_sync(FULL, ws, kk & 31u);
+        const uint32_t end = kk < 31u ? __shfl_sync(FULL, ws, (kk + 1u) & 31u) : wlast;
+        on[u] = kk < cnt && end - start <= 32u;
+        if (on[u]) st[u] = stageA(start, end - start);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (on[u]) stageB(st[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (on[u]) stageC(st[u]);
+    }
+  }
 }
 
-static uint32_t host_flat_grid(uint32_t E) {
-  const uint64_t nwin = ((uint64_t) E + 31u) / 32u;
-  const uint64_t blocks = (nwin + WARPS - 1) / WARPS;
+static uint32_t host_flat_grid(uint32_t n_windows) {
+  const uint64_t nbatch = ((uint64_t) n_windows + 31u) / 32u;
+  const uint64_t blocks = (nbatch + WARPS - 1) / WARPS;
   return (uint32_t) (blocks < 1 ? 1 : blocks);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, v, d);
+    if ((int) lane_id() >= d) v += t;
+  }
+  return v;
+}
+
+// index of the r-th (0-based) set bit of m; r < popc(m)
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t r) {
+  uint32_t pos = 0, c;
+  c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; m >>= 16; pos += 16; }
+  c = __popc(m & 0xFFu);   if (r >= c) { r -= c; m >>= 8;  pos += 8; }
+  c = __popc(m & 0xFu);    if (r >= c) { r -= c; m >>= 4;  pos += 4; }
+  c = __popc(m & 0x3u);    if (r >= c) { r -= c; m >>= 2;  pos += 2; }
+  c = m & 1u;              if (r >= c) pos += 1;
+  return pos;
+}
+
+// Deal the pairs {(i, j) : j in P_i} of a window out to the lanes.  P is each
+// lane's mask of partner lanes (j > i).  body(live, i, j) is called
+// warp-uniformly ceil(T/32) times; lanes beyond the list get live = false.
+template <typename Body>
+__device__ __forceinline__ void for_each_pair(uint32_t P, Body body) {
+  const uint32_t lane = lane_id();
+  const uint32_t c = __popc(P);
+  const uint32_t incl = warp_incl_scan_u32(c);
+  const uint32_t total = __shfl_sync(FULL, incl, 31);
+  const uint32_t excl = incl - c;
+  for (uint32_t q0 = 0; q0 < total; q0 += 32u) {
+    const uint32_t q = q0 + lane;
+    const bool live = q < total;
+    uint32_t i = 0;                                // number of lanes with incl <= q = owner of pair q
+#pragma unroll
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+      const uint32_t t = __shfl_sync(FULL, incl, (i + step - 1u) & 31u);
+      if (t <= q) i += step;
+    }
+    i &= 31u;
+    const uint32_t r = q - __shfl_sync(FULL, excl, i);
+    const uint32_t Pi = __shfl_sync(FULL, P, i);
+    const uint32_t j = live ? nth_set_bit(Pi, r) : 0u;
+    body(live, i, j);
+  }
 }
 
 // ------------------------------------------------------------------ per-vertex facts
@@ -217,26 +380,8 @@ void launch_fill_srcp(const GraphArgs &g, uint32_t *srcp, uint32_t *big_rows, cu
 struct SlotFacts {
   int32_t dist;
   float std_dev, cn;
-  uint32_t len, fl;          // fl: bit0 sense, bit1 edge unmarked on entry, bit2 dst marked on entry
+  uint32_t len;
 };
-constexpr uint32_t SF_SENSE = 1u, SF_OK = 2u, SF_WM = 4u;
-
-__device__ __forceinline__ SlotFacts slot_facts(const FilterArgs &a, uint32_t s, uint32_t *dst_out) {
-  const GraphArgs &g = a.g;
-  SlotFacts f;
-  const uint32_t w = g.dst[s];
-  const uint2 vi = a.vinfo[w];
-  const uint32_t fl = g.flags[s];
-  const bool wm = (vi.y & VI_MARKED) != 0;
-  const bool ok = a.fused_repeats ? !wm : !edge_state_marked(g.estate[s]);
-  f.dist = g.dist[s];
-  f.std_dev = g.std_dev[s];
-  f.cn = __uint_as_float(vi.x);
-  f.len = vi.y & ~VI_MARKED;
-  f.fl = (fl & F_SENSE) | (ok ? SF_OK : 0u) | (wm ? SF_WM : 0u);
-  *dst_out = w;
-  return f;
-}
 
 __device__ __forceinline__ SlotFacts shfl_facts(const SlotFacts &f, uint32_t src_lane) {
   SlotFacts r;
@@ -244,80 +389,81 @@ __device__ __forceinline__ SlotFacts shfl_facts(const SlotFacts &f, uint32_t src
   r.std_dev = __shfl_sync(FULL, f.std_dev, src_lane);
   r.cn = __shfl_sync(FULL, f.cn, src_lane);
   r.len = __shfl_sync(FULL, f.len, src_lane);
-  r.fl = __shfl_sync(FULL, f.fl, src_lane);
   return r;
 }
 
-// one same-row pair, e1 = earlier adjacency slot (algorithms.c:283-295, 301-320)
-__device__ __forceinline__ void pair_eval(const FilterArgs &a, const SlotFacts &e1, const SlotFacts &e2,
-                                          bool &prop1, bool &prop2, bool &fire) {
-  if ((e1.fl ^ e2.fl) & SF_SENSE) return;
-  // check_mark_polymorphic, algorithms.c:232-238
-  if (ambiguous_order(e1.dist, e1.std_dev, e2.dist, e2.std_dev, a.ambig) &&
-      __fadd_rn(e1.cn, e2.cn) < a.cncutoff) {
-    if (e1.cn < e2.cn) prop1 = true; else prop2 = true;
-  }
-  if ((e1.fl & e2.fl & SF_OK) && a.ocutoff >= 0)
-    fire |= interval_overlap(e1.dist, e1.len, e2.dist, e2.len) > a.ocutoff;
-}
+// Proposals of check_mark_polymorphic (algorithms.c:283-295) and, in the same
+// sweep over the pairs, G0[v,s] = "some same-direction pair of edges that are
+// unmarked on entry overlaps by more than ocutoff" (algorithms.c:301-324 before
+// any mark of this filter run is taken into account; k4_fire_init repairs the
+// rows next to polymorphic vertices).  gbits must be zero on entry.
+struct PairsState {
+  uint32_t start, n, sp, dst, fl, own_y;
+  uint2 vi;
+  SlotFacts me;
+  uint8_t es;
+};
 
-// Proposals of check_mark_polymorphic and, in the same sweep over the pairs,
-// G0[v,s] = "some same-direction pair of edges that are unmarked on entry
-// overlaps by more than ocutoff" (algorithms.c:301-324 before any mark of this
-// filter run is taken into account; k4_fire_init repairs the rows next to
-// polymorphic vertices).  gbits must be zero on entry.
 __global__ void __launch_bounds__(32 * WARPS) k4_pairs(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
-  const uint32_t nwin = (uint32_t) (((uint64_t) g.E + 31u) / 32u);
-  for (uint32_t w = blockIdx.x * WARPS + (threadIdx.x >> 5); w < nwin; w += gridDim.x * WARPS) {
-    const Window W = open_window(g, w);
-    // rows that cannot propose or fire: marked on entry (algorithms.c:279)
-    bool act_lo = false;
-    if (W.own_lo) act_lo = !(a.vinfo[W.row].y & VI_MARKED) && (W.ve - W.vb) >= 2u;
-    if (!__any_sync(FULL, act_lo)) continue;
-    const bool act_last = __shfl_sync(FULL, (int) act_lo, W.vb_last) != 0;   // every lane shuffles
-    const bool act_hi = W.own_hi && act_last;
-    SlotFacts lo = {}, hi = {};
-    uint32_t dst_lo = 0, dst_hi = 0;
-    if (act_lo) lo = slot_facts(a, W.s_lo, &dst_lo);
-    if (act_hi) hi = slot_facts(a, W.s_hi, &dst_hi);
-    bool prop_lo = false, prop_hi = false, fire_lo = false, fire_hi = false;
-    // lo requesters: partner at virtual index lane + o (lo of lane+o, or hi of lane+o-32)
-    const uint32_t maxlen = __reduce_max_sync(FULL, act_lo ? W.ve - lane : 0u);
-    for (uint32_t o = 1; o < maxlen; o++) {
-      const bool from_lo = lane >= o;
-      SlotFacts src;
-      src.dist = from_lo ? lo.dist : hi.dist;
-      src.std_dev = from_lo ? lo.std_dev : hi.std_dev;
-      src.cn = from_lo ? lo.cn : hi.cn;
-      src.len = from_lo ? lo.len : hi.len;
-      src.fl = from_lo ? lo.fl : hi.fl;
-      const SlotFacts p = shfl_facts(src, (lane + o) & 31u);
-      bool pm = false, po = false;
-      if (act_lo && lane + o < W.ve) pair_eval(a, lo, p, pm, po, fire_lo);
-      prop_lo |= pm;
-      const bool back = __shfl_sync(FULL, (int) po, (lane - o) & 31u) != 0;
-      if (from_lo) prop_lo |= back; else prop_hi |= back;
-    }
-    // hi requesters pair with hi partners only
-    for (uint32_t o = 1; o < W.nhi; o++) {
-      const SlotFacts p = shfl_facts(hi, (lane + o) & 31u);
-      bool pm = false, po = false;
-      if (act_hi && lane + o < W.nhi) pair_eval(a, hi, p, pm, po, fire_hi);
-      prop_hi |= pm;
-      const bool back = __shfl_sync(FULL, (int) po, (lane - o) & 31u) != 0;
-      if (lane >= o) prop_hi |= back;
-    }
-    // proposals (target must be unmarked, algorithms.c:242)
-    warp_append2(act_lo && prop_lo && !(lo.fl & SF_WM), make_uint2(W.row, dst_lo), a.proposals,
-                 a.proposals_cap, &g.counters[CNT_PROPOSALS], &g.counters[CNT_OVERFLOW]);
-    warp_append2(act_hi && prop_hi && !(hi.fl & SF_WM), make_uint2(W.row_last, dst_hi), a.proposals,
-                 a.proposals_cap, &g.counters[CNT_PROPOSALS], &g.counters[CNT_OVERFLOW]);
-    const bool g1 = row_any(W, fire_lo && (lo.fl & SF_SENSE), fire_hi && (hi.fl & SF_SENSE));
-    const bool g0 = row_any(W, fire_lo && !(lo.fl & SF_SENSE), fire_hi && !(hi.fl & SF_SENSE));
-    if (W.head && W.own_lo && (g0 || g1)) a.gbits[W.row] = (uint8_t) ((g0 ? 1u : 0u) | (g1 ? 2u : 0u));
-  }
+  for_each_window<2>(g,
+    [&](uint32_t start, uint32_t n) {
+      PairsState t;
+      t.start = start;
+      t.n = n;
+      const bool valid = lane < n;
+      const uint32_t s = start + lane;
+      t.sp = valid ? g.srcp[s] : NONE;
+      t.dst = valid ? g.dst[s] : 0u;
+      t.fl = valid ? g.flags[s] : 0u;
+      t.me.dist = valid ? g.dist[s] : 0;
+      t.me.std_dev = valid ? g.std_dev[s] : 0.f;
+      t.es = (valid && !a.fused_repeats) ? g.estate[s] : (uint8_t) 0;
+      return t;
+    },
+    [&](PairsState &t) {
+      const bool valid = lane < t.n;
+      t.own_y = valid ? a.vinfo[t.sp & S_POS].y : VI_MARKED;
+      t.vi = valid ? a.vinfo[t.dst] : make_uint2(0u, 0u);
+    },
+    [&](PairsState &t) {
+      const Window W = open_window(t.start, t.n, t.sp);
+      // rows that cannot propose or fire: marked on entry (algorithms.c:279), < 2 edges
+      const bool act = W.valid && !(t.own_y & VI_MARKED) && (W.ve - W.vb) >= 2u;
+      if (!__any_sync(FULL, act)) return;
+      SlotFacts me = t.me;
+      me.cn = __uint_as_float(t.vi.x);
+      me.len = t.vi.y & ~VI_MARKED;
+      const bool wm = (t.vi.y & VI_MARKED) != 0;
+      const bool ok = act && (a.fused_repeats ? !wm : !edge_state_marked(t.es));
+      const bool sense = (t.fl & F_SENSE) != 0;
+      const uint32_t A = __ballot_sync(FULL, act), S = __ballot_sync(FULL, act && sense);
+      const uint32_t OK = __ballot_sync(FULL, ok);
+      const uint32_t higher = lane == 31u ? 0u : FULL << (lane + 1u);
+      const uint32_t P = act ? (W.rowmask & higher & (sense ? S : (A & ~S))) : 0u;
+      uint32_t prop_mask = 0, fire_mask = 0;
+      for_each_pair(P, [&](bool live, uint32_t i, uint32_t j) {
+        const SlotFacts e1 = shfl_facts(me, i), e2 = shfl_facts(me, j);   // e1 = earlier adjacency slot
+        uint32_t hit = 0, fire = 0;
+        if (live) {
+          // check_mark_polymorphic, algorithms.c:232-238
+          if (__fadd_rn(e1.cn, e2.cn) < a.cncutoff &&
+              ambiguous_order(e1.dist, e1.std_dev, e2.dist, e2.std_dev, a.ambig))
+            hit = 1u << (e1.cn < e2.cn ? i : j);
+          if (((OK >> i) & (OK >> j) & 1u) && a.ocutoff >= 0 &&
+              interval_overlap(e1.dist, e1.len, e2.dist, e2.len) > a.ocutoff)
+            fire = 1u << i;
+        }
+        prop_mask |= __reduce_or_sync(FULL, hit);
+        fire_mask |= __reduce_or_sync(FULL, fire);
+      });
+      // proposals (target must be unmarked, algorithms.c:242)
+      warp_append2(act && ((prop_mask >> lane) & 1u) && !wm, make_uint2(W.row, t.dst), a.proposals,
+                   a.proposals_cap, &g.counters[CNT_PROPOSALS], &g.counters[CNT_OVERFLOW]);
+      const uint32_t g1 = fire_mask & W.rowmask & S, g0 = fire_mask & W.rowmask & ~S;
+      if (W.head && act && (g0 | g1)) a.gbits[W.row] = (uint8_t) ((g0 ? 1u : 0u) | (g1 ? 2u : 0u));
+    });
 }
 
 // block per big row; per-block scratch: copy_num[max_deg] f32, mark[max_deg] u8
@@ -366,7 +512,7 @@ void launch_pairs(const FilterArgs &a, cudaStream_t s) {
   if (a.g.E == 0) return;
   {
     KernelTimer t_("k4_pairs", s);
-    k4_pairs<<<host_flat_grid(a.g.E), 32 * WARPS, 0, s>>>(a);
+    k4_pairs<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_pairs_big", s);
@@ -441,21 +587,41 @@ __device__ __forceinline__ bool slot_unmarked(const FilterArgs &a, uint32_t s, u
 
 // G[v,s]: max overlap over same-direction pairs that are unmarked when v is
 // reached, not yet counting the fires of smaller neighbours (algorithms.c:301-320).
-// Thread per row; only rows next to a polymorphic vertex recompute.
-__global__ void __launch_bounds__(128) k4_fire_init(FilterArgs a) {
+// Streaming pass by position: rows away from every polymorphic vertex keep the
+// pairs pass's static answer; the others are listed for k4_fire_redo.
+__global__ void __launch_bounds__(256) k4_fire_init(FilterArgs a, uint32_t *__restrict__ redo_list,
+                                                     uint32_t *__restrict__ n_redo) {
   const GraphArgs &g = a.g;
+  __shared__ uint32_t s_q[8][WarpQueue::QCAP];
+  WarpQueue q{s_q[threadIdx.x >> 5], 0u};
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= g.V) return;
-  const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
-  if (d > BIG_ROW) return;
-  const uint32_t v_id = id_at(g, p);
-  const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < v_id);
-  uint8_t gb = 0;
-  if (active && a.ocutoff < 0) {
-    gb = 3;            // 0 > ocutoff: both directions fire whatever the pairs (:301-324)
-  } else if (active && !a.dirty[p]) {
-    gb = a.gbits[p];   // the pairs pass's static answer stands: no polymorphic vertex nearby
-  } else if (active && d >= 2) {
+  bool redo = false;
+  if (p < g.V) {
+    const uint32_t d = g.row_ptr[p + 1] - g.row_ptr[p];
+    if (d <= BIG_ROW) {
+      const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < id_at(g, p));
+      redo = active && a.ocutoff >= 0 && d >= 2 && a.dirty[p] != 0;
+      if (!redo) {
+        const uint32_t gb = !active ? 0u : (a.ocutoff < 0 ? 3u : (uint32_t) a.gbits[p]);   // 0 > ocutoff: :301-324
+        a.gbits[p] = (uint8_t) gb;
+        a.fstat[p] = a.ocutoff < 0 ? (uint8_t) (FS_DECIDED_ALL | gb)     // no dependence on neighbours
+                                   : (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
+      }
+    }
+  }
+  q.push(redo, p, redo_list, n_redo);
+  q.flush(redo_list, n_redo);
+}
+
+// thread per listed row (active, at most BIG_ROW slots, next to a polymorphic vertex)
+__global__ void __launch_bounds__(128) k4_fire_redo(FilterArgs a, const uint32_t *__restrict__ redo_list,
+                                                     const uint32_t *__restrict__ n_redo) {
+  const GraphArgs &g = a.g;
+  const uint32_t n = *n_redo;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = redo_list[i];
+    const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
+    const uint32_t v_id = id_at(g, p);
     int32_t dist[BIG_ROW];
     uint32_t len[BIG_ROW];
     uint32_t sense_mask = 0, ok_mask = 0;
@@ -468,20 +634,19 @@ __global__ void __launch_bounds__(128) k4_fire_init(FilterArgs a) {
       if (slot_unmarked(a, r0 + k, vi.y, w, v_id)) ok_mask |= 1u << k;
     }
     long long mx[2] = {0, 0};
-    for (uint32_t i = 0; i + 1 < d; i++) {
-      if (!((ok_mask >> i) & 1u)) continue;
-      const uint32_t si = (sense_mask >> i) & 1u;
-      for (uint32_t j = i + 1; j < d; j++) {
-        if (!((ok_mask >> j) & 1u) || ((sense_mask >> j) & 1u) != si) continue;
-        const long long ov = interval_overlap(dist[i], len[i], dist[j], len[j]);
-        if (ov > mx[si]) mx[si] = ov;
+    for (uint32_t x = 0; x + 1 < d; x++) {
+      if (!((ok_mask >> x) & 1u)) continue;
+      const uint32_t sx = (sense_mask >> x) & 1u;
+      for (uint32_t y = x + 1; y < d; y++) {
+        if (!((ok_mask >> y) & 1u) || ((sense_mask >> y) & 1u) != sx) continue;
+        const long long ov = interval_overlap(dist[x], len[x], dist[y], len[y]);
+        if (ov > mx[sx]) mx[sx] = ov;
       }
     }
-    gb = (uint8_t) ((mx[0] > a.ocutoff ? 1 : 0) | (mx[1] > a.ocutoff ? 2 : 0));
+    const uint32_t gb = (mx[0] > a.ocutoff ? 1u : 0u) | (mx[1] > a.ocutoff ? 2u : 0u);
+    a.gbits[p] = (uint8_t) gb;
+    a.fstat[p] = (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
   }
-  a.gbits[p] = gb;
-  a.fstat[p] = a.ocutoff < 0 ? (uint8_t) (FS_DECIDED_ALL | gb)       // no dependence on neighbours
-                             : (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
 }
 
 // block per big row; undecided big rows go straight to the fire worklist
@@ -541,8 +706,9 @@ __global__ void __launch_bounds__(512) k4_fire_init_big(FilterArgs a, uint32_t *
 void launch_fire_init(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
   {
-    KernelTimer t_("k4_fire_init", s);
-    k4_fire_init<<<(a.g.V + 127) / 128, 128, 0, s>>>(a);
+    KernelTimer t_("k4_fire_init(2 kernels)", s);
+    k4_fire_init<<<(a.g.V + 255) / 256, 256, 0, s>>>(a, a.work_a, &a.g.counters[CNT_WORK_A]);
+    k4_fire_redo<<<a.g.sm_count * 16, 128, 0, s>>>(a, a.work_a, &a.g.counters[CNT_WORK_A]);
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_fire_init_big", s);
@@ -583,39 +749,64 @@ __device__ __forceinline__ uint8_t fire_decide(uint8_t st, uint32_t und, uint32_
 
 // first round over all rows of at most BIG_ROW slots (flat); rows still
 // undecided afterwards are appended to the worklist
+struct DenseState {
+  uint32_t start, n, sp, dst, fl, st, su;
+};
+
 __global__ void __launch_bounds__(32 * WARPS) k4_fire_dense(FilterArgs a, uint32_t *__restrict__ work_out,
                                                              uint32_t *__restrict__ n_out) {
   const GraphArgs &g = a.g;
   const volatile uint8_t *fstat = a.fstat;
-  const uint32_t nwin = (uint32_t) (((uint64_t) g.E + 31u) / 32u);
-  for (uint32_t w = blockIdx.x * WARPS + (threadIdx.x >> 5); w < nwin; w += gridDim.x * WARPS) {
-    const Window W = open_window(g, w);
-    uint32_t st = FS_DECIDED_ALL;
-    if (W.own_lo) st = fstat[W.row];
-    const uint32_t und_lo = (~st >> 2) & 3u;
-    if (!__any_sync(FULL, und_lo != 0u)) continue;
-    const uint32_t und_last = __shfl_sync(FULL, und_lo, W.vb_last);          // every lane shuffles
-    const uint32_t und_hi = W.own_hi ? und_last : 0u;
-    const uint32_t res_lo = und_lo ? fire_probe(g, fstat, W.s_lo, und_lo) : 0u;
-    const uint32_t res_hi = und_hi ? fire_probe(g, fstat, W.s_hi, und_hi) : 0u;
-    uint32_t res = 0;
+  const uint32_t lane = lane_id();
+  __shared__ uint32_t s_q[WARPS][WarpQueue::QCAP];
+  WarpQueue q{s_q[threadIdx.x >> 5], 0u};
+  for_each_window<4>(g,
+    [&](uint32_t start, uint32_t n) {
+      DenseState t;
+      t.start = start;
+      t.n = n;
+      const bool valid = lane < n;
+      const uint32_t s = start + lane;
+      t.sp = valid ? g.srcp[s] : NONE;
+      t.dst = valid ? g.dst[s] : 0u;
+      t.fl = valid ? g.flags[s] : 0u;
+      return t;
+    },
+    [&](DenseState &t) {
+      const bool valid = lane < t.n;
+      t.st = valid ? (uint32_t) fstat[t.sp & S_POS] : (uint32_t) FS_DECIDED_ALL;
+      t.su = (valid && (t.fl & F_LT)) ? (uint32_t) fstat[t.dst] : 0u;     // only smaller ids matter
+    },
+    [&](DenseState &t) {
+      const uint32_t und = (~t.st >> 2) & 3u;
+      if (!__any_sync(FULL, und != 0u)) return;
+      const Window W = open_window(t.start, t.n, t.sp);
+      uint32_t res = 0;
+      if (und && (t.fl & F_LT)) {
+        const bool rs = (t.fl & F_RSENSE) != 0, rm = (t.fl & F_RSAME) != 0;
+        const uint32_t sdir = twin_dir(rs, rm) ? 1u : 0u, du = rs ? 1u : 0u;
+        if ((und >> sdir) & 1u)
+          res = ((t.su >> (2 + du)) & 1u) ? (((t.su >> du) & 1u) ? (1u << sdir) : 0u) : (4u << sdir);
+      }
+      uint32_t row_res = 0;
 #pragma unroll
-    for (uint32_t b = 0; b < 4; b++)
-      if (row_any(W, (res_lo >> b) & 1u, (res_hi >> b) & 1u)) res |= 1u << b;
-    bool again = false;
-    if (W.head && W.own_lo && und_lo) {
-      const uint8_t nst = fire_decide((uint8_t) st, und_lo, res);
-      a.fstat[W.row] = nst;
-      again = (nst & FS_DECIDED_ALL) != FS_DECIDED_ALL;
-    }
-    warp_append(again, W.row, work_out, n_out);
-  }
+      for (uint32_t b = 0; b < 4; b++)
+        if (__ballot_sync(FULL, (res >> b) & 1u) & W.rowmask) row_res |= 1u << b;
+      bool again = false;
+      if (W.head && und) {
+        const uint8_t nst = fire_decide((uint8_t) t.st, und, row_res);
+        a.fstat[W.row] = nst;
+        again = (nst & FS_DECIDED_ALL) != FS_DECIDED_ALL;
+      }
+      q.push(again, W.row, work_out, n_out);
+    });
+  q.flush(work_out, n_out);
 }
 
 void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s) {
   if (a.g.E == 0) return;
   KernelTimer t_("k4_fire_dense", s);
-  k4_fire_dense<<<host_flat_grid(a.g.E), 32 * WARPS, 0, s>>>(a, work_out, n_out);
+  k4_fire_dense<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a, work_out, n_out);
 }
 
 // later rounds: thread per listed row (any degree)
@@ -680,63 +871,45 @@ __device__ __forceinline__ void final_state(const FilterArgs &a, uint32_t s, uin
   }
 }
 
+struct FinalState {
+  uint32_t start, n, sp, dst, fl, own, ru;
+};
+
 __global__ void __launch_bounds__(32 * WARPS) k4_finalize(FilterArgs a) {
   const GraphArgs &g = a.g;
-  const uint32_t nwin = (uint32_t) (((uint64_t) g.E + 31u) / 32u);
-  for (uint32_t w = blockIdx.x * WARPS + (threadIdx.x >> 5); w < nwin; w += gridDim.x * WARPS) {
-    const Window W = open_window(g, w);
-    if (!__any_sync(FULL, W.own_lo)) continue;
-    uint32_t own_lo = 0, ru_lo = 0, f_lo = 0, u_lo = 0, ru_hi = 0, f_hi = 0, u_hi = 0;
-    if (W.own_lo) {
-      own_lo = a.vres[W.row];
-      u_lo = g.dst[W.s_lo];
-      f_lo = g.flags[W.s_lo];
-      ru_lo = a.vres[u_lo];
-    }
-    const uint32_t own_hi = __shfl_sync(FULL, own_lo, W.vb_last);
-    if (W.own_hi) {
-      u_hi = g.dst[W.s_hi];
-      f_hi = g.flags[W.s_hi];
-      ru_hi = a.vres[u_hi];
-    }
-    // pass 1: latest neighbour that fired into (row, direction)
-    int inc_lo0 = -1, inc_lo1 = -1, inc_hi0 = -1, inc_hi1 = -1;
-    const bool fin_lo = W.own_lo && (ru_lo & ((f_lo & F_RSENSE) ? VR_F1 : VR_F0));
-    const bool fin_hi = W.own_hi && (ru_hi & ((f_hi & F_RSENSE) ? VR_F1 : VR_F0));
-    const int id_lo = fin_lo ? (int) id_at(g, u_lo) : -1, id_hi = fin_hi ? (int) id_at(g, u_hi) : -1;
-    const uint32_t dir_lo = twin_dir((f_lo & F_RSENSE) != 0, (f_lo & F_RSAME) != 0) ? 1u : 0u;
-    const uint32_t dir_hi = twin_dir((f_hi & F_RSENSE) != 0, (f_hi & F_RSAME) != 0) ? 1u : 0u;
-    uint32_t m = __ballot_sync(FULL, fin_lo);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t rvb = __shfl_sync(FULL, W.vb, l), dir = __shfl_sync(FULL, dir_lo, l);
-      const int id = __shfl_sync(FULL, id_lo, l);
-      const bool rlast = __shfl_sync(FULL, (int) W.last, l) != 0;
-      if (W.own_lo && W.vb == rvb) {
-        if (dir) inc_lo1 = max(inc_lo1, id); else inc_lo0 = max(inc_lo0, id);
+  const uint32_t lane = lane_id();
+  for_each_window<4>(g,
+    [&](uint32_t start, uint32_t n) {
+      FinalState t;
+      t.start = start;
+      t.n = n;
+      const bool valid = lane < n;
+      const uint32_t s = start + lane;
+      t.sp = valid ? g.srcp[s] : NONE;
+      t.dst = valid ? g.dst[s] : 0u;
+      t.fl = valid ? g.flags[s] : 0u;
+      return t;
+    },
+    [&](FinalState &t) {
+      const bool valid = lane < t.n;
+      t.own = valid ? a.vres[t.sp & S_POS] : 0u;
+      t.ru = valid ? a.vres[t.dst] : 0u;
+    },
+    [&](FinalState &t) {
+      const Window W = open_window(t.start, t.n, t.sp);
+      const uint32_t f = t.fl, ru = t.ru;
+      // pass 1: latest neighbour that fired into (row, direction)
+      int inc0 = -1, inc1 = -1;
+      const bool fin = W.valid && (ru & ((f & F_RSENSE) ? VR_F1 : VR_F0));
+      const int id = fin ? (int) id_at(g, t.dst) : -1;
+      const uint32_t dir = twin_dir((f & F_RSENSE) != 0, (f & F_RSAME) != 0) ? 1u : 0u;
+      if (__any_sync(FULL, fin)) {
+        inc0 = row_max(fin && !dir ? id : -1, W.vb, W.ve);
+        inc1 = row_max(fin && dir ? id : -1, W.vb, W.ve);
       }
-      if (W.own_hi && rlast) {
-        if (dir) inc_hi1 = max(inc_hi1, id); else inc_hi0 = max(inc_hi0, id);
-      }
-    }
-    m = __ballot_sync(FULL, fin_hi);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t dir = __shfl_sync(FULL, dir_hi, l);
-      const int id = __shfl_sync(FULL, id_hi, l);
-      if (W.own_lo && W.last) {
-        if (dir) inc_lo1 = max(inc_lo1, id); else inc_lo0 = max(inc_lo0, id);
-      }
-      if (W.own_hi) {
-        if (dir) inc_hi1 = max(inc_hi1, id); else inc_hi0 = max(inc_hi0, id);
-      }
-    }
-    // pass 2
-    if (W.own_lo) final_state(a, W.s_lo, f_lo, ru_lo, own_lo, W.row, inc_lo0, inc_lo1);
-    if (W.own_hi) final_state(a, W.s_hi, f_hi, ru_hi, own_hi, W.row_last, inc_hi0, inc_hi1);
-  }
+      // pass 2
+      if (W.valid) final_state(a, W.s, f, ru, t.own, W.row, inc0, inc1);
+    });
 }
 
 // warp per big row
@@ -775,7 +948,7 @@ void launch_finalize(const FilterArgs &a, cudaStream_t s) {
   if (a.g.E == 0) return;
   {
     KernelTimer t_("k4_finalize", s);
-    k4_finalize<<<host_flat_grid(a.g.E), 32 * WARPS, 0, s>>>(a);
+    k4_finalize<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_finalize_big", s);

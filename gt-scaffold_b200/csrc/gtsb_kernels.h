@@ -35,6 +35,7 @@ enum {
   CNT_FALLBACK,           // FB_* bits: the line-ordered build cannot handle this input
   CNT_EDGES,              // slots written by the line-ordered build
   CNT_CORRECTIONS,        // reverse-flag corrections posted by k2_resolve
+  CNT_WINDOWS,            // windows cut by k4_pack_windows
   CNT_NUM
 };
 
@@ -138,6 +139,8 @@ struct GraphArgs {
   uint32_t V, E;
   int sm_count;
   const uint32_t *row_ptr, *vid, *pos, *srcp, *dst;
+  const uint32_t *win_start;                // [n_windows + 1] windows of whole rows, <= 32 slots each
+  uint32_t n_windows;
   const int32_t *dist;
   const float *std_dev;
   uint8_t *flags;
@@ -181,6 +184,9 @@ void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out,
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
 void launch_finalize(const FilterArgs &a, cudaStream_t s);
+// cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)
+int launch_pack_windows(const GraphArgs &g, uint32_t *count, uint32_t *woff, uint32_t *win_start,
+                        uint32_t *scan_scratch, cudaStream_t s);
 // srcp column, F_LT flags and the big-row list of a plain CSR that was uploaded
 void launch_fill_srcp(const GraphArgs &g, uint32_t *srcp, uint32_t *big_rows, cudaStream_t s);
 
