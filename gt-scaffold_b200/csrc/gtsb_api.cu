@@ -75,7 +75,7 @@ struct gtsb_context {
   DevBuf wcount, woff, win_start;
   uint32_t n_windows = 0;
   DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
-      tmp_cursor, bucket, corrections, lineless_flag, lineless_rank;
+      tmp_cursor, bucket, bucket_line, corrections, lineless_flag, lineless_rank;
   DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
   uint32_t fallback_reason = 0;
   int force_general = 0;
@@ -312,11 +312,13 @@ int do_build_lines(gtsb_context *c) {
   ENSURE(c->rf, R);
   ENSURE(c->cnt_in, (V + 2) * 4);
   ENSURE(c->bptr2, (V + 2) * 4);
-  ENSURE(c->cursor2, (V + 2) * 4);
+  const uint64_t ngrp = (V >> GROUP_SHIFT) + 2;
+  ENSURE(c->cursor2, ngrp * 4);
   ENSURE(c->tmp_ent, R * sizeof(uint4));
   ENSURE(c->tmp_dest, R * 4);
   ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
   ENSURE(c->bucket, R * sizeof(uint4));
+  ENSURE(c->bucket_line, R + 16);
   const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
   ENSURE(c->corrections, (size_t) corr_cap * sizeof(uint4));
   ENSURE(c->lineless_flag, V + 1);
@@ -330,7 +332,7 @@ int do_build_lines(gtsb_context *c) {
   CK(cudaMemsetAsync(c->pos.p, 0xFF, (V + 1) * 4, s));
   CK(cudaMemsetAsync(c->cnt_in.p, 0, (V + 2) * 4, s));
   CK(cudaMemsetAsync(c->nown.p, 0, (V + 2) * 4, s));
-  CK(cudaMemsetAsync(c->cursor2.p, 0, (V + 2) * 4, s));
+  CK(cudaMemsetAsync(c->cursor2.p, 0, ngrp * 4, s));
   CK(cudaMemsetAsync(c->estate.p, 0, 2 * R ? 2 * R : 1, s));   // GIS_UNVISITED, graph.c:162
   CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, s));
 
@@ -361,6 +363,7 @@ int do_build_lines(gtsb_context *c) {
   a.k0 = c->k0.as<uint32_t>();
   a.tmp_ent = c->tmp_ent.as<uint4>();
   a.bucket = c->bucket.as<uint4>();
+  a.bucket_line = c->bucket_line.as<uint8_t>();
   a.corrections = c->corrections.as<uint4>();
   a.tmp_dest = c->tmp_dest.as<uint32_t>();
   a.tmp_cursor = c->tmp_cursor.as<uint32_t>();
@@ -726,7 +729,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
                     &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->wcount, &c->woff, &c->win_start, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
-                    &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket,
+                    &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
                     &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg};
   for (DevBuf *b : bufs) release(*b);

@@ -38,6 +38,10 @@ constexpr uint32_t UNSET = 0xFFFFFFFFu;
 constexpr int HEAD_TILE = 4096;             // records per block in the head passes
 constexpr uint32_t RF_UP = 1, RF_FIRST = 2;  // per-record flag byte
 constexpr uint32_t RF_LT = 4;                // id(ctg) < id(root): F_LT of the record's own slot
+constexpr uint32_t RF_DUP = 8;               // the line holds another record of the same neighbour
+constexpr uint32_t RF_CREATOR = RF_UP | RF_FIRST;
+constexpr int SEG_SHIFT = 7;                 // log2(SEG_LINES)
+static_assert((1 << SEG_SHIFT) == SEG_LINES, "SEG_SHIFT");
 
 // mailbox entry (uint4): x = k of the creator, y = position of the creator's
 // line | M_* bits, z = seed dist, w = seed std_dev
@@ -200,10 +204,15 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
         atomicOr(&a.counters[CNT_ERROR], 2u);
       } else {
         pc = a.pos[c];
-        bool first = true;
-        for (uint32_t t = s_ls[j] - g.rec0; t < r; t++) first &= s_ctg[t] != c;
-        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u));
-        if ((rf & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST)) {
+        bool first = true, dup = false;
+        for (uint32_t t = s_ls[j] - g.rec0; t < s_ls[j + 1] - g.rec0; t++)
+          if (s_ctg[t] == c && t != r) {
+            dup = true;
+            first &= t > r;
+          }
+        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u) |
+                        (dup ? RF_DUP : 0u));
+        if ((rf & RF_CREATOR) == RF_CREATOR) {
           atomicAdd(&a.cnt_in[pc], 1u);
           atomicAdd(&s_nown[j], 1u);
         }
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
   __syncthreads();
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
-    if ((s_rf[r] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST)) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
+    if ((s_rf[r] & RF_CREATOR) == RF_CREATOR) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
     if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   uint32_t carry = a.k0[g.p0];
   for (uint32_t base = 0; base < g.n; base += blockDim.x) {
     const uint32_t r = base + threadIdx.x;
-    const bool creator = r < g.n && (s_rf[r] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST);
+    const bool creator = r < g.n && (s_rf[r] & RF_CREATOR) == RF_CREATOR;
     uint32_t total;
     const uint32_t k = carry + block_excl_scan(creator ? 1u : 0u, &total);   // syncs: bin bases visible
     carry += total;
@@ -265,12 +274,14 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     // final flags of edge root->c: strict running maximum over the line's records
     float best = s_std[r];
     uint32_t bf = s_fl[r];
-    const uint32_t rb = s_ls[j + 1] - g.rec0;
-    for (uint32_t t = r + 1; t < rb; t++)
-      if (s_pc[t] == pc && best < s_std[t]) {
-        best = s_std[t];
-        bf = s_fl[t];
-      }
+    if (s_rf[r] & RF_DUP) {
+      const uint32_t rb = s_ls[j + 1] - g.rec0;
+      for (uint32_t t = r + 1; t < rb; t++)
+        if (s_pc[t] == pc && best < s_std[t]) {
+          best = s_std[t];
+          bf = s_fl[t];
+        }
+    }
     const uint32_t sf = s_fl[r];
     uint4 e;
     e.x = k;
@@ -286,9 +297,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   }
 }
 
-// pass D-B: stream the coarsely sorted entries into their mailboxes; the
-// targets of concurrently running blocks stay inside one or two coarse bins,
-// i.e. inside L2.  Four independent chains per thread hide the atomic latency.
+// pass D-B: stream the coarsely sorted entries into the mailbox region of
+// their destination GROUP of 2^GROUP_SHIFT positions (k2_resolve sorts a
+// segment's mail by line in shared memory).  One cursor per group: few enough
+// to stay cache-resident, enough of them that the atomics of the threads in
+// flight do not queue up on the same address (measured: ~70 ns per queued
+// same-address atomic).
 __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
   if (a.counters[CNT_FALLBACK] | a.counters[CNT_ERROR]) return;
   constexpr int ILP = 4;
@@ -305,10 +319,16 @@ __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
     }
 #pragma unroll
     for (int k = 0; k < ILP; k++)
-      if (pc[k] != UNSET) at[k] = a.bptr[pc[k]] + atomicAdd(&a.cursor[pc[k]], 1u);
+      if (pc[k] != UNSET) {
+        const uint32_t grp = pc[k] >> GROUP_SHIFT;
+        at[k] = a.bptr[grp << GROUP_SHIFT] + atomicAdd(&a.cursor[grp], 1u);
+      }
 #pragma unroll
     for (int k = 0; k < ILP; k++)
-      if (pc[k] != UNSET) a.bucket[at[k]] = ent[k];
+      if (pc[k] != UNSET) {
+        a.bucket[at[k]] = ent[k];
+        a.bucket_line[at[k]] = (uint8_t) (pc[k] & (SEG_LINES - 1));
+      }
   }
 }
 
@@ -323,18 +343,21 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + SEG_ENT_CAP);
   uint32_t *s_bp = s_ls + SEG_LINES + 4;
   uint32_t *s_k0 = s_bp + SEG_LINES + 4;            // creators before each line
-  uint32_t *s_pc = s_k0 + SEG_LINES + 4;
-  int32_t *s_dist = reinterpret_cast<int32_t *>(s_pc + SEG_REC_CAP);
-  float *s_std = reinterpret_cast<float *>(s_dist + SEG_REC_CAP);
-  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_std + SEG_REC_CAP);
+  uint32_t *s_fill = s_k0 + SEG_LINES + 4;
+  uint32_t *s_pc = s_fill + SEG_LINES + 4;
+  float *s_std = reinterpret_cast<float *>(s_pc + SEG_REC_CAP);
+  uint16_t *s_match = reinterpret_cast<uint16_t *>(s_std + SEG_REC_CAP);   // mail entry -> the line's first record of that neighbour
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_match + SEG_ENT_CAP);
   uint8_t *s_rf = s_fl + SEG_REC_CAP;
   uint8_t *s_line = s_rf + SEG_REC_CAP;
   uint8_t *s_eline = s_line + SEG_REC_CAP;
+  constexpr uint16_t NO_MATCH = 0xFFFF;
   Seg g;
   if (!seg_open(a, blockIdx.x, g, s_ls)) return;
   for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) {
     s_bp[j] = a.bptr[g.p0 + j];
     s_k0[j] = a.k0[g.p0 + j];
+    s_fill[j] = 0;
   }
   __syncthreads();
   const uint32_t ent0 = s_bp[0], nent = s_bp[g.nlines] - ent0;
@@ -343,16 +366,20 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     return;
   }
   seg_lines(a, g, s_ls, s_line);
-  for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x)
-    for (uint32_t e = s_bp[j] - ent0; e < s_bp[j + 1] - ent0; e++) s_eline[e] = (uint8_t) j;
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
     s_pc[r] = a.pc[g.rec0 + r];
-    s_dist[r] = a.dist[g.rec0 + r];
     s_std[r] = a.std_dev[g.rec0 + r];
     s_fl[r] = a.flags[g.rec0 + r];
     s_rf[r] = a.rf[g.rec0 + r];
   }
-  for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) s_ent[e] = a.bucket[ent0 + e];
+  // the segment's mail, counting-sorted by line
+  for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) {
+    const uint32_t j = a.bucket_line[ent0 + e];
+    const uint32_t at = s_bp[j] - ent0 + atomicAdd(&s_fill[j], 1u);
+    s_ent[at] = a.bucket[ent0 + e];
+    s_eline[at] = (uint8_t) j;
+    s_match[at] = NO_MATCH;
+  }
   // row offsets
   for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) {
     const uint32_t p = g.p0 + j;
@@ -368,11 +395,56 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     }
   }
   __syncthreads();
+  // own records: creators write their slot (rank among the line's creators from
+  // a block scan), down records find their mail
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < g.n; base += blockDim.x) {
+    const uint32_t t = base + threadIdx.x;
+    const bool live = t < g.n;
+    const uint32_t rf = live ? s_rf[t] : 0u;
+    uint32_t total;
+    const uint32_t before = carry + block_excl_scan((rf & RF_CREATOR) == RF_CREATOR ? 1u : 0u, &total);
+    carry += total;
+    if (!(rf & RF_FIRST)) continue;
+    const uint32_t j = s_line[t], c = s_pc[t];
+    const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
+    if (!(rf & RF_UP)) {                          // down: the creator's mail must be here
+      bool found = false;
+      for (uint32_t e = ea; e < eb; e++)
+        if ((s_ent[e].y & E_OTHER_MASK) == c) {
+          s_match[e] = (uint16_t) t;
+          found = true;
+        }
+      if (!found) raise(a.counters, FB_DOWN_ORPHAN);
+      continue;
+    }
+    const uint32_t q = before - (s_k0[j] - s_k0[0]);
+    float best = s_std[t];
+    uint32_t bi = t;
+    if (rf & RF_DUP) {
+      const uint32_t rb = s_ls[j + 1] - g.rec0;
+      for (uint32_t t2 = t + 1; t2 < rb; t2++)
+        if (s_pc[t2] == c && best < s_std[t2]) {
+          best = s_std[t2];
+          bi = t2;
+        }
+    }
+    const uint32_t bf = s_fl[bi] & (F_SENSE | F_SAME);
+    const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
+    const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
+    const uint32_t slot = row0 + (eb - ea) + q;
+    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
+    a.dst[slot] = c;
+    a.edist[slot] = a.dist[g.rec0 + bi];
+    a.estd[slot] = best;
+    a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u) | ((rf & RF_LT) ? F_LT : 0u));
+    a.eid[slot] = 2u * (s_k0[j] + q);
+  }
+  __syncthreads();
   // twin-created slots, ordered by the creator's k
   for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) {
     const uint32_t j = s_eline[e];
     const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
-    const uint32_t ra = s_ls[j] - g.rec0, rb = s_ls[j + 1] - g.rec0;
     const uint4 m = s_ent[e];
     const uint32_t u = m.y & E_OTHER_MASK;
     uint32_t rank = 0;
@@ -383,12 +455,20 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     float best = __uint_as_float(m.w);
     int32_t bdist = (int32_t) m.z;
     uint32_t bf = seedf;
-    for (uint32_t t = ra; t < rb; t++)
-      if (s_pc[t] == u && best < s_std[t]) {                                   // parser.c:362
-        best = s_std[t];
-        bdist = s_dist[t];
-        bf = s_fl[t] & (F_SENSE | F_SAME);
+    const uint32_t t0 = s_match[e];
+    if (t0 != NO_MATCH) {                          // the line's own records of u, in file order
+      const uint32_t rb = (s_rf[t0] & RF_DUP) ? s_ls[j + 1] - g.rec0 : t0 + 1u;
+      uint32_t bi = NO_MATCH;
+      for (uint32_t t = t0; t < rb; t++)
+        if (s_pc[t] == u && best < s_std[t]) {                                 // parser.c:362
+          best = s_std[t];
+          bi = t;
+        }
+      if (bi != NO_MATCH) {
+        bdist = a.dist[g.rec0 + bi];
+        bf = s_fl[bi] & (F_SENSE | F_SAME);
       }
+    }
     const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
     const uint32_t slot = row0 + rank;
     a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
@@ -404,40 +484,6 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
       if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, g.p0 + j, bf, 0u);
       else raise(a.counters, FB_SEGMENT);
     }
-  }
-  // own records: creators write their slot, down records check their mail
-  for (uint32_t t = threadIdx.x; t < g.n; t += blockDim.x) {
-    const uint32_t rf = s_rf[t];
-    if (!(rf & RF_FIRST)) continue;
-    const uint32_t j = s_line[t], c = s_pc[t];
-    const uint32_t ea = s_bp[j] - ent0, eb = s_bp[j + 1] - ent0;
-    const uint32_t ra = s_ls[j] - g.rec0, rb = s_ls[j + 1] - g.rec0;
-    if (!(rf & RF_UP)) {                          // down: the creator's mail must be here
-      bool found = false;
-      for (uint32_t e = ea; e < eb; e++) found |= (s_ent[e].y & E_OTHER_MASK) == c;
-      if (!found) raise(a.counters, FB_DOWN_ORPHAN);
-      continue;
-    }
-    uint32_t q = 0;
-    for (uint32_t t2 = ra; t2 < t; t2++) q += (s_rf[t2] & (RF_UP | RF_FIRST)) == (RF_UP | RF_FIRST);
-    float best = s_std[t];
-    int32_t bdist = s_dist[t];
-    uint32_t bf = s_fl[t] & (F_SENSE | F_SAME);
-    for (uint32_t t2 = t + 1; t2 < rb; t2++)
-      if (s_pc[t2] == c && best < s_std[t2]) {
-        best = s_std[t2];
-        bdist = s_dist[t2];
-        bf = s_fl[t2] & (F_SENSE | F_SAME);
-      }
-    const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
-    const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
-    const uint32_t slot = row0 + (eb - ea) + q;
-    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
-    a.dst[slot] = c;
-    a.edist[slot] = bdist;
-    a.estd[slot] = best;
-    a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u) | ((rf & RF_LT) ? F_LT : 0u));
-    a.eid[slot] = 2u * (s_k0[j] + q);
   }
 }
 
@@ -498,7 +544,7 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
 
 size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
 size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
-size_t build2_smem_resolve() { return SEG_ENT_CAP * 17 + 3 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 15 + 16; }
+size_t build2_smem_resolve() { return SEG_ENT_CAP * 19 + 4 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 16; }
 
 int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);

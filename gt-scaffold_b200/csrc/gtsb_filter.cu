@@ -404,7 +404,7 @@ struct PairsState {
   uint8_t es;
 };
 
-__global__ void __launch_bounds__(32 * WARPS) k4_pairs(FilterArgs a) {
+__global__ void __launch_bounds__(32 * WARPS, 4) k4_pairs(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
   for_each_window<2>(g,
@@ -753,7 +753,7 @@ struct DenseState {
   uint32_t start, n, sp, dst, fl, st, su;
 };
 
-__global__ void __launch_bounds__(32 * WARPS) k4_fire_dense(FilterArgs a, uint32_t *__restrict__ work_out,
+__global__ void __launch_bounds__(32 * WARPS, 6) k4_fire_dense(FilterArgs a, uint32_t *__restrict__ work_out,
                                                              uint32_t *__restrict__ n_out) {
   const GraphArgs &g = a.g;
   const volatile uint8_t *fstat = a.fstat;
@@ -875,7 +875,7 @@ struct FinalState {
   uint32_t start, n, sp, dst, fl, own, ru;
 };
 
-__global__ void __launch_bounds__(32 * WARPS) k4_finalize(FilterArgs a) {
+__global__ void __launch_bounds__(32 * WARPS, 6) k4_finalize(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
   for_each_window<4>(g,

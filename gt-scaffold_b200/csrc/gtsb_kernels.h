@@ -53,6 +53,7 @@ constexpr uint32_t SEG_REC_CAP = 2048;    // staged records per segment
 constexpr uint32_t SEG_ENT_CAP = 1536;    // staged mailbox entries per segment
 constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread scans accept
 constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
+constexpr int GROUP_SHIFT = 3;            // mail is delivered to groups of 8 positions
 
 struct Build2Args {
   uint64_t R;
@@ -66,8 +67,10 @@ struct Build2Args {
   uint32_t *pos, *vid, *ls;                 // [V], [V], [V+1]
   uint32_t *tile_cnt, *tile_off;            // head tiles
   uint8_t *rf;                              // [R] RF_UP | RF_FIRST
-  uint32_t *cnt_in, *bptr, *cursor;         // [V+1] mailbox sizes / offsets / fill
+  uint32_t *cnt_in, *bptr;                  // [V+1] mailbox sizes / offsets
+  uint32_t *cursor;                         // [V >> GROUP_SHIFT] fill of every group's mailbox region
   uint4 *tmp_ent, *bucket, *corrections;
+  uint8_t *bucket_line;                     // [creators] line (within its segment) of every delivered entry
   uint32_t *tmp_dest, *tmp_cursor;
   uint8_t *lineless_flag;
   uint32_t *lineless_rank, *scan_scratch, *counters, *big_rows;
