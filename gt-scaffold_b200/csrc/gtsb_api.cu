@@ -339,6 +339,7 @@ int do_build_lines(gtsb_context *c) {
   Build2Args a{};
   a.R = R;
   a.V = (uint32_t) V;
+  a.Vg = (uint32_t) V;
   a.sm_count = c->sm_count;
   uint32_t shift = 0;
   while (((V ? V - 1 : 0) >> shift) >= (uint64_t) NB_COARSE) shift++;
@@ -362,6 +363,8 @@ int do_build_lines(gtsb_context *c) {
   a.nown = c->nown.as<uint32_t>();
   a.k0 = c->k0.as<uint32_t>();
   a.tmp_ent = c->tmp_ent.as<uint4>();
+  a.mail_ent = c->tmp_ent.as<uint4>();
+  a.mail_dest = c->tmp_dest.as<uint32_t>();
   a.bucket = c->bucket.as<uint4>();
   a.bucket_line = c->bucket_line.as<uint8_t>();
   a.corrections = c->corrections.as<uint4>();

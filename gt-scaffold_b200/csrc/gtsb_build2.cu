@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k2_head_counts(uint64_t R, const uint32_t
   if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V,
+__global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V, uint32_t Vg, uint32_t pos_base,
                                                       const uint32_t *__restrict__ root,
                                                       const uint32_t *__restrict__ tile_off,
                                                       uint32_t *__restrict__ ls, uint32_t *__restrict__ vid,
@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V,
   for (int k = 0; k < ITEMS; k++) {
     if (!((heads >> k) & 1u)) continue;
     const uint32_t r = mine[k];
-    if (r >= V) {
+    if (r >= Vg) {
       atomicOr(&counters[CNT_ERROR], 1u);
     } else if (l < V) {
       ls[l] = (uint32_t) (base + k);
       vid[l] = r;
-      if (atomicExch(&pos[r], l) != UNSET) raise(counters, FB_MULTIRUN);
+      if (atomicExch(&pos[r], pos_base + l) != UNSET) raise(counters, FB_MULTIRUN);
     } else {
       raise(counters, FB_MULTIRUN);     // more lines than vertices
     }
@@ -185,9 +185,14 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   uint32_t *s_nown = s_ls + SEG_LINES + 4;
   uint32_t *s_ctg = s_nown + SEG_LINES + 4;
   uint8_t *s_line = reinterpret_cast<uint8_t *>(s_ctg + SEG_REC_CAP);
+  __shared__ uint32_t s_bounds[MAX_RANKS + 1], s_rcnt[MAX_RANKS];
   Seg g;
   const bool ok = seg_open(a, blockIdx.x, g, s_ls);
   for (uint32_t j = threadIdx.x; j < SEG_LINES; j += blockDim.x) s_nown[j] = 0;
+  for (uint32_t j = threadIdx.x; j < (uint32_t) a.nranks; j += blockDim.x) {
+    s_rcnt[j] = 0;
+    s_bounds[j + 1] = a.rank_bounds[j + 1];
+  }
   if (ok) {
     seg_lines(a, g, s_ls, s_line);
     for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) s_ctg[r] = a.ctg[g.rec0 + r];
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
       uint8_t rf = 0;
       uint32_t pc = UNSET;
       const uint32_t me = a.vid[p];
-      if (c >= a.V) {
+      if (c >= a.Vg) {
         atomicOr(&a.counters[CNT_ERROR], 1u);
       } else if (c == me) {
         atomicOr(&a.counters[CNT_ERROR], 2u);
@@ -210,11 +215,17 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
             dup = true;
             first &= t > r;
           }
-        rf = (uint8_t) ((p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u) |
+        rf = (uint8_t) ((a.pos_base + p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u) |
                         (dup ? RF_DUP : 0u));
         if ((rf & RF_CREATOR) == RF_CREATOR) {
-          atomicAdd(&a.cnt_in[pc], 1u);
           atomicAdd(&s_nown[j], 1u);
+          if (a.nranks == 0) {
+            atomicAdd(&a.cnt_in[pc], 1u);
+          } else {                                    // partitioned: the receiving rank counts its mail
+            uint32_t o = 0;
+            while (o + 1 < (uint32_t) a.nranks && pc >= s_bounds[o + 1]) o++;
+            atomicAdd(&s_rcnt[o], 1u);
+          }
         }
       }
       a.rf[g.rec0 + r] = rf;
@@ -223,10 +234,22 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   }
   __syncthreads();
   for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) a.nown[g.p0 + j] = s_nown[j];
+  for (uint32_t j = threadIdx.x; j < (uint32_t) a.nranks; j += blockDim.x)
+    if (s_rcnt[j]) atomicAdd(&a.rank_cnt[j], s_rcnt[j]);
 }
 
 __global__ void k2_init_cursors(Build2Args a) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.nranks) {                                  // bins = destination ranks, sized by k2_classify's counts
+    if (b == 0) {
+      uint32_t run = 0;
+      for (int r = 0; r < a.nranks; r++) {
+        a.tmp_cursor[r] = run;
+        run += a.rank_cnt[r];
+      }
+    }
+    return;
+  }
   if (b > NB_COARSE) return;
   const uint64_t p = (uint64_t) b << a.coarse_shift;
   a.tmp_cursor[b] = a.bptr[p < a.V ? p : a.V];
@@ -245,8 +268,17 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_bin + 3 * NB_COARSE);
   uint8_t *s_rf = s_fl + SEG_REC_CAP;
   uint8_t *s_line = s_rf + SEG_REC_CAP;
+  __shared__ uint32_t s_bounds[MAX_RANKS + 1];
   Seg g;
   if (!seg_open(a, blockIdx.x, g, s_ls)) return;
+  for (uint32_t j = threadIdx.x; j < (uint32_t) a.nranks; j += blockDim.x) s_bounds[j + 1] = a.rank_bounds[j + 1];
+  // coarse bin of a destination position: a range of positions, or the rank that holds it
+  auto bin_of = [&](uint32_t pc) -> uint32_t {
+    if (a.nranks == 0) return pc >> a.coarse_shift;
+    uint32_t o = 0;
+    while (o + 1 < (uint32_t) a.nranks && pc >= s_bounds[o + 1]) o++;
+    return o;
+  };
   seg_lines(a, g, s_ls, s_line);
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
     s_pc[r] = a.pc[g.rec0 + r];
@@ -257,12 +289,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
   __syncthreads();
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
-    if ((s_rf[r] & RF_CREATOR) == RF_CREATOR) atomicAdd(&s_bin[s_pc[r] >> a.coarse_shift], 1u);
+    if ((s_rf[r] & RF_CREATOR) == RF_CREATOR) atomicAdd(&s_bin[bin_of(s_pc[r])], 1u);
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
     if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
   // creator rank in record order = k - k0[first line]: one block scan per 256 records
-  uint32_t carry = a.k0[g.p0];
+  uint32_t carry = a.k_base + a.k0[g.p0];
   for (uint32_t base = 0; base < g.n; base += blockDim.x) {
     const uint32_t r = base + threadIdx.x;
     const bool creator = r < g.n && (s_rf[r] & RF_CREATOR) == RF_CREATOR;
@@ -285,12 +317,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     const uint32_t sf = s_fl[r];
     uint4 e;
     e.x = k;
-    e.y = (g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
+    e.y = (a.pos_base + g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
           ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u) |
           ((s_rf[r] & RF_LT) ? 0u : M_LT);
     e.z = (uint32_t) a.dist[g.rec0 + r];
     e.w = __float_as_uint(s_std[r]);
-    const uint32_t b = pc >> a.coarse_shift;
+    const uint32_t b = bin_of(pc);
     const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
     a.tmp_ent[at] = e;
     a.tmp_dest[at] = pc;
@@ -314,8 +346,8 @@ __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
 #pragma unroll
     for (int k = 0; k < ILP; k++) {
       const uint32_t e = e0 + k * stride;
-      pc[k] = e < n ? a.tmp_dest[e] : UNSET;
-      if (e < n) ent[k] = a.tmp_ent[e];
+      pc[k] = e < n ? a.mail_dest[e] - a.pos_base : UNSET;
+      if (e < n) ent[k] = a.mail_ent[e];
     }
 #pragma unroll
     for (int k = 0; k < ILP; k++)
@@ -391,7 +423,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     }
     if (deg > BIG_ROW) {
       atomicMax(&a.counters[CNT_MAX_DEG], deg);
-      a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = p;
+      a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = a.pos_base + p;
     }
   }
   __syncthreads();
@@ -433,12 +465,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     const bool sm = (s_fl[t] & F_SAME) != 0, tw = twin_dir((s_fl[t] & F_SENSE) != 0, sm);
     const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
     const uint32_t slot = row0 + (eb - ea) + q;
-    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
+    a.srcp[slot] = (a.pos_base + g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
     a.dst[slot] = c;
     a.edist[slot] = a.dist[g.rec0 + bi];
     a.estd[slot] = best;
     a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u) | ((rf & RF_LT) ? F_LT : 0u));
-    a.eid[slot] = 2u * (s_k0[j] + q);
+    a.eid[slot] = 2u * (a.k_base + s_k0[j] + q);
   }
   __syncthreads();
   // twin-created slots, ordered by the creator's k
@@ -471,7 +503,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     }
     const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
     const uint32_t slot = row0 + rank;
-    a.srcp[slot] = (g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
+    a.srcp[slot] = (a.pos_base + g.p0 + j) | (deg > BIG_ROW ? S_BIG : 0u);
     a.dst[slot] = u;
     a.edist[slot] = bdist;
     a.estd[slot] = best;
@@ -481,22 +513,34 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     if (bf != seedf) {
       // the creator assumed its twin keeps the seed's flags: tell it otherwise
       const uint32_t at = atomicAdd(&a.counters[CNT_CORRECTIONS], 1u);
-      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, g.p0 + j, bf, 0u);
+      if (at < a.corrections_cap) a.corrections[at] = make_uint4(u, a.pos_base + g.p0 + j, bf, 0u);
       else raise(a.counters, FB_SEGMENT);
     }
   }
 }
 
 // fix-up: reverse flags of creator-side slots whose twin did not keep the seed
-__global__ void __launch_bounds__(128) k2_corrections(Build2Args a) {
+// {position of the creator's row, position of the twin's row, flags of the twin}
+__global__ void __launch_bounds__(128) k2_corrections(Build2Args a, const uint4 *__restrict__ list,
+                                                       const uint32_t *__restrict__ n_dev, uint32_t n_host) {
   if (a.counters[CNT_FALLBACK] | a.counters[CNT_ERROR]) return;
-  const uint32_t n = min(a.counters[CNT_CORRECTIONS], a.corrections_cap);
+  const uint32_t n = n_dev != nullptr ? min(*n_dev, a.corrections_cap) : n_host;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint4 c = a.corrections[i];
-    for (uint32_t s = a.row_ptr[c.x]; s < a.row_ptr[c.x + 1]; s++)
+    const uint4 c = list[i];
+    const uint32_t row = c.x - a.pos_base;
+    if (row >= a.V) continue;                      // another rank's row
+    for (uint32_t s = a.row_ptr[row]; s < a.row_ptr[row + 1]; s++)
       if (a.dst[s] == c.y)
         a.eflags[s] = (uint8_t) ((a.eflags[s] & (F_SENSE | F_SAME | F_LT)) | ((c.z & F_SENSE) ? F_RSENSE : 0u) |
                                  ((c.z & F_SAME) ? F_RSAME : 0u));
+  }
+}
+
+// partitioned build: mail received per local position
+__global__ void __launch_bounds__(256) k2_count_mail(Build2Args a, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = a.mail_dest[i] - a.pos_base;
+    if (p < a.V) atomicAdd(&a.cnt_in[p], 1u); else atomicOr(&a.counters[CNT_ERROR], 8u);
   }
 }
 
@@ -546,14 +590,36 @@ size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5
 size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
 size_t build2_smem_resolve() { return SEG_ENT_CAP * 19 + 4 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 16; }
 
-int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
+static void build2_attrs() {
+  static bool attr_done = false;
+  if (attr_done) return;
+  cudaFuncSetAttribute(k2_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_classify());
+  cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
+  cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
+  attr_done = true;
+}
+
+int launch_b2_head_counts(const Build2Args &a, cudaStream_t s) {
   const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
+  k2_head_counts<<<ntiles, 256, 0, s>>>(a.R, a.root, a.tile_cnt);
+  exclusive_scan<uint32_t>(a.tile_cnt, ntiles, a.tile_off, a.scan_scratch, s);
+  return 4;
+}
+
+int launch_b2_head_write(const Build2Args &a, cudaStream_t s) {
+  const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
+  k2_head_write<<<ntiles, 256, 0, s>>>(a.R, a.V, a.Vg, a.pos_base, a.root, a.tile_off, a.ls, a.vid, a.pos,
+                                        a.counters);
+  return 1;
+}
+
+int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   {
     KernelTimer t_("k2_heads(2 kernels+scan)", s);
-    k2_head_counts<<<ntiles, 256, 0, s>>>(a.R, a.root, a.tile_cnt);
-    exclusive_scan<uint32_t>(a.tile_cnt, ntiles, a.tile_off, a.scan_scratch, s);
-    k2_head_write<<<ntiles, 256, 0, s>>>(a.R, a.V, a.root, a.tile_off, a.ls, a.vid, a.pos, a.counters);
+    launch_b2_head_counts(a, s);
+    launch_b2_head_write(a, s);
   }
+  const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
   KernelTimer t_("k2_lineless(2 kernels+scan)", s);
   const uint32_t vb = (a.V + 256) / 256;
   k2_lineless_flags<<<vb, 256, 0, s>>>(a.V, a.pos, a.lineless_flag);
@@ -563,37 +629,59 @@ int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   return 2 + 3 + 2 + 3;
 }
 
-int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k2_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_classify());
-    cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
-    cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
-    attr_done = true;
-  }
+int launch_b2_classify(const Build2Args &a, cudaStream_t s) {
+  build2_attrs();
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
-  {
-    KernelTimer t_("k2_classify", s);
-    k2_classify<<<nseg, SEG_THREADS, build2_smem_classify(), s>>>(a);
-  }
-  exclusive_scan<uint32_t>(a.cnt_in, a.V, a.bptr, a.scan_scratch, s);
-  exclusive_scan<uint32_t>(a.nown, a.V, a.k0, a.scan_scratch, s);
-  {
-    KernelTimer t_("k2_partition", s);
-    k2_init_cursors<<<1, 128, 0, s>>>(a);
-    k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
-  }
+  KernelTimer t_("k2_classify", s);
+  k2_classify<<<nseg, SEG_THREADS, build2_smem_classify(), s>>>(a);
+  return 1;
+}
+
+int launch_b2_partition(const Build2Args &a, cudaStream_t s) {
+  build2_attrs();
+  const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  KernelTimer t_("k2_partition", s);
+  k2_init_cursors<<<1, 128, 0, s>>>(a);
+  k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
+  return 2;
+}
+
+int launch_b2_count_mail(const Build2Args &a, uint32_t n_mail, cudaStream_t s) {
+  if (n_mail == 0) return 0;
+  KernelTimer t_("k2_count_mail", s);
+  k2_count_mail<<<a.sm_count * 8, 256, 0, s>>>(a, n_mail);
+  return 1;
+}
+
+int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
+  build2_attrs();
+  const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
   {
     KernelTimer t_("k2_deliver", s);
     k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
   }
-  {
-    KernelTimer t_("k2_resolve", s);
-    k2_resolve<<<nseg, SEG_THREADS, build2_smem_resolve(), s>>>(a);
-  }
+  KernelTimer t_("k2_resolve", s);
+  k2_resolve<<<nseg, SEG_THREADS, build2_smem_resolve(), s>>>(a);
+  return 2;
+}
+
+int launch_b2_apply_corrections(const Build2Args &a, const uint4 *list, uint32_t n, cudaStream_t s) {
+  if (n == 0) return 0;
   KernelTimer t_("k2_corrections", s);
-  k2_corrections<<<64, 128, 0, s>>>(a);
-  return 1 + 6 + 2 + 1 + 1 + 1;
+  k2_corrections<<<64, 128, 0, s>>>(a, list, nullptr, n);
+  return 1;
+}
+
+int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
+  int n = launch_b2_classify(a, s);
+  exclusive_scan<uint32_t>(a.cnt_in, a.V, a.bptr, a.scan_scratch, s);
+  exclusive_scan<uint32_t>(a.nown, a.V, a.k0, a.scan_scratch, s);
+  n += 6;
+  n += launch_b2_partition(a, s);
+  n += launch_b2_deliver_resolve(a, s);
+  KernelTimer t_("k2_corrections", s);
+  k2_corrections<<<64, 128, 0, s>>>(a, a.corrections, a.counters + CNT_CORRECTIONS, 0u);
+  return n + 1;
 }
 
 int launch_export_csr(const ExportArgs &x, uint32_t *deg_tmp, uint32_t *scan_scratch, cudaStream_t s) {

@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(256) k4_vertex_facts(FilterArgs a, int do_repe
                                                         int fresh, float copy_num_cutoff,
                                                         float astat_cutoff, int use_copy_num) {
   const GraphArgs &g = a.g;
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= g.V) return;
+  const uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= g.V) return;
+  const uint32_t p = g.row_base + pl;
   const uint32_t v = id_at(g, p);
   const VAttr at = g.vattr[v];
   bool rep = false;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(512) k4_pairs_big(FilterArgs a) {
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
     const uint32_t p = g.big_rows[li];
     if (a.vinfo[p].y & VI_MARKED) continue;                        // block-uniform
-    const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
     for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
       cn[k] = __uint_as_float(a.vinfo[g.dst[r0 + k]].x);
       mark[k] = 0;
@@ -568,7 +569,9 @@ __global__ void __launch_bounds__(256) k4_dirty(FilterArgs a, uint32_t n) {
   const uint2 pr = a.proposals[i];
   if (a.poly_cur[pr.y] != id_at(g, pr.x)) return;             // not the winning proposer
   a.dirty[pr.y] = 1;
-  for (uint32_t s = g.row_ptr[pr.y]; s < g.row_ptr[pr.y + 1]; s++) a.dirty[g.dst[s]] = 1;
+  const uint32_t rl = pr.y - g.row_base;                      // the target's row, if this device holds it
+  if (rl >= g.V) return;
+  for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) a.dirty[g.dst[s]] = 1;
 }
 
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s) {
@@ -594,10 +597,11 @@ __global__ void __launch_bounds__(256) k4_fire_init(FilterArgs a, uint32_t *__re
   const GraphArgs &g = a.g;
   __shared__ uint32_t s_q[8][WarpQueue::QCAP];
   WarpQueue q{s_q[threadIdx.x >> 5], 0u};
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = g.row_base + pl;
   bool redo = false;
-  if (p < g.V) {
-    const uint32_t d = g.row_ptr[p + 1] - g.row_ptr[p];
+  if (pl < g.V) {
+    const uint32_t d = g.row_ptr[pl + 1] - g.row_ptr[pl];
     if (d <= BIG_ROW) {
       const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < id_at(g, p));
       redo = active && a.ocutoff >= 0 && d >= 2 && a.dirty[p] != 0;
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(128) k4_fire_redo(FilterArgs a, const uint32_t
   const uint32_t n = *n_redo;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = redo_list[i];
-    const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
     const uint32_t v_id = id_at(g, p);
     int32_t dist[BIG_ROW];
     uint32_t len[BIG_ROW];
@@ -659,7 +663,7 @@ __global__ void __launch_bounds__(512) k4_fire_init_big(FilterArgs a, uint32_t *
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
     const uint32_t p = g.big_rows[li];
     const uint32_t v_id = id_at(g, p);
-    const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
     const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < v_id);
     uint8_t gb = 0;
     if (active && a.ocutoff < 0) {
@@ -823,7 +827,8 @@ __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t
     uint8_t st = fstat[p];
     const uint32_t und = (~(uint32_t) st >> 2) & 3u;
     uint32_t res = 0;
-    for (uint32_t s = g.row_ptr[p]; s < g.row_ptr[p + 1]; s++) res |= fire_probe(g, fstat, s, und);
+    const uint32_t rl = p - g.row_base;
+    for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) res |= fire_probe(g, fstat, s, und);
     st = fire_decide(st, und, res);
     a.fstat[p] = st;
     again = (st & FS_DECIDED_ALL) != FS_DECIDED_ALL;
@@ -842,8 +847,9 @@ void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_
 
 __global__ void __launch_bounds__(256) k4_vres(FilterArgs a) {
   const GraphArgs &g = a.g;
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= g.V) return;
+  const uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= g.V) return;
+  const uint32_t p = g.row_base + pl;
   const uint32_t t = a.poly_cur[p];
   const uint32_t f = a.fstat[p];
   a.vres[p] = (t == NO_TIME ? VR_TIME_MASK : t) | ((f & 1u) ? VR_F0 : 0u) | ((f & 2u) ? VR_F1 : 0u) |
@@ -918,7 +924,7 @@ __global__ void __launch_bounds__(256) k4_finalize_big(FilterArgs a) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t li = warp; li < g.n_big_rows; li += nwarps) {
     const uint32_t p = g.big_rows[li];
-    const uint32_t r0 = g.row_ptr[p], d = g.row_ptr[p + 1] - r0;
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
     const uint32_t own = a.vres[p];
     int inc0 = -1, inc1 = -1;
     for (uint32_t k = lane_id(); k < d; k += 32) {

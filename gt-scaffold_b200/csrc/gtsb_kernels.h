@@ -55,9 +55,18 @@ constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread sc
 constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
 constexpr int GROUP_SHIFT = 3;            // mail is delivered to groups of 8 positions
 
+constexpr int MAX_RANKS = 64;
 struct Build2Args {
   uint64_t R;
-  uint32_t V;
+  uint32_t V;                               // positions (rows) held by this device
+  uint32_t Vg;                              // vertices of the whole graph (= V unless partitioned over ranks)
+  uint32_t pos_base;                        // global position of local position 0
+  uint32_t k_base;                          // creating records on earlier ranks
+  int nranks;                               // 0: single device
+  const uint32_t *rank_bounds;              // [nranks + 1] first global position of every rank
+  uint32_t *rank_cnt;                       // [nranks] mail this rank sends to every rank
+  const uint4 *mail_ent;                    // the stream k2_deliver reads (tmp_ent, or what the ranks sent us)
+  const uint32_t *mail_dest;
   int sm_count;
   uint32_t coarse_shift, corrections_cap;
   const uint32_t *root, *ctg;
@@ -83,6 +92,14 @@ struct Build2Args {
 };
 int launch_build2_lines(const Build2Args &a, cudaStream_t s);
 int launch_build2_rows(const Build2Args &a, cudaStream_t s);
+// the same passes one at a time, for the rank-partitioned build (gtsb_dist.cu)
+int launch_b2_head_counts(const Build2Args &a, cudaStream_t s);     // -> tile_off[ntiles] = number of lines
+int launch_b2_head_write(const Build2Args &a, cudaStream_t s);
+int launch_b2_classify(const Build2Args &a, cudaStream_t s);
+int launch_b2_partition(const Build2Args &a, cudaStream_t s);
+int launch_b2_count_mail(const Build2Args &a, uint32_t n_mail, cudaStream_t s);
+int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s);
+int launch_b2_apply_corrections(const Build2Args &a, const uint4 *list, uint32_t n, cudaStream_t s);
 
 struct ExportArgs {        // line layout -> plain CSR in vertex order
   uint32_t V;
@@ -139,7 +156,9 @@ void launch_build_emit(const BuildArgs &a, cudaStream_t s);
 constexpr uint32_t S_BIG = 1u << 31;      // srcp: slot of a row with more than BIG_ROW slots
 constexpr uint32_t S_POS = (1u << 27) - 1u;
 struct GraphArgs {
-  uint32_t V, E;
+  uint32_t V, E;                            // rows / slots held by this device
+  uint32_t row_base;                        // position of row 0 (0 unless the graph is partitioned over ranks):
+                                            // row_ptr is indexed by p - row_base, everything else by position p
   int sm_count;
   const uint32_t *row_ptr, *vid, *pos, *srcp, *dst;
   const uint32_t *win_start;                // [n_windows + 1] windows of whole rows, <= 32 slots each
