@@ -33,6 +33,7 @@ EXPORTS = [
     "gtsb_filter", "gtsb_pipeline", "gtsb_nof_edges", "gtsb_get_vertex_states", "gtsb_get_csr",
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
+    "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
 ]
 
 
@@ -90,6 +91,9 @@ def load_library():
     L.gtsb_get_profile.argtypes = [vp, C.c_char_p, u64, C.POINTER(C.c_double), C.POINTER(C.c_uint32),
                                    C.c_uint32]
     L.gtsb_ambig_thresholds.argtypes = [f32, C.POINTER(f32), C.POINTER(f32), C.POINTER(i32)]
+    L.gtsb_dist_unique_id.argtypes = [vp]
+    L.gtsb_dist_init.argtypes = [vp, i32, i32, vp]
+    L.gtsb_get_edges.argtypes = [vp, C.POINTER(u64)] + [vp] * 7
     _lib = L
     return L
 
@@ -103,6 +107,35 @@ def ambig_thresholds(cutoff: float):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def dist_unique_id() -> bytes:
+    """The 128-byte NCCL id rank 0 creates and hands to every rank (by the
+    caller's own means: torch.distributed, MPI, a file ...)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.gtsb_dist_unique_id(buf) != 0:
+        raise RuntimeError("gtsb_dist_unique_id failed (NCCL not loadable)")
+    return buf.raw
+
+
+def shard_lines(inp, world: int, rank: int):
+    """Rank `rank`'s share of a .de file: a contiguous chunk of whole lines
+    (maximal runs of one root contig), ranks in file order, balanced by record
+    count.  Vertex attributes are not sharded."""
+    root = np.asarray(inp.root)
+    R = root.shape[0]
+    cuts = [0]
+    for r in range(1, world):
+        i = min(R, (R * r) // world)
+        while 0 < i < R and root[i] == root[i - 1]:      # move to the next line start
+            i += 1
+        cuts.append(max(i, cuts[-1]))
+    cuts.append(R)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    kw = {k: getattr(inp, k)[lo:hi] for k in ("root", "ctg", "dist", "std_dev", "num_pairs", "flags")}
+    return type(inp)(inp.seq_len, inp.astat, inp.copy_num, name=inp.name,
+                     meta=dict(inp.meta, shard=(rank, world, lo, hi)), **kw)
 
 
 class ScaffoldGraphB200:
@@ -169,6 +202,11 @@ class ScaffoldGraphB200:
         g.build()
         return g
 
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """Join the ranks that hold one partitioned graph (NCCL over NVLink)."""
+        self._ck(self.L.gtsb_dist_init(self.h, rank, world, unique_id))
+        self.rank, self.world = rank, world
+
     # ---- the hot path
     def build(self):
         self._ck(self.L.gtsb_build(self.h))
@@ -198,6 +236,18 @@ class ScaffoldGraphB200:
         out = np.zeros(self.V, np.uint8)
         self._ck(self.L.gtsb_get_vertex_states(self.h, _ptr(out)))
         return out
+
+    def edges(self):
+        """This device's edges with vertex ids (all edges unless partitioned)."""
+        n = C.c_uint64()
+        self._ck(self.L.gtsb_get_edges(self.h, C.byref(n), *[None] * 7))
+        E = int(n.value)
+        o = dict(eid=np.zeros(E, np.uint32), src=np.zeros(E, np.uint32), dst=np.zeros(E, np.uint32),
+                 dist=np.zeros(E, np.int32), std_dev=np.zeros(E, np.float32), flags=np.zeros(E, np.uint8),
+                 estate=np.zeros(E, np.uint8))
+        self._ck(self.L.gtsb_get_edges(self.h, C.byref(n), *[_ptr(o[k]) for k in
+                                                             ("eid", "src", "dst", "dist", "std_dev", "flags", "estate")]))
+        return o
 
     def csr(self, eid=True, win_rec=False):
         E, V = self.E, self.V

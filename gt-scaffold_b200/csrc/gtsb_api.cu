@@ -1,29 +1,11 @@
 // gtsb_api.cu -- context, device memory and the C ABI (include/gtscaffold_b200.h).
-#include <math.h>
-#include <stdarg.h>
-#include <string.h>
-
-#include <string>
-#include <vector>
-
-#include "../../include/gtscaffold_b200.h"
-#include "gtsb_common.cuh"
-#include "gtsb_kernels.h"
+#include "gtsb_context.h"
 #include "gtsb_scan.cuh"
 #include "gtsb_threshold.h"
 
 using namespace gtsb;
 
 namespace gtsb {
-struct Profiler {
-  struct Rec { const char *name; cudaEvent_t a, b; };
-  std::vector<Rec> recs;
-  std::vector<cudaEvent_t> pool;
-  cudaEvent_t get() {
-    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
-    cudaEvent_t e; cudaEventCreate(&e); return e;
-  }
-};
 static thread_local Profiler *g_prof = nullptr;
 KernelTimer::KernelTimer(const char *n, cudaStream_t s) : name(n), stream(s), slot(-1) {
   if (g_prof == nullptr) return;
@@ -38,71 +20,7 @@ KernelTimer::~KernelTimer() {
 }
 }  // namespace gtsb
 
-namespace {
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-  bool owned = true;
-  template <typename T> T *as() const { return static_cast<T *>(p); }
-};
-
-struct Timer {
-  cudaEvent_t a = nullptr, b = nullptr;
-};
-
-}  // namespace
-
-struct gtsb_context {
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  std::string err;
-  bool want_win = false;
-
-  uint64_t V = 0, R = 0, E = 0;
-  bool have_vertices = false, have_records = false, have_graph = false;
-  bool line_layout = false;     // rows in .de line order (rs/re/vid/pos) instead of plain CSR
-  bool csr_exported = false;    // plain CSR copy of a line-layout graph is current
-
-  // inputs
-  DevBuf vattr, astat, seq_len_in, copy_num_in;
-  DevBuf root, ctg, dist, std_dev, flags;
-  // graph
-  DevBuf row_ptr, srcp, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
-  DevBuf vid, pos;              // line layout
-  DevBuf wcount, woff, win_start;
-  uint32_t n_windows = 0;
-  DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
-      tmp_cursor, bucket, bucket_line, corrections, lineless_flag, lineless_rank;
-  DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
-  uint32_t fallback_reason = 0;
-  int force_general = 0;
-  // build work
-  DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
-      big_rows, counters, lscratch, ltag;
-  // filter work
-  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, dirty;
-  uint32_t n_big_rows = 0, max_deg = 0;
-
-  uint32_t *h_counters = nullptr;   // pinned
-  gtsb_stats stats{};
-  Timer t_build, t_rep, t_filter;
-
-  bool profile = false;
-  gtsb::Profiler prof;
-  std::vector<std::string> prof_names;
-  std::vector<double> prof_ms;
-  std::vector<uint32_t> prof_calls;
-
-  // cached ambiguous-order thresholds
-  bool ambig_valid = false;
-  float ambig_cutoff = 0.f;
-  AmbigParams ambig{};
-};
-
-namespace {
+namespace gtsbi {
 
 int fail(gtsb_context *c, const char *fmt, ...) {
   char buf[512];
@@ -113,14 +31,6 @@ int fail(gtsb_context *c, const char *fmt, ...) {
   c->err = buf;
   return -1;
 }
-
-#define CK(call)                                                                        \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return fail(c, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__,     \
-                  __LINE__, cudaGetErrorString(e_));                                    \
-  } while (0)
 
 int ensure(gtsb_context *c, DevBuf &b, size_t bytes) {
   if (bytes == 0) bytes = 16;
@@ -148,11 +58,6 @@ void release(DevBuf &b) {
   b.cap = 0;
   b.owned = true;
 }
-
-#define ENSURE(buf, bytes)                      \
-  do {                                          \
-    if (ensure(c, buf, (bytes)) != 0) return -1; \
-  } while (0)
 
 int read_counters(gtsb_context *c) {
   CK(cudaMemcpyAsync(c->h_counters, c->counters.p, CNT_NUM * sizeof(uint32_t),
@@ -208,8 +113,9 @@ int vertices_common(gtsb_context *c, uint64_t V) {
 
 GraphArgs graph_args(gtsb_context *c) {
   GraphArgs g{};
-  g.V = (uint32_t) c->V;
+  g.V = (uint32_t) (c->world > 1 ? c->Vloc : c->V);
   g.E = (uint32_t) c->E;
+  g.row_base = c->world > 1 ? c->row_base : 0u;
   g.sm_count = c->sm_count;
   g.row_ptr = c->row_ptr.as<uint32_t>();
   g.vid = c->line_layout ? c->vid.as<uint32_t>() : nullptr;
@@ -246,11 +152,8 @@ int get_ambig(gtsb_context *c, float pcutoff) {
   return 0;
 }
 
-struct ProfScope {
-  gtsb_context *c;
-  explicit ProfScope(gtsb_context *ctx) : c(ctx) { gtsb::g_prof = c->profile ? &c->prof : nullptr; }
-  ~ProfScope() { gtsb::g_prof = nullptr; }
-};
+ProfScope::ProfScope(gtsb_context *ctx) : c(ctx) { gtsb::g_prof = c->profile ? &c->prof : nullptr; }
+ProfScope::~ProfScope() { gtsb::g_prof = nullptr; }
 
 // fold finished event pairs into the per-kernel totals (stream must be idle)
 void prof_collect(gtsb_context *c) {
@@ -540,18 +443,8 @@ int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int us
   return 0;
 }
 
-// fused = the three stages back to back on a fresh graph (gtsb_pipeline): the
-// repeat predicate is evaluated inside the vertex-facts pass and the REPEAT edge
-// marks (pred(v) || pred(w)) are derived by the final pass instead of being
-// stored first and overwritten later
-int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, bool fused = false,
-              float cn_cutoff = 0.f, float astat_cutoff = 0.f, int use_cn = 0) {
-  ProfScope ps_(c);
-  if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
-  if (get_ambig(c, pcutoff) != 0) return -1;
-  c->csr_exported = false;
-  const uint64_t V = c->V, E = c->E;
-  cudaStream_t s = c->stream;
+// work arrays of the filter: per-vertex ones for Vg vertices, proposals for E slots
+int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a) {
   ENSURE(c->proposals, (E + 1) * sizeof(uint2));
   ENSURE(c->poly_cur, (V + 1) * 4);
   ENSURE(c->poly_new, (V + 1) * 4);
@@ -562,16 +455,12 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   ENSURE(c->vinfo, (V + 1) * sizeof(uint2));
   ENSURE(c->vres, (V + 1) * 4);
   ENSURE(c->dirty, V + 1);
-  FilterArgs a{};
   a.big_blocks = (uint32_t) c->sm_count * 2;
   if (c->n_big_rows) {
     if (a.big_blocks > c->n_big_rows) a.big_blocks = c->n_big_rows;
     ENSURE(c->big_scratch, (size_t) a.big_blocks * c->max_deg * BIG_SCRATCH_STRIDE);
   }
   a.g = graph_args(c);
-  a.ambig = c->ambig;
-  a.cncutoff = cncutoff;
-  a.ocutoff = ocutoff;
   a.proposals = c->proposals.as<uint2>();
   a.proposals_cap = (uint32_t) E;
   a.poly_cur = c->poly_cur.as<uint32_t>();
@@ -585,6 +474,26 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   a.big_scratch = c->big_scratch.as<uint8_t>();
   a.vinfo = c->vinfo.as<uint2>();
   a.vres = c->vres.as<uint32_t>();
+  return 0;
+}
+
+// fused = the three stages back to back on a fresh graph (gtsb_pipeline): the
+// repeat predicate is evaluated inside the vertex-facts pass and the REPEAT edge
+// marks (pred(v) || pred(w)) are derived by the final pass instead of being
+// stored first and overwritten later
+int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, bool fused = false,
+              float cn_cutoff = 0.f, float astat_cutoff = 0.f, int use_cn = 0) {
+  ProfScope ps_(c);
+  if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
+  if (get_ambig(c, pcutoff) != 0) return -1;
+  c->csr_exported = false;
+  const uint64_t V = c->V, E = c->E;
+  cudaStream_t s = c->stream;
+  FilterArgs a{};
+  if (ensure_filter_buffers(c, V, E, a) != 0) return -1;
+  a.ambig = c->ambig;
+  a.cncutoff = cncutoff;
+  a.ocutoff = ocutoff;
   a.fused_repeats = fused ? 1 : 0;
 
   uint32_t *cnt = c->counters.as<uint32_t>();
@@ -645,6 +554,7 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
     uint32_t *t = win; win = wout; wout = t;
     int ti = in_idx; in_idx = out_idx; out_idx = ti;
   }
+  launch_vres(a, s);
   launch_finalize(a, s);
   c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   CK(cudaGetLastError());
@@ -688,7 +598,9 @@ int export_csr(gtsb_context *c) {
   return 0;
 }
 
-}  // namespace
+}  // namespace gtsbi
+
+using namespace gtsbi;
 
 // =============================================================== C ABI
 
@@ -724,6 +636,7 @@ void gtsb_destroy(gtsb_context *c) {
   if (c == nullptr) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  dist_release(c);
   DevBuf *bufs[] = {&c->vattr, &c->astat, &c->seq_len_in, &c->copy_num_in, &c->root, &c->ctg, &c->dist,
                     &c->std_dev, &c->flags, &c->row_ptr, &c->dst, &c->edist, &c->estd, &c->eflags,
                     &c->eid, &c->win_rec, &c->estate, &c->vstate, &c->rep_pred, &c->cnt, &c->bptr,
@@ -888,6 +801,7 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
 
 int gtsb_build(gtsb_context *c) {
   if (c == nullptr) return -1;
+  if (c->world > 1) return fail(c, "a rank-partitioned graph runs through gtsb_pipeline only");
   CK(cudaSetDevice(c->device));
   if (timer_begin(c, c->t_build) != 0) return -1;
   if (do_build(c) != 0) return -1;
@@ -896,6 +810,7 @@ int gtsb_build(gtsb_context *c) {
 
 int gtsb_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
   if (c == nullptr) return -1;
+  if (c->world > 1) return fail(c, "a rank-partitioned graph runs through gtsb_pipeline only");
   CK(cudaSetDevice(c->device));
   if (timer_begin(c, c->t_rep) != 0) return -1;
   if (do_mark_repeats(c, cn_cutoff, astat_cutoff, use_cn) != 0) return -1;
@@ -904,6 +819,7 @@ int gtsb_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int 
 
 int gtsb_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff) {
   if (c == nullptr) return -1;
+  if (c->world > 1) return fail(c, "a rank-partitioned graph runs through gtsb_pipeline only");
   CK(cudaSetDevice(c->device));
   if (timer_begin(c, c->t_filter) != 0) return -1;
   if (do_filter(c, pcutoff, cncutoff, ocutoff) != 0) return -1;
@@ -914,6 +830,7 @@ int gtsb_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
                   float cncutoff, int64_t ocutoff) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (c->world > 1) return dist_pipeline(c, cn_cutoff, astat_cutoff, use_cn, pcutoff, cncutoff, ocutoff);
   if (do_build(c) != 0) return -1;
   return do_filter(c, pcutoff, cncutoff, ocutoff, true, cn_cutoff, astat_cutoff, use_cn);
 }
@@ -932,6 +849,7 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
                  uint8_t *flags, uint32_t *eid, uint32_t *win_rec, uint8_t *estate) {
   if (c == nullptr) return -1;
   if (!c->have_graph) return fail(c, "gtsb_get_csr: no graph");
+  if (c->world > 1) return fail(c, "gtsb_get_csr: a rank holds only its rows of a partitioned graph; use gtsb_get_edges");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const uint64_t V = c->V, E = c->E;
@@ -963,6 +881,7 @@ int gtsb_device_pointers(gtsb_context *c, const uint32_t **row_ptr, const uint32
                          const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (c->world > 1) return fail(c, "gtsb_device_pointers: not available for a partitioned graph");
   if (export_csr(c) != 0) return -1;
   const bool ll = c->line_layout;
   if (row_ptr) *row_ptr = ll ? c->x_row_ptr.as<uint32_t>() : c->row_ptr.as<uint32_t>();

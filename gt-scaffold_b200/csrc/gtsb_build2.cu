@@ -632,6 +632,7 @@ int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
 int launch_b2_classify(const Build2Args &a, cudaStream_t s) {
   build2_attrs();
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  if (nseg == 0) return 0;
   KernelTimer t_("k2_classify", s);
   k2_classify<<<nseg, SEG_THREADS, build2_smem_classify(), s>>>(a);
   return 1;
@@ -640,6 +641,7 @@ int launch_b2_classify(const Build2Args &a, cudaStream_t s) {
 int launch_b2_partition(const Build2Args &a, cudaStream_t s) {
   build2_attrs();
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  if (nseg == 0) return 0;
   KernelTimer t_("k2_partition", s);
   k2_init_cursors<<<1, 128, 0, s>>>(a);
   k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
@@ -656,6 +658,7 @@ int launch_b2_count_mail(const Build2Args &a, uint32_t n_mail, cudaStream_t s) {
 int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
   build2_attrs();
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  if (nseg == 0) return 0;
   {
     KernelTimer t_("k2_deliver", s);
     k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);

@@ -1,0 +1,129 @@
+// gtsb_context.h -- the context behind the C ABI and the helpers shared by the
+// translation units that drive the kernels (gtsb_api.cu, gtsb_dist.cu).
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gtscaffold_b200.h"
+#include "gtsb_common.cuh"
+#include "gtsb_kernels.h"
+
+namespace gtsb {
+struct Profiler {
+  struct Rec { const char *name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+}  // namespace gtsb
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  bool owned = true;
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct gtsb_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  bool want_win = false;
+
+  uint64_t V = 0, R = 0, E = 0;
+  bool have_vertices = false, have_records = false, have_graph = false;
+  bool line_layout = false;     // rows in .de line order (rs/re/vid/pos) instead of plain CSR
+  bool csr_exported = false;    // plain CSR copy of a line-layout graph is current
+
+  // inputs
+  DevBuf vattr, astat, seq_len_in, copy_num_in;
+  DevBuf root, ctg, dist, std_dev, flags;
+  // graph
+  DevBuf row_ptr, srcp, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
+  DevBuf vid, pos;              // line layout
+  DevBuf wcount, woff, win_start;
+  uint32_t n_windows = 0;
+  DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
+      tmp_cursor, bucket, bucket_line, corrections, lineless_flag, lineless_rank;
+  DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
+  uint32_t fallback_reason = 0;
+  int force_general = 0;
+  // build work
+  DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
+      big_rows, counters, lscratch, ltag;
+  // filter work
+  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, dirty;
+  uint32_t n_big_rows = 0, max_deg = 0;
+
+  uint32_t *h_counters = nullptr;   // pinned
+  gtsb_stats stats{};
+  Timer t_build, t_rep, t_filter;
+
+  bool profile = false;
+  gtsb::Profiler prof;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<uint32_t> prof_calls;
+
+  // rank-partitioned graph (gtsb_dist.cu); world == 1: single device
+  int rank = 0, world = 1;
+  void *dstate = nullptr;            // DistState of gtsb_dist.cu
+  uint32_t row_base = 0;            // global position of local row 0
+  uint64_t Vloc = 0;                // rows held by this rank (== V when world == 1)
+
+  // cached ambiguous-order thresholds
+  bool ambig_valid = false;
+  float ambig_cutoff = 0.f;
+  gtsb::AmbigParams ambig{};
+};
+
+
+namespace gtsbi {
+
+int fail(gtsb_context *c, const char *fmt, ...);
+int ensure(gtsb_context *c, DevBuf &b, size_t bytes);
+int read_counters(gtsb_context *c);
+gtsb::GraphArgs graph_args(gtsb_context *c);
+int get_ambig(gtsb_context *c, float pcutoff);
+int ensure_windows(gtsb_context *c, uint64_t V, uint64_t max_edges);
+int ensure_rows(gtsb_context *c, uint64_t R);
+int ensure_filter_buffers(gtsb_context *c, uint64_t Vg, uint64_t E, gtsb::FilterArgs &a);
+
+struct ProfScope {                      // routes KernelTimer to the context's profiler while alive
+  gtsb_context *c;
+  explicit ProfScope(gtsb_context *ctx);
+  ~ProfScope();
+};
+
+// rank-partitioned pipeline (gtsb_dist.cu)
+int dist_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn, float pcutoff,
+                  float cncutoff, int64_t ocutoff);
+void dist_release(gtsb_context *c);
+
+}  // namespace gtsbi
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return gtsbi::fail(c, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, \
+                         __LINE__, cudaGetErrorString(e_));                             \
+  } while (0)
+
+#define ENSURE(buf, bytes)                             \
+  do {                                                 \
+    if (gtsbi::ensure(c, buf, (bytes)) != 0) return -1; \
+  } while (0)

@@ -1,0 +1,681 @@
+// gtsb_dist.cu -- one scaffold graph partitioned over the GPUs of a box
+// (SURVEY.md section 8e).
+//
+// Rank g holds a contiguous chunk of the .de lines (file order) and owns the
+// rows of the contigs heading those lines; contigs without a line go to the
+// last rank.  Positions -- the device's vertex names -- are global and equal to
+// the single-device numbering (lines in file order, then lineless contigs by
+// id), so a partitioned run builds exactly the rows of a single-device run,
+// just spread over the ranks.  What crosses NVLink:
+//
+//   build   position table id -> position          allreduce(min), 4 B/vertex
+//           contig ids by position                  allgatherv,     4 B/vertex
+//           mail (creator -> twin row)              all-to-all,     20 B/pair
+//           reverse-flag corrections                allgatherv,     rare
+//   filter  packed neighbour facts vinfo            allgatherv,     8 B/vertex
+//           polymorphic proposals                   allgatherv,     8 B/proposal;
+//             the polyTime fix-point then runs redundantly on every rank
+//           rows next to polymorphic contigs        allreduce(max), 1 B/vertex
+//           fire status, once per fire round        allgatherv,     1 B/vertex
+//           final per-vertex facts vres             allgatherv,     4 B/vertex
+//           vertex states                           allreduce(max), 1 B/vertex
+//
+// Both directed edges of a link are evaluated by their own rows' owners from
+// the same vertex-level facts, so the symmetric edge marks agree without any
+// edge exchange.  NCCL is loaded with dlopen when gtsb_dist_init is called;
+// single-device use never touches it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "gtsb_context.h"
+#include "gtsb_scan.cuh"
+
+using namespace gtsb;
+using namespace gtsbi;
+
+namespace gtsbd {
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+NcclApi g_nccl;
+
+const char *load_nccl() {
+  if (g_nccl.lib != nullptr) return nullptr;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) return "libnccl.so.2 not found";
+#define SYM(field, name)                                                     \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));    \
+  if (g_nccl.field == nullptr) return "NCCL symbol " name " missing";
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GetErrorString, "ncclGetErrorString")
+  SYM(Broadcast, "ncclBroadcast")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+#undef SYM
+  g_nccl.lib = h;
+  return nullptr;
+}
+
+struct DistState {
+  ncclComm_t comm = nullptr;
+  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all;
+  uint32_t *h_small = nullptr;     // pinned, world * SMALL_N words
+};
+constexpr int SMALL_N = MAX_RANKS + 4;
+
+#define NK(call)                                                                               \
+  do {                                                                                         \
+    ncclResult_t r_ = (call);                                                                  \
+    if (r_ != ncclSuccess)                                                                     \
+      return fail(c, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+// every rank contributes n (<= SMALL_N) words; host gets the world x n matrix
+int small_allgather(gtsb_context *c, const uint32_t *mine, int n, std::vector<uint32_t> &out) {
+  DistState *D = static_cast<DistState *>(c->dstate);
+  uint32_t *dev = D->small.as<uint32_t>();
+  for (int i = 0; i < n; i++) D->h_small[i] = mine[i];
+  CK(cudaMemcpyAsync(dev + (size_t) c->rank * n, D->h_small, n * 4, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(dev + (size_t) c->rank * n, dev, n, ncclUint32, D->comm, c->stream));
+  CK(cudaMemcpyAsync(D->h_small, dev, (size_t) c->world * n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  out.assign(D->h_small, D->h_small + (size_t) c->world * n);
+  return 0;
+}
+
+// in-place allgather of slices [lo[r], lo[r+1]) of an array of `es`-byte elements
+int allgatherv(gtsb_context *c, const char *what, void *buf, size_t es, const std::vector<uint64_t> &lo) {
+  DistState *D = static_cast<DistState *>(c->dstate);
+  KernelTimer t_(what, c->stream);
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < c->world; r++) {
+    const size_t bytes = (size_t) (lo[r + 1] - lo[r]) * es;
+    if (bytes == 0) continue;
+    char *p = static_cast<char *>(buf) + (size_t) lo[r] * es;
+    NK(g_nccl.Broadcast(p, p, bytes, ncclUint8, r, D->comm, c->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+
+// any rank in trouble stops every rank at the same place (the collectives that
+// follow must be entered by all ranks or by none)
+int agree(gtsb_context *c, int local_rc, const char *where) {
+  std::vector<uint32_t> all;
+  const uint32_t mine = local_rc != 0 ? 1u : 0u;
+  if (small_allgather(c, &mine, 1, all) != 0) return -1;
+  for (int r = 0; r < c->world; r++)
+    if (all[r]) {
+      if (local_rc == 0) return fail(c, "%s: rank %d failed (see its message)", where, r);
+      return -1;
+    }
+  return 0;
+}
+
+// ---- kernels that exist only for the partitioned graph
+
+// a contig heads lines on two ranks: its table entry is not ours
+__global__ void k_dist_check_pos(uint32_t L, uint32_t pos_base, const uint32_t *__restrict__ vid,
+                                 const uint32_t *__restrict__ pos, uint32_t *__restrict__ counters) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L && pos[vid[l]] != pos_base + l) atomicOr(&counters[CNT_FALLBACK], FB_MULTIRUN);
+}
+
+// contigs without a line: positions L_total + rank among them, rows on the last rank
+__global__ void k_dist_lineless(uint32_t Vg, uint32_t L_total, const uint8_t *__restrict__ flag,
+                                const uint32_t *__restrict__ rank, uint32_t *__restrict__ pos,
+                                uint32_t *__restrict__ vid_global, int is_last) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= Vg || !flag[v]) return;
+  const uint32_t p = L_total + rank[v];
+  pos[v] = p;
+  if (is_last) vid_global[p] = v;
+}
+
+__global__ void k_dist_flags(uint32_t Vg, const uint32_t *__restrict__ pos, uint8_t *__restrict__ flag) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < Vg) flag[v] = pos[v] == 0xFFFFFFFFu ? 1 : 0;
+}
+
+__global__ void k_dist_fill(uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t value) {
+  const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi) a[i] = value;
+}
+
+__global__ void k_edges(GraphArgs g, const uint32_t *__restrict__ eid_in, uint32_t *__restrict__ eid,
+                        uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint8_t *__restrict__ flags) {
+  const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= g.E) return;
+  const uint32_t sp = g.srcp[s] & S_POS, dp = g.dst[s];
+  eid[s] = eid_in[s];
+  src[s] = g.vid != nullptr ? g.vid[sp] : sp;
+  dst[s] = g.vid != nullptr ? g.vid[dp] : dp;
+  flags[s] = g.flags[s] & 0x0Fu;
+}
+
+}  // namespace gtsbd
+
+using namespace gtsbd;
+
+namespace gtsbi {
+
+void dist_release(gtsb_context *c) {
+  DistState *D = static_cast<DistState *>(c->dstate);
+  if (D == nullptr) return;
+  if (D->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(D->comm);
+  for (DevBuf *b : {&D->small, &D->bounds, &D->rank_cnt, &D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all})
+    if (b->owned && b->p != nullptr) cudaFree(b->p);
+  if (D->h_small != nullptr) cudaFreeHost(D->h_small);
+  delete D;
+  c->dstate = nullptr;
+  c->world = 1;
+  c->rank = 0;
+}
+
+namespace detail {
+
+struct Plan {                     // what the ranks agreed on while building
+  std::vector<uint64_t> lo;       // [N+1] first global position of every rank
+  uint32_t L = 0;                 // lines of this rank
+  uint64_t L_total = 0;
+  uint32_t own_lo = 0, Vloc = 0;
+};
+
+// lines, positions, contig ids by position
+int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P) {
+  const int N = c->world, me = c->rank;
+  const bool last = me == N - 1;
+  const uint64_t Vg = c->V, R = c->R;
+  cudaStream_t s = c->stream;
+  uint32_t *cnt = c->counters.as<uint32_t>();
+  const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
+  std::vector<uint32_t> all;
+  uint32_t L = 0;
+  if (R) {
+    KernelTimer t_("k2_heads(2 kernels+scan)", s);
+    c->stats.kernel_launches += launch_b2_head_counts(a, s);
+    CK(cudaMemcpyAsync(&L, a.tile_off + ntiles, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (small_allgather(c, &L, 1, all) != 0) return -1;
+  P.lo.assign(N + 1, 0);
+  for (int r = 0; r < N; r++) P.lo[r + 1] = P.lo[r] + all[r];
+  P.L = L;
+  P.L_total = P.lo[N];
+  if (P.L_total > Vg) return fail(c, "more lines than contigs: a contig heads more than one line");
+  P.lo[N] = Vg;                                               // the last rank also holds the lineless contigs
+  P.own_lo = (uint32_t) P.lo[me];
+  P.Vloc = (uint32_t) (P.lo[me + 1] - P.lo[me]);
+  c->row_base = P.own_lo;
+  c->Vloc = P.Vloc;
+  uint32_t hb[MAX_RANKS + 1];
+  for (int r = 0; r <= N; r++) hb[r] = (uint32_t) P.lo[r];
+  CK(cudaMemcpyAsync(D->bounds.p, hb, (N + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  a.V = L;                        // capacity of the line lists while the heads are written
+  a.pos_base = P.own_lo;
+  a.vid = c->vid.as<uint32_t>() + P.own_lo;
+  if (R) {
+    KernelTimer t_("k2_heads(2 kernels+scan)", s);
+    c->stats.kernel_launches += launch_b2_head_write(a, s);
+  }
+  {
+    KernelTimer t_("nccl_allreduce_pos", s);
+    NK(g_nccl.AllReduce(c->pos.p, c->pos.p, Vg, ncclUint32, ncclMin, D->comm, s));
+  }
+  {
+    KernelTimer t_("k_dist_lineless(4 kernels+scan)", s);
+    const uint32_t vb = (uint32_t) ((Vg + 255) / 256);
+    if (L) k_dist_check_pos<<<(L + 255) / 256, 256, 0, s>>>(L, P.own_lo, a.vid, a.pos, cnt);
+    k_dist_flags<<<vb, 256, 0, s>>>((uint32_t) Vg, a.pos, c->lineless_flag.as<uint8_t>());
+    exclusive_scan<uint8_t>(c->lineless_flag.as<uint8_t>(), Vg, c->lineless_rank.as<uint32_t>(),
+                            c->scan_scratch.as<uint32_t>(), s);
+    k_dist_lineless<<<vb, 256, 0, s>>>((uint32_t) Vg, (uint32_t) P.L_total, c->lineless_flag.as<uint8_t>(),
+                                       c->lineless_rank.as<uint32_t>(), a.pos, c->vid.as<uint32_t>(), last ? 1 : 0);
+    // line starts of the positions without records (and the end of the last line)
+    k_dist_fill<<<(P.Vloc - L + 1 + 255) / 256, 256, 0, s>>>(a.ls, L, P.Vloc + 1, (uint32_t) R);
+    c->stats.kernel_launches += 7;
+  }
+  if (allgatherv(c, "nccl_allgather_vid", c->vid.p, 4, P.lo) != 0) return -1;
+  a.V = P.Vloc;
+  return 0;
+}
+
+int dist_build(gtsb_context *c, DistState *D, Plan &P) {
+  const int N = c->world, me = c->rank;
+  const bool last = me == N - 1;
+  const uint64_t Vg = c->V, R = c->R;
+  cudaStream_t s = c->stream;
+  uint32_t *cnt = c->counters.as<uint32_t>();
+  std::vector<uint32_t> all;
+  const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
+  const uint64_t cap_rows = (R < Vg ? R : Vg) + (last ? Vg : 0) + 2;     // lines (+ every lineless contig)
+  int rc = [&]() -> int {
+    if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records on one rank");
+    ENSURE(c->tile_cnt, (ntiles + 2) * 4);
+    ENSURE(c->tile_off, (ntiles + 2) * 4);
+    ENSURE(c->pos, (Vg + 1) * 4);
+    ENSURE(c->vid, (Vg + 1) * 4);
+    ENSURE(c->ls, cap_rows * 4);
+    ENSURE(c->nown, cap_rows * 4);
+    ENSURE(c->k0, cap_rows * 4);
+    ENSURE(c->cnt_in, cap_rows * 4);
+    ENSURE(c->bptr2, cap_rows * 4);
+    ENSURE(c->row_ptr, cap_rows * 4);
+    ENSURE(c->big_rows, cap_rows * 4);
+    ENSURE(c->cursor2, ((cap_rows >> GROUP_SHIFT) + 2) * 4);
+    ENSURE(c->lineless_flag, Vg + 1);
+    ENSURE(c->lineless_rank, (Vg + 2) * 4);
+    const uint64_t scan_n = Vg > R ? Vg : R;
+    ENSURE(c->scan_scratch, scan_scratch_elems(scan_n) * 4);
+    ENSURE(c->rf, R + 1);
+    ENSURE(c->pc, (R + 1) * 4);
+    ENSURE(c->tmp_ent, (R + 1) * sizeof(uint4));
+    ENSURE(c->tmp_dest, (R + 1) * 4);
+    ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
+    ENSURE(D->bounds, (MAX_RANKS + 2) * 4);
+    ENSURE(D->rank_cnt, (MAX_RANKS + 2) * 4);
+    CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
+    CK(cudaMemsetAsync(c->pos.p, 0xFF, (Vg + 1) * 4, s));
+    CK(cudaMemsetAsync(c->vstate.p, 0, Vg ? Vg : 1, s));
+    CK(cudaMemsetAsync(c->nown.p, 0, cap_rows * 4, s));
+    CK(cudaMemsetAsync(c->cnt_in.p, 0, cap_rows * 4, s));
+    CK(cudaMemsetAsync(c->cursor2.p, 0, ((cap_rows >> GROUP_SHIFT) + 2) * 4, s));
+    CK(cudaMemsetAsync(D->rank_cnt.p, 0, (MAX_RANKS + 2) * 4, s));
+    return 0;
+  }();
+  if (agree(c, rc, "build setup") != 0) return -1;
+
+  Build2Args a{};
+  a.R = R;
+  a.Vg = (uint32_t) Vg;
+  a.sm_count = c->sm_count;
+  a.nranks = N;
+  a.root = c->root.as<uint32_t>();
+  a.ctg = c->ctg.as<uint32_t>();
+  a.dist = c->dist.as<int32_t>();
+  a.std_dev = c->std_dev.as<float>();
+  a.flags = c->flags.as<uint8_t>();
+  a.pos = c->pos.as<uint32_t>();
+  a.ls = c->ls.as<uint32_t>();
+  a.tile_cnt = c->tile_cnt.as<uint32_t>();
+  a.tile_off = c->tile_off.as<uint32_t>();
+  a.rf = c->rf.as<uint8_t>();
+  a.pc = c->pc.as<uint32_t>();
+  a.cnt_in = c->cnt_in.as<uint32_t>();
+  a.bptr = c->bptr2.as<uint32_t>();
+  a.cursor = c->cursor2.as<uint32_t>();
+  a.nown = c->nown.as<uint32_t>();
+  a.k0 = c->k0.as<uint32_t>();
+  a.tmp_ent = c->tmp_ent.as<uint4>();
+  a.tmp_dest = c->tmp_dest.as<uint32_t>();
+  a.tmp_cursor = c->tmp_cursor.as<uint32_t>();
+  a.scan_scratch = c->scan_scratch.as<uint32_t>();
+  a.counters = cnt;
+  a.big_rows = c->big_rows.as<uint32_t>();
+  a.row_ptr = c->row_ptr.as<uint32_t>();
+  a.rank_bounds = D->bounds.as<uint32_t>();
+  a.rank_cnt = D->rank_cnt.as<uint32_t>();
+
+  rc = dist_positions(c, D, a, P);
+  if (agree(c, rc, "positions") != 0) return -1;
+
+  // ---- classify, creator ranks, mail per destination rank
+  c->stats.kernel_launches += launch_b2_classify(a, s);
+  exclusive_scan<uint32_t>(a.nown, P.Vloc, a.k0, a.scan_scratch, s);
+  uint32_t mine[MAX_RANKS + 4];
+  rc = [&]() -> int {
+    if (read_counters(c) != 0) return -1;
+    if (c->h_counters[CNT_ERROR] & 1u) return fail(c, "gtsb_pipeline: a record names a vertex id >= nof_vertices");
+    if (c->h_counters[CNT_ERROR] & 2u) return fail(c, "gtsb_pipeline: self link (root == ctg) is not supported");
+    if (c->h_counters[CNT_FALLBACK])
+      return fail(c, "gtsb_pipeline: input outside what the rank-partitioned build accepts (reason mask %u: "
+                     "1 = a contig heads several lines, 2 = line longer than %u records, 4 = oversized segment)",
+                  c->h_counters[CNT_FALLBACK], MAX_LINE_RECS);
+    CK(cudaMemcpyAsync(&mine[1], a.rank_cnt, N * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&mine[0], a.k0 + P.Vloc, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+  }();
+  if (agree(c, rc, "classify") != 0) return -1;
+  if (small_allgather(c, mine, N + 1, all) != 0) return -1;
+  uint64_t k_base = 0, n_creators = 0;
+  for (int r = 0; r < N; r++) {
+    if (r < me) k_base += all[(size_t) r * (N + 1)];
+    n_creators += all[(size_t) r * (N + 1)];
+  }
+  if (2 * n_creators >= 0xFFFFFFF0ull) return fail(c, "too many edges for 32-bit edge ids");
+  a.k_base = (uint32_t) k_base;
+  std::vector<uint64_t> s_off(N + 1, 0), r_off(N + 1, 0);
+  for (int r = 0; r < N; r++) {
+    s_off[r + 1] = s_off[r] + all[(size_t) me * (N + 1) + 1 + r];      // what I send to r
+    r_off[r + 1] = r_off[r] + all[(size_t) r * (N + 1) + 1 + me];      // what r sends to me
+  }
+  const uint64_t M = r_off[N];                                         // mail for my rows
+
+  // ---- messages grouped by destination rank, then the exchange
+  c->stats.kernel_launches += launch_b2_partition(a, s);
+  rc = [&]() -> int {
+    ENSURE(D->rx_ent, (M + 1) * sizeof(uint4));
+    ENSURE(D->rx_dest, (M + 1) * 4);
+    ENSURE(c->bucket, (M + 1) * sizeof(uint4));
+    ENSURE(c->bucket_line, M + 16);
+    const uint64_t max_rows = (M + mine[0] + 1) / 2 + 1;               // slots = mail + own creators
+    if (ensure_rows(c, max_rows) != 0) return -1;
+    const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
+    ENSURE(c->corrections, (size_t) corr_cap * sizeof(uint4));
+    a.corrections_cap = corr_cap;
+    return 0;
+  }();
+  if (agree(c, rc, "mail buffers") != 0) return -1;
+  {
+    KernelTimer t_("nccl_alltoall_mail", s);
+    NK(g_nccl.GroupStart());
+    for (int r = 0; r < N; r++) {
+      const size_t ns = (size_t) (s_off[r + 1] - s_off[r]), nr = (size_t) (r_off[r + 1] - r_off[r]);
+      if (ns) {
+        NK(g_nccl.Send(a.tmp_ent + s_off[r], ns * 16, ncclUint8, r, D->comm, s));
+        NK(g_nccl.Send(a.tmp_dest + s_off[r], ns, ncclUint32, r, D->comm, s));
+      }
+      if (nr) {
+        NK(g_nccl.Recv(D->rx_ent.as<uint4>() + r_off[r], nr * 16, ncclUint8, r, D->comm, s));
+        NK(g_nccl.Recv(D->rx_dest.as<uint32_t>() + r_off[r], nr, ncclUint32, r, D->comm, s));
+      }
+    }
+    NK(g_nccl.GroupEnd());
+  }
+
+  // ---- receiver side: mailboxes of my rows, rows
+  a.mail_ent = D->rx_ent.as<uint4>();
+  a.mail_dest = D->rx_dest.as<uint32_t>();
+  a.bucket = c->bucket.as<uint4>();
+  a.bucket_line = c->bucket_line.as<uint8_t>();
+  a.corrections = c->corrections.as<uint4>();
+  a.srcp = c->srcp.as<uint32_t>();
+  a.dst = c->dst.as<uint32_t>();
+  a.eid = c->eid.as<uint32_t>();
+  a.edist = c->edist.as<int32_t>();
+  a.estd = c->estd.as<float>();
+  a.eflags = c->eflags.as<uint8_t>();
+  c->stats.kernel_launches += launch_b2_count_mail(a, (uint32_t) M, s);
+  exclusive_scan<uint32_t>(a.cnt_in, P.Vloc, a.bptr, a.scan_scratch, s);
+  c->stats.kernel_launches += launch_b2_deliver_resolve(a, s);
+  rc = [&]() -> int {
+    if (read_counters(c) != 0) return -1;
+    if (c->h_counters[CNT_ERROR] & 8u) return fail(c, "gtsb_pipeline: mail for a row of another rank (internal)");
+    if (c->h_counters[CNT_FALLBACK])
+      return fail(c, "gtsb_pipeline: input outside what the rank-partitioned build accepts (reason mask %u: "
+                     "4 = oversized segment, 8 = a link listed only on the later line)", c->h_counters[CNT_FALLBACK]);
+    return 0;
+  }();
+  if (agree(c, rc, "rows") != 0) return -1;
+  c->E = P.Vloc ? c->h_counters[CNT_EDGES] : 0;
+  c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
+  c->max_deg = c->h_counters[CNT_MAX_DEG];
+
+  // ---- reverse-flag corrections may belong to rows of other ranks
+  const uint32_t my_corr = c->h_counters[CNT_CORRECTIONS] < a.corrections_cap ? c->h_counters[CNT_CORRECTIONS]
+                                                                                : a.corrections_cap;
+  if (small_allgather(c, &my_corr, 1, all) != 0) return -1;
+  std::vector<uint64_t> c_off(N + 1, 0);
+  for (int r = 0; r < N; r++) c_off[r + 1] = c_off[r] + all[r];
+  if (c_off[N]) {
+    rc = [&]() -> int {
+      ENSURE(D->corr_all, c_off[N] * sizeof(uint4));
+      if (my_corr)
+        CK(cudaMemcpyAsync(D->corr_all.as<uint4>() + c_off[me], a.corrections, (size_t) my_corr * sizeof(uint4),
+                           cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }();
+    if (agree(c, rc, "corrections") != 0) return -1;
+    if (allgatherv(c, "nccl_allgather_corrections", D->corr_all.p, sizeof(uint4), c_off) != 0) return -1;
+    c->stats.kernel_launches += launch_b2_apply_corrections(a, D->corr_all.as<uint4>(), (uint32_t) c_off[N], s);
+  }
+
+  // ---- windows over my rows
+  rc = ensure_windows(c, P.Vloc, c->E + 1);
+  if (agree(c, rc, "windows") != 0) return -1;
+  c->line_layout = true;
+  c->csr_exported = false;
+  c->have_graph = true;
+  {
+    GraphArgs g{};
+    g.V = P.Vloc;
+    g.row_ptr = c->row_ptr.as<uint32_t>();
+    g.counters = cnt;
+    c->stats.kernel_launches += launch_pack_windows(g, c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
+                                                    c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
+  }
+  if (read_counters(c) != 0) return agree(c, -1, "windows");
+  c->n_windows = P.Vloc ? c->h_counters[CNT_WINDOWS] : 0;
+  c->stats.nof_edges = c->E;
+  c->stats.big_rows = c->n_big_rows;
+  c->stats.max_degree = c->max_deg;
+  return agree(c, 0, "build");
+}
+
+int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, float astat_cutoff, int use_cn,
+                float cncutoff, int64_t ocutoff) {
+  const int N = c->world, me = c->rank;
+  const uint64_t Vg = c->V;
+  cudaStream_t s = c->stream;
+  uint32_t *cnt = c->counters.as<uint32_t>();
+  std::vector<uint32_t> all;
+  FilterArgs a{};
+  int rc = [&]() -> int {
+    if (ensure_filter_buffers(c, Vg, c->E, a) != 0) return -1;
+    CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
+    CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (Vg + 1) * 4, s));
+    CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (Vg + 1) * 4, s));
+    CK(cudaMemsetAsync(c->dirty.p, 0, Vg + 1, s));
+    CK(cudaMemsetAsync(c->gbits.p, 0, Vg + 1, s));
+    CK(cudaMemsetAsync(c->fstat.p, 0x0C, Vg + 1, s));
+    return 0;
+  }();
+  if (agree(c, rc, "filter setup") != 0) return -1;
+  a.ambig = c->ambig;
+  a.cncutoff = cncutoff;
+  a.ocutoff = ocutoff;
+  a.fused_repeats = 1;
+
+  // phase 1
+  launch_vertex_facts(a, 1, cn_cutoff, astat_cutoff, use_cn, s);
+  if (allgatherv(c, "nccl_allgather_vinfo", c->vinfo.p, sizeof(uint2), P.lo) != 0) return -1;
+  launch_pairs(a, s);
+  c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
+  rc = [&]() -> int {
+    if (read_counters(c) != 0) return -1;
+    if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
+    if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
+    return 0;
+  }();
+  if (agree(c, rc, "pairs") != 0) return -1;
+  const uint32_t my_prop = c->h_counters[CNT_PROPOSALS];
+  if (small_allgather(c, &my_prop, 1, all) != 0) return -1;
+  std::vector<uint64_t> p_off(N + 1, 0);
+  for (int r = 0; r < N; r++) p_off[r + 1] = p_off[r] + all[r];
+  const uint64_t nprop64 = p_off[N];
+  if (nprop64 >= 0xFFFFFFF0ull) return fail(c, "too many proposals");
+  const uint32_t nprop = (uint32_t) nprop64;
+  c->stats.proposals = nprop;
+  c->stats.poly_sweeps = 0;
+  if (nprop) {
+    rc = [&]() -> int {
+      ENSURE(D->prop_all, (size_t) nprop * sizeof(uint2));
+      if (my_prop)
+        CK(cudaMemcpyAsync(D->prop_all.as<uint2>() + p_off[me], a.proposals, (size_t) my_prop * sizeof(uint2),
+                           cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }();
+    if (agree(c, rc, "proposals") != 0) return -1;
+    if (allgatherv(c, "nccl_allgather_proposals", D->prop_all.p, sizeof(uint2), p_off) != 0) return -1;
+    // every rank holds every proposal: the polyTime fix-point runs redundantly,
+    // identically, without any exchange
+    FilterArgs pa = a;
+    pa.proposals = D->prop_all.as<uint2>();
+    for (;;) {
+      CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
+      launch_poly_sweep(pa, nprop, s);
+      c->stats.kernel_launches += 3;
+      c->stats.poly_sweeps++;
+      if (read_counters(c) != 0) return -1;
+      if (!c->h_counters[CNT_POLY_CHANGED]) break;
+      if (c->stats.poly_sweeps > Vg + 2) return fail(c, "gtsb_filter: polyTime sweeps did not converge");
+    }
+    launch_dirty(pa, nprop, s);
+    c->stats.kernel_launches += 1;
+    KernelTimer t_("nccl_allreduce_dirty", s);
+    NK(g_nccl.AllReduce(c->dirty.p, c->dirty.p, Vg, ncclUint8, ncclMax, D->comm, s));
+  }
+
+  // phase 2
+  CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
+  launch_fire_init(a, s);
+  c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
+  if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
+  c->stats.fire_rounds = 0;
+  if (ocutoff >= 0) {
+    uint32_t *win = a.work_b, *wout = a.work_a;
+    int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
+    launch_fire_dense(a, a.work_b, cnt + CNT_WORK_B, s);
+    c->stats.kernel_launches += c->E ? 1 : 0;
+    for (;;) {
+      c->stats.fire_rounds++;
+      if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
+      if (read_counters(c) != 0) return agree(c, -1, "fire round");
+      const uint32_t n_in = c->h_counters[in_idx];
+      if (small_allgather(c, &n_in, 1, all) != 0) return -1;
+      uint64_t pending = 0;
+      for (int r = 0; r < N; r++) pending += all[r];
+      if (pending == 0) break;
+      if (c->stats.fire_rounds > Vg + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
+      CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
+      launch_fire_round(a, win, n_in, wout, cnt + out_idx, s);
+      c->stats.kernel_launches += n_in ? 1 : 0;
+      uint32_t *t = win; win = wout; wout = t;
+      int ti = in_idx; in_idx = out_idx; out_idx = ti;
+    }
+  }
+
+  // final states
+  launch_vres(a, s);
+  if (allgatherv(c, "nccl_allgather_vres", c->vres.p, 4, P.lo) != 0) return -1;
+  launch_finalize(a, s);
+  c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
+  return 0;
+}
+
+}  // namespace detail
+
+using namespace detail;
+
+int dist_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn, float pcutoff,
+                  float cncutoff, int64_t ocutoff) {
+  ProfScope ps_(c);
+  DistState *D = static_cast<DistState *>(c->dstate);
+  if (D == nullptr) return fail(c, "gtsb_dist_init has not been called");
+  int rc = 0;
+  if (!c->have_vertices || !c->have_records) rc = fail(c, "gtsb_pipeline: vertices and records must be set first");
+  if (rc == 0 && get_ambig(c, pcutoff) != 0) rc = -1;
+  if (agree(c, rc, "inputs") != 0) return -1;
+  Plan P;
+  if (dist_build(c, D, P) != 0) return -1;
+  if (dist_filter(c, D, P, cn_cutoff, astat_cutoff, use_cn, cncutoff, ocutoff) != 0) return -1;
+  {
+    KernelTimer t_("nccl_allreduce_vstate", c->stream);
+    NK(g_nccl.AllReduce(c->vstate.p, c->vstate.p, c->V, ncclUint8, ncclMax, D->comm, c->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gtsbi
+
+// =============================================================== C ABI
+
+extern "C" {
+
+int gtsb_dist_unique_id(void *id128) {
+  const char *err = load_nccl();
+  if (err != nullptr) {
+    fprintf(stderr, "gtscaffold_b200: %s\n", err);
+    return -1;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return -1;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int gtsb_dist_init(gtsb_context *c, int rank, int world, const void *id128) {
+  if (c == nullptr) return -1;
+  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return fail(c, "gtsb_dist_init: bad rank/world");
+  if (world == 1) return 0;
+  const char *err = load_nccl();
+  if (err != nullptr) return fail(c, "gtsb_dist_init: %s", err);
+  CK(cudaSetDevice(c->device));
+  dist_release(c);
+  DistState *D = new DistState();
+  c->dstate = D;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NK(g_nccl.CommInitRank(&D->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  ENSURE(D->small, (size_t) MAX_RANKS * SMALL_N * 4);
+  CK(cudaMallocHost(&D->h_small, (size_t) MAX_RANKS * SMALL_N * 4));
+  return 0;
+}
+
+int gtsb_get_edges(gtsb_context *c, uint64_t *nof_edges, uint32_t *eid, uint32_t *src, uint32_t *dst,
+                   int32_t *dist, float *std_dev, uint8_t *flags, uint8_t *estate) {
+  if (c == nullptr) return -1;
+  if (!c->have_graph) return fail(c, "gtsb_get_edges: no graph");
+  CK(cudaSetDevice(c->device));
+  const uint64_t E = c->E;
+  if (nof_edges) *nof_edges = E;
+  if (E == 0 || (!eid && !src && !dst && !dist && !std_dev && !flags && !estate)) return 0;
+  if (c->eid.p == nullptr) return fail(c, "gtsb_get_edges: this graph has no edge ids (not built here)");
+  cudaStream_t s = c->stream;
+  ENSURE(c->x_eid, (E + 1) * 4);
+  ENSURE(c->x_dst, (E + 1) * 4);
+  ENSURE(c->x_row_ptr, (E + 1) * 4);     // src ids
+  ENSURE(c->x_flags, E + 1);
+  c->csr_exported = false;               // the export buffers are reused
+  k_edges<<<(uint32_t) ((E + 255) / 256), 256, 0, s>>>(graph_args(c), c->eid.as<uint32_t>(), c->x_eid.as<uint32_t>(),
+                                                       c->x_row_ptr.as<uint32_t>(), c->x_dst.as<uint32_t>(),
+                                                       c->x_flags.as<uint8_t>());
+  c->stats.kernel_launches++;
+  if (eid) CK(cudaMemcpyAsync(eid, c->x_eid.p, E * 4, cudaMemcpyDeviceToHost, s));
+  if (src) CK(cudaMemcpyAsync(src, c->x_row_ptr.p, E * 4, cudaMemcpyDeviceToHost, s));
+  if (dst) CK(cudaMemcpyAsync(dst, c->x_dst.p, E * 4, cudaMemcpyDeviceToHost, s));
+  if (dist) CK(cudaMemcpyAsync(dist, c->edist.p, E * 4, cudaMemcpyDeviceToHost, s));
+  if (std_dev) CK(cudaMemcpyAsync(std_dev, c->estd.p, E * 4, cudaMemcpyDeviceToHost, s));
+  if (flags) CK(cudaMemcpyAsync(flags, c->x_flags.p, E, cudaMemcpyDeviceToHost, s));
+  if (estate) CK(cudaMemcpyAsync(estate, c->estate.p, E, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // extern "C"

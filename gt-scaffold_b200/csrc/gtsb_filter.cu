@@ -945,13 +945,14 @@ __global__ void __launch_bounds__(256) k4_finalize_big(FilterArgs a) {
   }
 }
 
-void launch_finalize(const FilterArgs &a, cudaStream_t s) {
+void launch_vres(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0) return;
-  {
-    KernelTimer t_("k4_vres", s);
-    k4_vres<<<(a.g.V + 255) / 256, 256, 0, s>>>(a);
-  }
-  if (a.g.E == 0) return;
+  KernelTimer t_("k4_vres", s);
+  k4_vres<<<(a.g.V + 255) / 256, 256, 0, s>>>(a);
+}
+
+void launch_finalize(const FilterArgs &a, cudaStream_t s) {
+  if (a.g.V == 0 || a.g.E == 0) return;
   {
     KernelTimer t_("k4_finalize", s);
     k4_finalize<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);

@@ -205,7 +205,8 @@ void launch_fire_init(const FilterArgs &a, cudaStream_t s);
 void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
-void launch_finalize(const FilterArgs &a, cudaStream_t s);
+void launch_vres(const FilterArgs &a, cudaStream_t s);          // final per-vertex facts (+ POLYMORPHIC vertex marks)
+void launch_finalize(const FilterArgs &a, cudaStream_t s);      // final edge states; needs every neighbour's vres
 // cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)
 int launch_pack_windows(const GraphArgs &g, uint32_t *count, uint32_t *woff, uint32_t *win_start,
                         uint32_t *scan_scratch, cudaStream_t s);

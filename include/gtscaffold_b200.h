@@ -93,6 +93,22 @@ int gtsb_filter(gtsb_context *ctx, float pcutoff, float cncutoff, int64_t ocutof
 int gtsb_pipeline(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff, int use_copy_num,
                   float pcutoff, float cncutoff, int64_t ocutoff);
 
+/* ---- one graph partitioned over the GPUs of a box (one process per GPU).
+   Rank r is given a contiguous chunk of the .de records (whole lines, ranks in
+   file order) with gtsb_set_records_*, and the attributes of ALL contigs with
+   gtsb_set_vertices_*; gtsb_pipeline then builds and filters the global graph,
+   each rank holding the rows of the contigs that head its lines (contigs
+   without a line: last rank).  Vertex states come back complete on every rank;
+   edges stay with their rank (gtsb_get_edges).  The exchanges are NCCL over
+   NVLink; the 128-byte id from rank 0 has to reach every rank by the caller's
+   own means (MPI, torch.distributed, a file). */
+int gtsb_dist_unique_id(void *id128);
+int gtsb_dist_init(gtsb_context *ctx, int rank, int world, const void *id128);
+/* this device's edges with the reference's vertex ids: eid = index into
+   graph->edges[] (creation order; within a vertex, adjacency order = eid order) */
+int gtsb_get_edges(gtsb_context *ctx, uint64_t *nof_edges, uint32_t *eid, uint32_t *src, uint32_t *dst,
+                   int32_t *dist, float *std_dev, uint8_t *flags, uint8_t *estate);
+
 /* ---- results (device-resident until fetched; NULL pointers are skipped) */
 uint64_t gtsb_nof_edges(const gtsb_context *ctx);
 int gtsb_get_vertex_states(gtsb_context *ctx, uint8_t *vstate);
