@@ -83,6 +83,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_emit = print
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -132,7 +135,7 @@ def run_reference_arm(args, pkg):
                        "line_order": args.line_order, **{k: PARAMS[k] for k in ("pcutoff", "cncutoff", "ocutoff")}},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def run_b200_arm(args, pkg):
@@ -149,13 +152,39 @@ def run_b200_arm(args, pkg):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- workload: weak scaling, every rank owns one graph of the named shape
+    # ---- workload.  N = 1: one graph of the named shape.  N > 1: weak scaling on ONE graph of
+    # N x that many contigs, its .de lines cut into N chunks (rank r = r-th chunk of the file),
+    # rows partitioned accordingly, NCCL exchanges inside gtsb_pipeline.
     V = args.vertices
-    t = pkg.synth.generate_torch(args.workload, V=V, device=dev, line_order=args.line_order,
-                                 seed=None if world == 1 else 0x5CAFF01D + 1000 * rank)
-    Vn, Rn = int(t["seq_len"].shape[0]), int(t["root"].shape[0])
+    if world == 1:
+        t = pkg.synth.generate_torch(args.workload, V=V, device=dev, line_order=args.line_order)
+    else:
+        Vper = V if V is not None else pkg.synth.CONFIGS[args.workload][1]
+        full = pkg.synth.generate_torch(args.workload, V=Vper * world, device=dev, line_order=args.line_order)
+        Rg = int(full["root"].shape[0])
+        fr = pkg.api.chunk_fractions(world)            # later chunks receive more mail: cut them shorter
+        cuts = [0]
+        for r in range(1, world):
+            i = max(1, int(Rg * fr[r]))
+            w = full["root"][i - 1:i + 65536].cpu()
+            brk = (w[1:] != w[:-1]).nonzero().flatten()
+            cuts.append(i + int(brk[0]) if len(brk) else Rg)          # first line start at or after i
+        cuts.append(Rg)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        t = {k: full[k] for k in ("seq_len", "astat", "copy_num", "meta")}
+        for k in ("root", "ctg", "dist", "std_dev", "flags"):
+            t[k] = full[k][lo:hi].clone()
+        del full
+        torch.cuda.empty_cache()
+    Vn, Rn = int(t["seq_len"].shape[0]), int(t["root"].shape[0])      # Vn: contigs of the whole graph
     stream = torch.cuda.current_stream(dev)
     g = pkg.ScaffoldGraphB200(device=local, stream=stream.cuda_stream)
+    uid = None
+    if world > 1:
+        box = [pkg.api.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+        g.dist_init(rank, world, uid)
     P = PARAMS
 
     def set_device_inputs():
@@ -204,9 +233,13 @@ def run_b200_arm(args, pkg):
     host = {k: t[k].cpu().pin_memory() for k in ("seq_len", "astat", "copy_num", "root", "ctg", "dist",
                                                   "std_dev", "flags")}
     vstate_h = torch.empty(Vn, dtype=torch.uint8).pin_memory()
-    estate_h = torch.empty(2 * Rn, dtype=torch.uint8).pin_memory()
-    eid_h = torch.empty(2 * Rn, dtype=torch.int32).pin_memory()
-    g2 = pkg.ScaffoldGraphB200(device=local, stream=stream.cuda_stream)
+    estate_h = torch.empty(2 * Rn + 16, dtype=torch.uint8).pin_memory()
+    eid_h = torch.empty(2 * Rn + 16, dtype=torch.int32).pin_memory()
+    if world == 1:
+        g2 = pkg.ScaffoldGraphB200(device=local, stream=stream.cuda_stream)
+    else:
+        g2 = g                                     # one NCCL communicator per rank is enough
+    import ctypes
 
     def e2e_step():
         g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
@@ -218,8 +251,13 @@ def run_b200_arm(args, pkg):
         g2.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
                     P["cncutoff"], P["ocutoff"])
         g2._ck(g2.L.gtsb_get_vertex_states(g2.h, vstate_h.data_ptr()))
-        g2._ck(g2.L.gtsb_get_csr(g2.h, None, None, None, None, None, eid_h.data_ptr(), None,
-                                 estate_h.data_ptr()))
+        if world == 1:
+            g2._ck(g2.L.gtsb_get_csr(g2.h, None, None, None, None, None, eid_h.data_ptr(), None,
+                                     estate_h.data_ptr()))
+        else:
+            n = ctypes.c_uint64()
+            g2._ck(g2.L.gtsb_get_edges(g2.h, ctypes.byref(n), eid_h.data_ptr(), None, None, None, None, None,
+                                       estate_h.data_ptr()))
 
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(min(args.warmup, 2)):
@@ -235,12 +273,13 @@ def run_b200_arm(args, pkg):
     e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3) / e2e_steps
     h2d = Vn * 12 + Rn * 17
     d2h = Vn + E * 5
-    g2.close()
+    if world == 1:
+        g2.close()
 
     # ---- max over ranks, whole-job aggregate
     ms_step = ms_total / args.steps
     vals = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(E), float(Vn)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(E), float(Vn) / world], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -252,8 +291,9 @@ def run_b200_arm(args, pkg):
         return
 
     peak, peak_src = peaks()
-    alg_bytes = B_E * E + B_V * Vn                     # per GPU
-    dom = max(kern.items(), key=lambda kv: kv[1][0]) if kern else ("n/a", (float("nan"), 0))
+    alg_bytes = B_E * E_all / world + B_V * Vn / world  # per GPU (mean over the ranks)
+    comp = {k: v for k, v in kern.items() if not k.startswith(("nccl_", "PHASE_"))}
+    dom = max(comp.items(), key=lambda kv: kv[1][0]) if comp else ("n/a", (float("nan"), 0))
     stage_of = lambda n: ("mark_repeats" if "repeat" in n else
                           "filter" if any(x in n for x in ("pairs", "poly", "overlap", "fire", "finalize"))
                           else "build")
@@ -273,20 +313,28 @@ def run_b200_arm(args, pkg):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32/i32/f32 (+i64,f64 in the exact slow path)", "data": "synthetic",
-            "config": {"workload": args.workload, "vertices_per_gpu": Vn, "records_per_gpu": Rn,
+            "config": {"workload": args.workload, "vertices_per_gpu": Vn // world, "records_per_gpu": Rn,
                        "edges_per_gpu": int(E), "line_order": args.line_order,
+                       "graph": ("one graph" if world == 1 else
+                                 f"one graph of {Vn} contigs partitioned over {world} ranks by .de line chunk; "
+                                 "NCCL all-to-all (mail) and allgathers (vertex facts) inside the timed step"),
                        "l2": "inputs (%.2f GB) larger than L2; no flush" % ((Vn * 12 + Rn * 17) / 1e9),
                        **{k: P[k] for k in ("pcutoff", "cncutoff", "ocutoff", "astat_cutoff", "copy_num_cutoff")}},
             "e2e": {"value": E_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
             "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds")}}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries ONE JSON line: whatever libraries print (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -119,15 +119,32 @@ def dist_unique_id() -> bytes:
     return buf.raw
 
 
-def shard_lines(inp, world: int, rank: int):
+MAIL_WEIGHT = 0.6
+
+
+def chunk_fractions(world: int, mail_weight: float = MAIL_WEIGHT):
+    """Where to cut a .de file into `world` chunks (fractions of its records).
+    The record that creates a link sits on the EARLIER of the two lines and
+    mails the twin edge to the later one, so a rank that holds late lines
+    receives more mail: work per record grows like 1 + mail_weight * x with the
+    relative file position x.  Equal integrals of that weight per chunk."""
+    g = float(mail_weight)
+    if g <= 0:
+        return [r / world for r in range(world + 1)]
+    total = 1.0 + g / 2.0
+    return [((1.0 + 2.0 * g * (r / world) * total) ** 0.5 - 1.0) / g for r in range(world)] + [1.0]
+
+
+def shard_lines(inp, world: int, rank: int, mail_weight: float = MAIL_WEIGHT):
     """Rank `rank`'s share of a .de file: a contiguous chunk of whole lines
-    (maximal runs of one root contig), ranks in file order, balanced by record
-    count.  Vertex attributes are not sharded."""
+    (maximal runs of one root contig), ranks in file order, cut at
+    chunk_fractions().  Vertex attributes are not sharded."""
     root = np.asarray(inp.root)
     R = root.shape[0]
+    fr = chunk_fractions(world, mail_weight)
     cuts = [0]
     for r in range(1, world):
-        i = min(R, (R * r) // world)
+        i = min(R, int(R * fr[r]))
         while 0 < i < R and root[i] == root[i - 1]:      # move to the next line start
             i += 1
         cuts.append(max(i, cuts[-1]))

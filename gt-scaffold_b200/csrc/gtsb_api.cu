@@ -543,16 +543,19 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
     n_in = c->h_counters[CNT_WORK_B];
   }
   while (n_in) {
-    CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
-    launch_fire_round(a, win, n_in, wout, cnt + out_idx, s);
-    c->stats.kernel_launches += 1;
-    c->stats.fire_rounds++;
+    // worklists only shrink: n_in bounds the next rounds' lists, so a few rounds are queued per sync
+    for (int k = 0; k < FIRE_ROUNDS_PER_SYNC; k++) {
+      CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
+      launch_fire_round(a, win, cnt + in_idx, n_in, wout, cnt + out_idx, s);
+      c->stats.kernel_launches += 1;
+      c->stats.fire_rounds++;
+      uint32_t *t = win; win = wout; wout = t;
+      int ti = in_idx; in_idx = out_idx; out_idx = ti;
+    }
     if (read_counters(c) != 0) return -1;
-    const uint32_t n_out = c->h_counters[out_idx];
-    if (n_out >= n_in && c->stats.fire_rounds > V + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
-    n_in = n_out;
-    uint32_t *t = win; win = wout; wout = t;
-    int ti = in_idx; in_idx = out_idx; out_idx = ti;
+    const uint32_t n_next = c->h_counters[in_idx];
+    if (n_next >= n_in && c->stats.fire_rounds > V + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
+    n_in = n_next;
   }
   launch_vres(a, s);
   launch_finalize(a, s);

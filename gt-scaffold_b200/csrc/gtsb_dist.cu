@@ -26,6 +26,8 @@
 // single-device use never touches it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include "gtsb_context.h"
 #include "gtsb_scan.cuh"
@@ -81,7 +83,7 @@ struct DistState {
   DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all;
   uint32_t *h_small = nullptr;     // pinned, world * SMALL_N words
 };
-constexpr int SMALL_N = MAX_RANKS + 4;
+constexpr int SMALL_N = MAX_RANKS + 8;
 
 #define NK(call)                                                                               \
   do {                                                                                         \
@@ -118,18 +120,29 @@ int allgatherv(gtsb_context *c, const char *what, void *buf, size_t es, const st
   return 0;
 }
 
-// any rank in trouble stops every rank at the same place (the collectives that
-// follow must be entered by all ranks or by none)
-int agree(gtsb_context *c, int local_rc, const char *where) {
+// Every rank contributes n words and its own status; any rank in trouble stops
+// every rank at the same place (the collectives that follow must be entered by
+// all ranks or by none).  out = world x n matrix.  One host synchronisation.
+int exchange(gtsb_context *c, int local_rc, const char *where, const uint32_t *mine, int n,
+             std::vector<uint32_t> &out) {
+  uint32_t buf[SMALL_N];
+  buf[0] = local_rc != 0 ? 1u : 0u;
+  for (int i = 0; i < n; i++) buf[1 + i] = mine[i];
   std::vector<uint32_t> all;
-  const uint32_t mine = local_rc != 0 ? 1u : 0u;
-  if (small_allgather(c, &mine, 1, all) != 0) return -1;
-  for (int r = 0; r < c->world; r++)
-    if (all[r]) {
-      if (local_rc == 0) return fail(c, "%s: rank %d failed (see its message)", where, r);
-      return -1;
-    }
+  if (small_allgather(c, buf, n + 1, all) != 0) return -1;
+  out.resize((size_t) c->world * n);
+  int bad = -1;
+  for (int r = 0; r < c->world; r++) {
+    if (all[(size_t) r * (n + 1)] && bad < 0) bad = r;
+    for (int i = 0; i < n; i++) out[(size_t) r * n + i] = all[(size_t) r * (n + 1) + 1 + i];
+  }
+  if (bad >= 0) return local_rc == 0 ? fail(c, "%s: rank %d failed (see its message)", where, bad) : -1;
   return 0;
+}
+
+int agree(gtsb_context *c, int local_rc, const char *where) {
+  std::vector<uint32_t> none;
+  return exchange(c, local_rc, where, nullptr, 0, none);
 }
 
 // ---- kernels that exist only for the partitioned graph
@@ -194,6 +207,28 @@ void dist_release(gtsb_context *c) {
 
 namespace detail {
 
+// GTSB_TRACE=1: host wall clock at the marks below, after draining the stream (dev aid)
+struct Trace {
+  bool on;
+  double t0;
+  cudaStream_t s;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  explicit Trace(cudaStream_t st) : on(getenv("GTSB_TRACE") != nullptr), t0(0), s(st) {
+    if (on) { cudaStreamSynchronize(s); t0 = now(); }
+  }
+  void mark(int rank, const char *what) {
+    if (!on) return;
+    const double a = now();
+    cudaStreamSynchronize(s);
+    const double b = now();
+    fprintf(stderr, "[trace r%d] %-22s host %8.3f ms  drained %8.3f ms\n", rank, what, a - t0, b - t0);
+  }
+};
+
 struct Plan {                     // what the ranks agreed on while building
   std::vector<uint64_t> lo;       // [N+1] first global position of every rank
   uint32_t L = 0;                 // lines of this rank
@@ -202,7 +237,7 @@ struct Plan {                     // what the ranks agreed on while building
 };
 
 // lines, positions, contig ids by position
-int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P) {
+int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int setup_rc) {
   const int N = c->world, me = c->rank;
   const bool last = me == N - 1;
   const uint64_t Vg = c->V, R = c->R;
@@ -211,13 +246,13 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P) {
   const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
   std::vector<uint32_t> all;
   uint32_t L = 0;
-  if (R) {
+  if (R && setup_rc == 0) {
     KernelTimer t_("k2_heads(2 kernels+scan)", s);
     c->stats.kernel_launches += launch_b2_head_counts(a, s);
     CK(cudaMemcpyAsync(&L, a.tile_off + ntiles, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
-  if (small_allgather(c, &L, 1, all) != 0) return -1;
+  if (exchange(c, setup_rc, "build setup", &L, 1, all) != 0) return -1;
   P.lo.assign(N + 1, 0);
   for (int r = 0; r < N; r++) P.lo[r + 1] = P.lo[r] + all[r];
   P.L = L;
@@ -261,7 +296,7 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P) {
   return 0;
 }
 
-int dist_build(gtsb_context *c, DistState *D, Plan &P) {
+int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   const int N = c->world, me = c->rank;
   const bool last = me == N - 1;
   const uint64_t Vg = c->V, R = c->R;
@@ -270,7 +305,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
   std::vector<uint32_t> all;
   const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
   const uint64_t cap_rows = (R < Vg ? R : Vg) + (last ? Vg : 0) + 2;     // lines (+ every lineless contig)
-  int rc = [&]() -> int {
+  int rc = inputs_rc != 0 ? inputs_rc : [&]() -> int {
     if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records on one rank");
     ENSURE(c->tile_cnt, (ntiles + 2) * 4);
     ENSURE(c->tile_off, (ntiles + 2) * 4);
@@ -304,7 +339,9 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     CK(cudaMemsetAsync(D->rank_cnt.p, 0, (MAX_RANKS + 2) * 4, s));
     return 0;
   }();
-  if (agree(c, rc, "build setup") != 0) return -1;
+  const int setup_rc = rc;
+  Trace tr(s);
+  tr.mark(me, "setup");
 
   Build2Args a{};
   a.R = R;
@@ -337,8 +374,9 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
   a.rank_bounds = D->bounds.as<uint32_t>();
   a.rank_cnt = D->rank_cnt.as<uint32_t>();
 
-  rc = dist_positions(c, D, a, P);
-  if (agree(c, rc, "positions") != 0) return -1;
+  rc = dist_positions(c, D, a, P, setup_rc);      // exchanges the setup status with the line counts
+  if (rc != 0) return -1;
+  tr.mark(me, "positions");
 
   // ---- classify, creator ranks, mail per destination rank
   c->stats.kernel_launches += launch_b2_classify(a, s);
@@ -357,8 +395,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     CK(cudaStreamSynchronize(s));
     return 0;
   }();
-  if (agree(c, rc, "classify") != 0) return -1;
-  if (small_allgather(c, mine, N + 1, all) != 0) return -1;
+  if (exchange(c, rc, "classify", mine, N + 1, all) != 0) return -1;
   uint64_t k_base = 0, n_creators = 0;
   for (int r = 0; r < N; r++) {
     if (r < me) k_base += all[(size_t) r * (N + 1)];
@@ -372,6 +409,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     r_off[r + 1] = r_off[r] + all[(size_t) r * (N + 1) + 1 + me];      // what r sends to me
   }
   const uint64_t M = r_off[N];                                         // mail for my rows
+  tr.mark(me, "classify+exchange");
 
   // ---- messages grouped by destination rank, then the exchange
   c->stats.kernel_launches += launch_b2_partition(a, s);
@@ -387,7 +425,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     a.corrections_cap = corr_cap;
     return 0;
   }();
-  if (agree(c, rc, "mail buffers") != 0) return -1;
+  if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
   {
     KernelTimer t_("nccl_alltoall_mail", s);
     NK(g_nccl.GroupStart());
@@ -405,6 +443,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     NK(g_nccl.GroupEnd());
   }
 
+  tr.mark(me, "partition+alltoall");
   // ---- receiver side: mailboxes of my rows, rows
   a.mail_ent = D->rx_ent.as<uint4>();
   a.mail_dest = D->rx_dest.as<uint32_t>();
@@ -428,15 +467,15 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
                      "4 = oversized segment, 8 = a link listed only on the later line)", c->h_counters[CNT_FALLBACK]);
     return 0;
   }();
-  if (agree(c, rc, "rows") != 0) return -1;
   c->E = P.Vloc ? c->h_counters[CNT_EDGES] : 0;
   c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
   c->max_deg = c->h_counters[CNT_MAX_DEG];
 
+  tr.mark(me, "rows");
   // ---- reverse-flag corrections may belong to rows of other ranks
   const uint32_t my_corr = c->h_counters[CNT_CORRECTIONS] < a.corrections_cap ? c->h_counters[CNT_CORRECTIONS]
                                                                                 : a.corrections_cap;
-  if (small_allgather(c, &my_corr, 1, all) != 0) return -1;
+  if (exchange(c, rc, "rows", &my_corr, 1, all) != 0) return -1;
   std::vector<uint64_t> c_off(N + 1, 0);
   for (int r = 0; r < N; r++) c_off[r + 1] = c_off[r] + all[r];
   if (c_off[N]) {
@@ -447,14 +486,13 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
                            cudaMemcpyDeviceToDevice, s));
       return 0;
     }();
-    if (agree(c, rc, "corrections") != 0) return -1;
+    if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
     if (allgatherv(c, "nccl_allgather_corrections", D->corr_all.p, sizeof(uint4), c_off) != 0) return -1;
     c->stats.kernel_launches += launch_b2_apply_corrections(a, D->corr_all.as<uint4>(), (uint32_t) c_off[N], s);
   }
 
   // ---- windows over my rows
-  rc = ensure_windows(c, P.Vloc, c->E + 1);
-  if (agree(c, rc, "windows") != 0) return -1;
+  if (ensure_windows(c, P.Vloc, c->E + 1) != 0) return -1;
   c->line_layout = true;
   c->csr_exported = false;
   c->have_graph = true;
@@ -466,12 +504,13 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P) {
     c->stats.kernel_launches += launch_pack_windows(g, c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
                                                     c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
   }
-  if (read_counters(c) != 0) return agree(c, -1, "windows");
+  if (read_counters(c) != 0) return -1;
   c->n_windows = P.Vloc ? c->h_counters[CNT_WINDOWS] : 0;
   c->stats.nof_edges = c->E;
   c->stats.big_rows = c->n_big_rows;
   c->stats.max_degree = c->max_deg;
-  return agree(c, 0, "build");
+  tr.mark(me, "corrections+windows");
+  return 0;
 }
 
 int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, float astat_cutoff, int use_cn,
@@ -492,7 +531,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
     CK(cudaMemsetAsync(c->fstat.p, 0x0C, Vg + 1, s));
     return 0;
   }();
-  if (agree(c, rc, "filter setup") != 0) return -1;
+  if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
   a.ambig = c->ambig;
   a.cncutoff = cncutoff;
   a.ocutoff = ocutoff;
@@ -509,9 +548,8 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
     if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
     return 0;
   }();
-  if (agree(c, rc, "pairs") != 0) return -1;
   const uint32_t my_prop = c->h_counters[CNT_PROPOSALS];
-  if (small_allgather(c, &my_prop, 1, all) != 0) return -1;
+  if (exchange(c, rc, "pairs", &my_prop, 1, all) != 0) return -1;
   std::vector<uint64_t> p_off(N + 1, 0);
   for (int r = 0; r < N; r++) p_off[r + 1] = p_off[r] + all[r];
   const uint64_t nprop64 = p_off[N];
@@ -527,7 +565,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
                            cudaMemcpyDeviceToDevice, s));
       return 0;
     }();
-    if (agree(c, rc, "proposals") != 0) return -1;
+    if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
     if (allgatherv(c, "nccl_allgather_proposals", D->prop_all.p, sizeof(uint2), p_off) != 0) return -1;
     // every rank holds every proposal: the polyTime fix-point runs redundantly,
     // identically, without any exchange
@@ -559,21 +597,26 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
     int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
     launch_fire_dense(a, a.work_b, cnt + CNT_WORK_B, s);
     c->stats.kernel_launches += c->E ? 1 : 0;
+    c->stats.fire_rounds++;
+    if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
     for (;;) {
-      c->stats.fire_rounds++;
-      if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
-      if (read_counters(c) != 0) return agree(c, -1, "fire round");
+      // pending rows over all ranks; my own count bounds my next worklists (they only shrink)
+      const int rrc = read_counters(c);
       const uint32_t n_in = c->h_counters[in_idx];
-      if (small_allgather(c, &n_in, 1, all) != 0) return -1;
+      if (exchange(c, rrc, "fire round", &n_in, 1, all) != 0) return -1;
       uint64_t pending = 0;
       for (int r = 0; r < N; r++) pending += all[r];
       if (pending == 0) break;
       if (c->stats.fire_rounds > Vg + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
-      CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
-      launch_fire_round(a, win, n_in, wout, cnt + out_idx, s);
-      c->stats.kernel_launches += n_in ? 1 : 0;
-      uint32_t *t = win; win = wout; wout = t;
-      int ti = in_idx; in_idx = out_idx; out_idx = ti;
+      for (int k = 0; k < FIRE_ROUNDS_PER_SYNC; k++) {
+        CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
+        launch_fire_round(a, win, cnt + in_idx, n_in, wout, cnt + out_idx, s);
+        c->stats.kernel_launches += n_in ? 1 : 0;
+        c->stats.fire_rounds++;
+        if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
+        uint32_t *t = win; win = wout; wout = t;
+        int ti = in_idx; in_idx = out_idx; out_idx = ti;
+      }
     }
   }
 
@@ -597,9 +640,12 @@ int dist_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
   int rc = 0;
   if (!c->have_vertices || !c->have_records) rc = fail(c, "gtsb_pipeline: vertices and records must be set first");
   if (rc == 0 && get_ambig(c, pcutoff) != 0) rc = -1;
-  if (agree(c, rc, "inputs") != 0) return -1;
   Plan P;
-  if (dist_build(c, D, P) != 0) return -1;
+  {
+    KernelTimer t_("PHASE_build", c->stream);
+    if (dist_build(c, D, P, rc) != 0) return -1;
+  }
+  KernelTimer t_("PHASE_filter", c->stream);
   if (dist_filter(c, D, P, cn_cutoff, astat_cutoff, use_cn, cncutoff, ocutoff) != 0) return -1;
   {
     KernelTimer t_("nccl_allreduce_vstate", c->stream);

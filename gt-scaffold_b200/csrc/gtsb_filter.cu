@@ -815,9 +815,11 @@ void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out,
 
 // later rounds: thread per listed row (any degree)
 __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t *__restrict__ work_in,
-                                                     uint32_t n_in, uint32_t *__restrict__ work_out,
+                                                     const uint32_t *__restrict__ n_in_dev,
+                                                     uint32_t *__restrict__ work_out,
                                                      uint32_t *__restrict__ n_out) {
   const GraphArgs &g = a.g;
+  const uint32_t n_in = *n_in_dev;       // the grid is sized for an upper bound the host knows
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   bool again = false;
   uint32_t p = 0;
@@ -836,11 +838,11 @@ __global__ void __launch_bounds__(128) k_fire_round(FilterArgs a, const uint32_t
   warp_append(again, p, work_out, n_out);
 }
 
-void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
+void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, const uint32_t *n_in_dev, uint32_t n_max,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s) {
-  if (n_in == 0) return;
+  if (n_max == 0) return;
   KernelTimer t_("k_fire_round", s);
-  k_fire_round<<<(n_in + 127) / 128, 128, 0, s>>>(a, work_in, n_in, work_out, n_out);
+  k_fire_round<<<(n_max + 127) / 128, 128, 0, s>>>(a, work_in, n_in_dev, work_out, n_out);
 }
 
 // ------------------------------------------------------------------ final states

@@ -203,8 +203,11 @@ void launch_poly_sweep(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
 void launch_fire_init(const FilterArgs &a, cudaStream_t s);
 void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
-void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, uint32_t n_in,
+// one round over the listed rows; the list length is read on the device (n_in_dev), the grid
+// covers n_max >= it, so that several rounds can be queued between two host synchronisations
+void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, const uint32_t *n_in_dev, uint32_t n_max,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
+constexpr int FIRE_ROUNDS_PER_SYNC = 3;
 void launch_vres(const FilterArgs &a, cudaStream_t s);          // final per-vertex facts (+ POLYMORPHIC vertex marks)
 void launch_finalize(const FilterArgs &a, cudaStream_t s);      // final edge states; needs every neighbour's vres
 // cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)

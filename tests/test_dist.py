@@ -22,8 +22,11 @@ def test_shard_lines_cuts_only_between_lines(pkg, synth):
         for a, b in zip(parts[:-1], parts[1:]):
             if len(a.root) and len(b.root):
                 assert a.root[-1] != b.root[0], "a line was split between two ranks"
-        sizes = [len(p.root) for p in parts]
+        even = [pkg.api.shard_lines(inp, world, r, mail_weight=0.0) for r in range(world)]
+        sizes = [len(p.root) for p in even]
         assert max(sizes) - min(sizes) <= 64, sizes            # balanced up to one line
+        sizes = [len(p.root) for p in parts]                   # default: later chunks are shorter
+        assert all(a + 64 >= b for a, b in zip(sizes[:-1], sizes[1:])), sizes
 
 
 def test_shard_lines_degenerate(pkg, synth):
