@@ -151,14 +151,15 @@ struct Seg {
 };
 
 // load the segment's line starts; false (block-uniform) if it cannot be staged
+template <int LINES = SEG_LINES, uint32_t REC_CAP = SEG_REC_CAP>
 __device__ __forceinline__ bool seg_open(const Build2Args &a, uint32_t s, Seg &g, uint32_t *s_ls) {
-  g.p0 = s * SEG_LINES;
-  g.nlines = min((uint32_t) SEG_LINES, a.V - g.p0);
+  g.p0 = s * LINES;
+  g.nlines = min((uint32_t) LINES, a.V - g.p0);
   for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) s_ls[j] = a.ls[g.p0 + j];
   __syncthreads();
   g.rec0 = s_ls[0];
   g.n = s_ls[g.nlines] - g.rec0;
-  if (g.n > SEG_REC_CAP) {
+  if (g.n > REC_CAP) {
     if (threadIdx.x == 0) raise(a.counters, FB_SEGMENT);
     return false;
   }
@@ -372,20 +373,20 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
-  uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + SEG_ENT_CAP);
-  uint32_t *s_bp = s_ls + SEG_LINES + 4;
-  uint32_t *s_k0 = s_bp + SEG_LINES + 4;            // creators before each line
-  uint32_t *s_fill = s_k0 + SEG_LINES + 4;
-  uint32_t *s_pc = s_fill + SEG_LINES + 4;
-  float *s_std = reinterpret_cast<float *>(s_pc + SEG_REC_CAP);
-  uint16_t *s_match = reinterpret_cast<uint16_t *>(s_std + SEG_REC_CAP);   // mail entry -> the line's first record of that neighbour
-  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_match + SEG_ENT_CAP);
-  uint8_t *s_rf = s_fl + SEG_REC_CAP;
-  uint8_t *s_line = s_rf + SEG_REC_CAP;
-  uint8_t *s_eline = s_line + SEG_REC_CAP;
+  uint32_t *s_ls = reinterpret_cast<uint32_t *>(s_ent + RSEG_ENT_CAP);
+  uint32_t *s_bp = s_ls + RSEG_LINES + 4;
+  uint32_t *s_k0 = s_bp + RSEG_LINES + 4;            // creators before each line
+  uint32_t *s_fill = s_k0 + RSEG_LINES + 4;
+  uint32_t *s_pc = s_fill + RSEG_LINES + 4;
+  float *s_std = reinterpret_cast<float *>(s_pc + RSEG_REC_CAP);
+  uint16_t *s_match = reinterpret_cast<uint16_t *>(s_std + RSEG_REC_CAP);   // mail entry -> the line's first record of that neighbour
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_match + RSEG_ENT_CAP);
+  uint8_t *s_rf = s_fl + RSEG_REC_CAP;
+  uint8_t *s_line = s_rf + RSEG_REC_CAP;
+  uint8_t *s_eline = s_line + RSEG_REC_CAP;
   constexpr uint16_t NO_MATCH = 0xFFFF;
   Seg g;
-  if (!seg_open(a, blockIdx.x, g, s_ls)) return;
+  if (!seg_open<RSEG_LINES, RSEG_REC_CAP>(a, blockIdx.x, g, s_ls)) return;
   for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) {
     s_bp[j] = a.bptr[g.p0 + j];
     s_k0[j] = a.k0[g.p0 + j];
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   }
   __syncthreads();
   const uint32_t ent0 = s_bp[0], nent = s_bp[g.nlines] - ent0;
-  if (nent > SEG_ENT_CAP) {
+  if (nent > RSEG_ENT_CAP) {
     if (threadIdx.x == 0) raise(a.counters, FB_SEGMENT);
     return;
   }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
   }
   // the segment's mail, counting-sorted by line
   for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) {
-    const uint32_t j = a.bucket_line[ent0 + e];
+    const uint32_t j = a.bucket_line[ent0 + e] & (RSEG_LINES - 1);   // delivered per SEG_LINES: low bits
     const uint32_t at = s_bp[j] - ent0 + atomicAdd(&s_fill[j], 1u);
     s_ent[at] = a.bucket[ent0 + e];
     s_eline[at] = (uint8_t) j;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
 
 size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
 size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
-size_t build2_smem_resolve() { return SEG_ENT_CAP * 19 + 4 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 16; }
+size_t build2_smem_resolve() { return RSEG_ENT_CAP * 19 + 4 * (RSEG_LINES + 4) * 4 + RSEG_REC_CAP * 11 + 16; }
 
 static void build2_attrs() {
   static bool attr_done = false;
@@ -664,7 +665,7 @@ int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
     k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
   }
   KernelTimer t_("k2_resolve", s);
-  k2_resolve<<<nseg, SEG_THREADS, build2_smem_resolve(), s>>>(a);
+  k2_resolve<<<(a.V + RSEG_LINES - 1) / RSEG_LINES, SEG_THREADS, build2_smem_resolve(), s>>>(a);
   return 2;
 }
 

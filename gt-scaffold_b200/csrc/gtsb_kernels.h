@@ -50,7 +50,8 @@ enum : uint32_t {
 constexpr int SEG_LINES = 128;            // lines (positions) per block
 constexpr int SEG_THREADS = 256;
 constexpr uint32_t SEG_REC_CAP = 2048;    // staged records per segment
-constexpr uint32_t SEG_ENT_CAP = 1536;    // staged mailbox entries per segment
+constexpr int RSEG_LINES = 64;            // k2_resolve works on half segments (more blocks per SM)
+constexpr uint32_t RSEG_REC_CAP = 1024, RSEG_ENT_CAP = 768;
 constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread scans accept
 constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
 constexpr int GROUP_SHIFT = 3;            // mail is delivered to groups of 8 positions
