@@ -629,13 +629,36 @@ __global__ void __launch_bounds__(128) k4_fire_redo(FilterArgs a, const uint32_t
     int32_t dist[BIG_ROW];
     uint32_t len[BIG_ROW];
     uint32_t sense_mask = 0, ok_mask = 0;
-    for (uint32_t k = 0; k < d; k++) {
-      const uint32_t w = g.dst[r0 + k];
-      const uint2 vi = a.vinfo[w];
-      dist[k] = g.dist[r0 + k];
-      len[k] = vi.y & ~VI_MARKED;
-      if (g.flags[r0 + k] & F_SENSE) sense_mask |= 1u << k;
-      if (slot_unmarked(a, r0 + k, vi.y, w, v_id)) ok_mask |= 1u << k;
+    for (uint32_t k0 = 0; k0 < d; k0 += 8) {       // 8 slots at a time: their loads and gathers overlap
+      uint32_t w[8], fl[8], pt[8];
+      uint2 vi[8];
+      int32_t di[8];
+      uint8_t es[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const bool in = k0 + j < d;
+        const uint32_t s = r0 + k0 + j;
+        w[j] = in ? g.dst[s] : 0u;
+        di[j] = in ? g.dist[s] : 0;
+        fl[j] = in ? g.flags[s] : 0u;
+        es[j] = (in && !a.fused_repeats) ? g.estate[s] : (uint8_t) 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const bool in = k0 + j < d;
+        vi[j] = in ? a.vinfo[w[j]] : make_uint2(0u, 0u);
+        pt[j] = in ? a.poly_cur[w[j]] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (k0 + j >= d) break;
+        const uint32_t k = k0 + j;
+        dist[k] = di[j];
+        len[k] = vi[j].y & ~VI_MARKED;
+        if (fl[j] & F_SENSE) sense_mask |= 1u << k;
+        const bool ok0 = a.fused_repeats ? !(vi[j].y & VI_MARKED) : !edge_state_marked(es[j]);
+        if (ok0 && !(pt[j] <= v_id)) ok_mask |= 1u << k;      // U(e), see slot_unmarked
+      }
     }
     long long mx[2] = {0, 0};
     for (uint32_t x = 0; x + 1 < d; x++) {
