@@ -241,19 +241,24 @@ def run_b200_arm(args, pkg):
         g2 = g                                     # one NCCL communicator per rank is enough
     import ctypes
 
+    # the .de parser's view of the records: lines (root, first record) instead of a root per record
+    line_root_np, line_start_np = pkg.api.lines_of(host["root"].numpy())
+    line_root_h = torch.from_numpy(line_root_np.view(np.int32)).pin_memory()
+    line_start_h = torch.from_numpy(line_start_np.view(np.int32)).pin_memory()
+    n_lines = int(line_root_h.shape[0])
+
     def e2e_step():
         g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
                                            host["copy_num"].data_ptr()))
         g2.V = Vn
-        g2._ck(g2.L.gtsb_set_records_host(g2.h, Rn, host["root"].data_ptr(), host["ctg"].data_ptr(),
-                                          host["dist"].data_ptr(), host["std_dev"].data_ptr(),
-                                          host["flags"].data_ptr()))
+        g2._ck(g2.L.gtsb_set_record_lines_host(g2.h, n_lines, line_root_h.data_ptr(), line_start_h.data_ptr(), Rn,
+                                               host["ctg"].data_ptr(), host["dist"].data_ptr(),
+                                               host["std_dev"].data_ptr(), host["flags"].data_ptr()))
         g2.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
                     P["cncutoff"], P["ocutoff"])
         g2._ck(g2.L.gtsb_get_vertex_states(g2.h, vstate_h.data_ptr()))
         if world == 1:
-            g2._ck(g2.L.gtsb_get_csr(g2.h, None, None, None, None, None, eid_h.data_ptr(), None,
-                                     estate_h.data_ptr()))
+            g2._ck(g2.L.gtsb_get_edge_states(g2.h, estate_h.data_ptr()))
         else:
             n = ctypes.c_uint64()
             g2._ck(g2.L.gtsb_get_edges(g2.h, ctypes.byref(n), eid_h.data_ptr(), None, None, None, None, None,
@@ -271,8 +276,8 @@ def run_b200_arm(args, pkg):
     ev3.record(stream)
     barrier()
     e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3) / e2e_steps
-    h2d = Vn * 12 + Rn * 17
-    d2h = Vn + E * 5
+    h2d = Vn * 12 + Rn * 13 + n_lines * 8 + 4
+    d2h = Vn + E * (1 if world == 1 else 5)
     if world == 1:
         g2.close()
 

@@ -34,6 +34,7 @@ EXPORTS = [
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
+    "gtsb_set_record_lines_host", "gtsb_get_edge_states",
 ]
 
 
@@ -94,6 +95,8 @@ def load_library():
     L.gtsb_dist_unique_id.argtypes = [vp]
     L.gtsb_dist_init.argtypes = [vp, i32, i32, vp]
     L.gtsb_get_edges.argtypes = [vp, C.POINTER(u64)] + [vp] * 7
+    L.gtsb_set_record_lines_host.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
+    L.gtsb_get_edge_states.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -133,6 +136,16 @@ def chunk_fractions(world: int, mail_weight: float = MAIL_WEIGHT):
         return [r / world for r in range(world + 1)]
     total = 1.0 + g / 2.0
     return [((1.0 + 2.0 * g * (r / world) * total) ** 0.5 - 1.0) / g for r in range(world)] + [1.0]
+
+
+def lines_of(root):
+    """(line_root, line_start) of a file-ordered root column: maximal runs of one root."""
+    root = np.asarray(root)
+    R = root.shape[0]
+    if R == 0:
+        return np.zeros(0, np.uint32), np.zeros(1, np.uint32)
+    starts = np.flatnonzero(np.concatenate([[True], root[1:] != root[:-1]]))
+    return root[starts].astype(np.uint32), np.concatenate([starts, [R]]).astype(np.uint32)
 
 
 def shard_lines(inp, world: int, rank: int, mail_weight: float = MAIL_WEIGHT):
@@ -190,6 +203,20 @@ class ScaffoldGraphB200:
              np.ascontiguousarray(dist, np.int32), np.ascontiguousarray(std_dev, np.float32),
              np.ascontiguousarray(flags, np.uint8)]
         self._ck(self.L.gtsb_set_records_host(self.h, a[0].shape[0], *[_ptr(x) for x in a]))
+
+    def set_record_lines(self, line_root, line_start, ctg, dist, std_dev, flags):
+        """Records in .de shape: line l = records [line_start[l], line_start[l+1]) of root line_root[l]."""
+        a = [np.ascontiguousarray(line_root, np.uint32), np.ascontiguousarray(line_start, np.uint32),
+             np.ascontiguousarray(ctg, np.uint32), np.ascontiguousarray(dist, np.int32),
+             np.ascontiguousarray(std_dev, np.float32), np.ascontiguousarray(flags, np.uint8)]
+        self._ck(self.L.gtsb_set_record_lines_host(self.h, a[0].shape[0], _ptr(a[0]), _ptr(a[1]), a[2].shape[0],
+                                                   *[_ptr(x) for x in a[2:]]))
+
+    def edge_states(self):
+        """estate indexed by eid (graph->edges[] order)."""
+        out = np.zeros(self.E, np.uint8)
+        self._ck(self.L.gtsb_get_edge_states(self.h, _ptr(out)))
+        return out
 
     def set_vertices_device(self, V, seq_len_ptr, astat_ptr, copy_num_ptr):
         self.V = int(V)

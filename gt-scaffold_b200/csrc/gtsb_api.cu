@@ -82,6 +82,38 @@ int timer_end(gtsb_context *c, Timer &t, float *ms) {
   return 0;
 }
 
+// line-shaped records -> the root column (one thread per line, a warp for long lines)
+__global__ void __launch_bounds__(256) k_expand_roots(uint32_t L, const uint32_t *__restrict__ line_root,
+                                                       const uint32_t *__restrict__ line_start,
+                                                       uint32_t *__restrict__ root) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = 0, n = 0, r = 0;
+  if (l < L) {
+    b = line_start[l];
+    n = line_start[l + 1] - b;
+    r = line_root[l];
+  }
+  const bool big = n > 64;
+  if (!big)
+    for (uint32_t k = 0; k < n; k++) root[b + k] = r;
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t bb = __shfl_sync(0xffffffffu, b, src), nn = __shfl_sync(0xffffffffu, n, src),
+                   rr = __shfl_sync(0xffffffffu, r, src);
+    for (uint32_t k = lane_id(); k < nn; k += 32) root[bb + k] = rr;
+  }
+}
+
+// estate by slot -> estate by eid
+__global__ void __launch_bounds__(256) k_states_by_eid(uint64_t E, const uint32_t *__restrict__ eid,
+                                                        const uint8_t *__restrict__ estate,
+                                                        uint8_t *__restrict__ out) {
+  const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < E) out[eid[s]] = estate[s];
+}
+
 __global__ void k_pack_vattr(uint32_t V, const uint32_t *__restrict__ seq_len,
                              const float *__restrict__ copy_num, VAttr *__restrict__ out) {
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -648,7 +680,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
                     &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->wcount, &c->woff, &c->win_start, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
-                    &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line,
+                    &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line, &c->line_root, &c->line_start,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
                     &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg};
   for (DevBuf *b : bufs) release(*b);
@@ -727,6 +759,40 @@ int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, con
   ENSURE(c->flags, R);
   if (R) {
     CK(cudaMemcpyAsync(c->root.p, root, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ctg.p, ctg, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->dist.p, dist, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->std_dev.p, std_dev, R * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->flags.p, flags, R, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->R = R;
+  c->have_records = true;
+  c->stats.nof_records = R;
+  return 0;
+}
+
+int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line_root, const uint32_t *line_start,
+                               uint64_t R, const uint32_t *ctg, const int32_t *dist, const float *std_dev,
+                               const uint8_t *flags) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (R >= 0xFFFFFFF0ull || L > R) return fail(c, "gtsb_set_record_lines_host: bad sizes");
+  DevBuf *bs[] = {&c->root, &c->ctg, &c->dist, &c->std_dev, &c->flags};
+  for (DevBuf *b : bs)
+    if (!b->owned) *b = DevBuf();
+  ENSURE(c->root, R * 4);
+  ENSURE(c->ctg, R * 4);
+  ENSURE(c->dist, R * 4);
+  ENSURE(c->std_dev, R * 4);
+  ENSURE(c->flags, R);
+  ENSURE(c->line_root, (L + 1) * 4);
+  ENSURE(c->line_start, (L + 2) * 4);
+  if (R) {
+    CK(cudaMemcpyAsync(c->line_root.p, line_root, L * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->line_start.p, line_start, (L + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    k_expand_roots<<<(uint32_t) ((L + 255) / 256), 256, 0, c->stream>>>((uint32_t) L, c->line_root.as<uint32_t>(),
+                                                                        c->line_start.as<uint32_t>(),
+                                                                        c->root.as<uint32_t>());
+    c->stats.kernel_launches++;
     CK(cudaMemcpyAsync(c->ctg.p, ctg, R * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->dist.p, dist, R * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->std_dev.p, std_dev, R * 4, cudaMemcpyHostToDevice, c->stream));
@@ -877,6 +943,24 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
   CK(cudaStreamSynchronize(s));
   if (!ll && flags != nullptr)
     for (uint64_t i = 0; i < E; i++) flags[i] &= 0x0Fu;          // F_LT is device-only
+  return 0;
+}
+
+int gtsb_get_edge_states(gtsb_context *c, uint8_t *estate_by_eid) {
+  if (c == nullptr) return -1;
+  if (!c->have_graph) return fail(c, "gtsb_get_edge_states: no graph");
+  if (c->world > 1) return fail(c, "gtsb_get_edge_states: a rank holds only its rows of a partitioned graph; use gtsb_get_edges");
+  if (c->eid.p == nullptr || c->R == 0) return fail(c, "gtsb_get_edge_states: this graph has no edge ids (not built here)");
+  CK(cudaSetDevice(c->device));
+  const uint64_t E = c->E;
+  if (E == 0 || estate_by_eid == nullptr) return 0;
+  ENSURE(c->x_estate, E + 1);
+  c->csr_exported = false;               // the export buffer is reused
+  k_states_by_eid<<<(uint32_t) ((E + 255) / 256), 256, 0, c->stream>>>(E, c->eid.as<uint32_t>(), c->estate.as<uint8_t>(),
+                                                                       c->x_estate.as<uint8_t>());
+  c->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(estate_by_eid, c->x_estate.p, E, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

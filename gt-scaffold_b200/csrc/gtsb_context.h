@@ -50,7 +50,7 @@ struct gtsb_context {
 
   // inputs
   DevBuf vattr, astat, seq_len_in, copy_num_in;
-  DevBuf root, ctg, dist, std_dev, flags;
+  DevBuf root, ctg, dist, std_dev, flags, line_root, line_start;
   // graph
   DevBuf row_ptr, srcp, dst, edist, estd, eflags, eid, win_rec, estate, vstate, rep_pred;
   DevBuf vid, pos;              // line layout

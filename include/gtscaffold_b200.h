@@ -76,6 +76,12 @@ int gtsb_set_records_host(gtsb_context *ctx, uint64_t nof_records, const uint32_
 int gtsb_set_records_device(gtsb_context *ctx, uint64_t nof_records, const uint32_t *root,
                             const uint32_t *ctg, const int32_t *dist, const float *std_dev,
                             const uint8_t *flags);
+/* the same records in the shape a .de parser has them in (parser.c:323-388: one
+   line per root contig): line l holds records [line_start[l], line_start[l+1])
+   of root line_root[l].  Saves the 4 B/record of the repeated root on the bus. */
+int gtsb_set_record_lines_host(gtsb_context *ctx, uint64_t nof_lines, const uint32_t *line_root,
+                               const uint32_t *line_start, uint64_t nof_records, const uint32_t *ctg,
+                               const int32_t *dist, const float *std_dev, const uint8_t *flags);
 /* an already-built graph (host CSR, flags incl. GTSB_RSENSE/RSAME, states);
    used by the GtScaffolderGraph binding of mark_repeats / filter */
 int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_edges,
@@ -116,6 +122,9 @@ int gtsb_get_vertex_states(gtsb_context *ctx, uint8_t *vstate);
 int gtsb_get_csr(gtsb_context *ctx, uint32_t *row_ptr, uint32_t *dst, int32_t *dist,
                  float *std_dev, uint8_t *flags, uint32_t *eid, uint32_t *win_rec,
                  uint8_t *estate);
+/* edge states only, indexed by eid (= index into graph->edges[]): what the binding
+   needs to write edge->state back, 1 B/edge on the bus.  Single-device graphs. */
+int gtsb_get_edge_states(gtsb_context *ctx, uint8_t *estate_by_eid);
 /* device pointers of the resident result (for callers that keep it on the GPU) */
 int gtsb_device_pointers(gtsb_context *ctx, const uint32_t **row_ptr, const uint32_t **dst,
                          const uint32_t **eid, const uint8_t **estate, const uint8_t **vstate);

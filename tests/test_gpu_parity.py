@@ -189,3 +189,22 @@ def test_filter_on_uploaded_graph_with_arbitrary_states(pkg, synth):
         c = g.csr(eid=False)
         assert np.array_equal(g.vstate(), ref.vstate()), seed
         assert np.array_equal(c["estate"], ref.estate()[eids]), seed
+
+
+def test_line_shaped_input_and_states_by_eid(pkg, synth):
+    """gtsb_set_record_lines_host / gtsb_get_edge_states: the same graph and marks as the
+    flat record input, with 4 B/record less on the way in and 1 B/edge on the way out."""
+    inp = synth.generate("c2_bacterial", V=20_000, seed=21, mirror_diff_frac=0.1, dup_same_line_frac=0.05)
+    a = pkg.ScaffoldGraphB200.new_from_records(inp)
+    a.mark_repeats()
+    a.filter()
+    ra = a.result()
+    b = pkg.ScaffoldGraphB200()
+    b.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+    line_root, line_start = pkg.api.lines_of(inp.root)
+    b.set_record_lines(line_root, line_start, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+    b.pipeline()
+    rb = b.result()
+    _cmp(rb, ra, "line-shaped input")
+    assert np.array_equal(b.edge_states(), ra["estate"])
+    assert np.array_equal(a.edge_states(), ra["estate"])
