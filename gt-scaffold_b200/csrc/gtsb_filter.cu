@@ -467,30 +467,50 @@ __global__ void __launch_bounds__(32 * WARPS, 4) k4_pairs(FilterArgs a) {
     });
 }
 
-// block per big row; per-block scratch: copy_num[max_deg] f32, mark[max_deg] u8
+// block per big row; per-block scratch: copy_num[max_deg] f32, low[max_deg] u32, mark[max_deg] u8.
+// A pair can only propose if cn1 + cn2 < cncutoff, so one of the two has cn < cncutoff / 2:
+// only the pairs with at least one such "low" slot are evaluated (|low| x d instead of d^2 / 2).
 __global__ void __launch_bounds__(512) k4_pairs_big(FilterArgs a) {
   const GraphArgs &g = a.g;
+  __shared__ uint32_t s_nlow;
   float *cn = reinterpret_cast<float *>(a.big_scratch + (size_t) blockIdx.x * g.max_deg * BIG_SCRATCH_STRIDE);
+  uint32_t *low = reinterpret_cast<uint32_t *>(cn + g.max_deg);
   uint8_t *mark = reinterpret_cast<uint8_t *>(cn + 2 * (size_t) g.max_deg);
+  const float half = __fmul_rn(a.cncutoff, 0.5f);
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
     const uint32_t p = g.big_rows[li];
     if (a.vinfo[p].y & VI_MARKED) continue;                        // block-uniform
     const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    if (threadIdx.x == 0) s_nlow = 0;
+    __syncthreads();
     for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
-      cn[k] = __uint_as_float(a.vinfo[g.dst[r0 + k]].x);
+      const float c = __uint_as_float(a.vinfo[g.dst[r0 + k]].x);
+      cn[k] = c;
       mark[k] = 0;
+      // c + c2 < cut with c2 >= c implies c < cut / 2 in exact arithmetic; the float sum can round
+      // down by half an ulp, so the list is taken with a margin and the exact test decides below
+      if (!(c > half + fabsf(half) * 1e-6f + 1e-30f)) low[atomicAdd(&s_nlow, 1u)] = k;
     }
     __syncthreads();
-    for (uint32_t i = 0; i + 1 < d; i++) {
+    const uint32_t nlow = s_nlow;
+    for (uint32_t x = 0; x < nlow; x++) {
+      const uint32_t i = low[x];
       const int32_t di = g.dist[r0 + i];
       const float si = g.std_dev[r0 + i], ci = cn[i];
       const uint32_t fi = g.flags[r0 + i] & F_SENSE;
-      for (uint32_t j = i + 1 + threadIdx.x; j < d; j += blockDim.x) {
-        if ((g.flags[r0 + j] & F_SENSE) != fi) continue;
+      for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+        if (j == i || (g.flags[r0 + j] & F_SENSE) != fi) continue;
         const float cj = cn[j];
-        if (ambiguous_order(di, si, g.dist[r0 + j], g.std_dev[r0 + j], a.ambig) &&
-            __fadd_rn(ci, cj) < a.cncutoff)
-          mark[ci < cj ? i : j] = 1;
+        if (!(__fadd_rn(ci, cj) < a.cncutoff)) continue;
+        // check_mark_polymorphic, algorithms.c:232-238 (edge1 = earlier adjacency slot)
+        const bool i_first = i < j;
+        const int32_t dj = g.dist[r0 + j];
+        const float sj = g.std_dev[r0 + j];
+        const bool amb = i_first ? ambiguous_order(di, si, dj, sj, a.ambig) : ambiguous_order(dj, sj, di, si, a.ambig);
+        if (!amb) continue;
+        const float c1 = i_first ? ci : cj, c2 = i_first ? cj : ci;
+        const uint32_t k1 = i_first ? i : j, k2 = i_first ? j : i;
+        mark[c1 < c2 ? k1 : k2] = 1;
       }
     }
     __syncthreads();
@@ -676,11 +696,14 @@ __global__ void __launch_bounds__(128) k4_fire_redo(FilterArgs a, const uint32_t
   }
 }
 
-// block per big row; undecided big rows go straight to the fire worklist
+// block per big row; undecided big rows go straight to the fire worklist.  Only
+// "some pair overlaps by more than ocutoff" is needed per direction, and a hub
+// almost always has such a pair early: the pair loop stops as soon as both
+// directions are settled (found, or fewer than two unmarked edges).
 __global__ void __launch_bounds__(512) k4_fire_init_big(FilterArgs a, uint32_t *__restrict__ work_out,
                                                          uint32_t *__restrict__ n_out) {
   const GraphArgs &g = a.g;
-  __shared__ long long s_mx[2];
+  __shared__ uint32_t s_found[2], s_cnt[2];
   uint32_t *len = reinterpret_cast<uint32_t *>(a.big_scratch + (size_t) blockIdx.x * g.max_deg * BIG_SCRATCH_STRIDE);
   uint8_t *ok = reinterpret_cast<uint8_t *>(len + 2 * (size_t) g.max_deg);
   for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
@@ -692,30 +715,33 @@ __global__ void __launch_bounds__(512) k4_fire_init_big(FilterArgs a, uint32_t *
     if (active && a.ocutoff < 0) {
       gb = 3;
     } else if (active) {
-      if (threadIdx.x < 2) s_mx[threadIdx.x] = 0;
+      if (threadIdx.x < 2) s_found[threadIdx.x] = s_cnt[threadIdx.x] = 0;
+      __syncthreads();
       for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
         const uint32_t w = g.dst[r0 + k];
         const uint2 vi = a.vinfo[w];
         len[k] = vi.y & ~VI_MARKED;
-        ok[k] = slot_unmarked(a, r0 + k, vi.y, w, v_id) ? 1 : 0;
+        const bool u = slot_unmarked(a, r0 + k, vi.y, w, v_id);
+        ok[k] = u ? 1 : 0;
+        if (u) atomicAdd(&s_cnt[(g.flags[r0 + k] & F_SENSE) ? 1 : 0], 1u);
       }
       __syncthreads();
-      long long mx[2] = {0, 0};
+      volatile uint32_t *found = s_found;
+      const bool need0 = s_cnt[0] >= 2, need1 = s_cnt[1] >= 2;
       for (uint32_t i = 0; i + 1 < d; i++) {
+        if ((!need0 || found[0]) && (!need1 || found[1])) break;     // no barrier inside: exits may differ by a few i
         if (!ok[i]) continue;
+        const uint32_t fi = g.flags[r0 + i] & F_SENSE;
+        if (found[fi]) continue;
         const int32_t di = g.dist[r0 + i];
         const uint32_t li_ = len[i];
-        const uint32_t fi = g.flags[r0 + i] & F_SENSE;
         for (uint32_t j = i + 1 + threadIdx.x; j < d; j += blockDim.x) {
           if (!ok[j] || (g.flags[r0 + j] & F_SENSE) != fi) continue;
-          const long long ov = interval_overlap(di, li_, g.dist[r0 + j], len[j]);
-          if (ov > mx[fi]) mx[fi] = ov;
+          if (interval_overlap(di, li_, g.dist[r0 + j], len[j]) > a.ocutoff) found[fi] = 1;
         }
       }
-      if (mx[0] > 0) atomicMax(&s_mx[0], mx[0]);
-      if (mx[1] > 0) atomicMax(&s_mx[1], mx[1]);
       __syncthreads();
-      gb = (uint8_t) ((s_mx[0] > a.ocutoff ? 1 : 0) | (s_mx[1] > a.ocutoff ? 2 : 0));
+      gb = (uint8_t) ((s_found[0] ? 1 : 0) | (s_found[1] ? 2 : 0));
     }
     if (threadIdx.x == 0) {
       a.gbits[p] = gb;
