@@ -330,6 +330,13 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   }
 }
 
+// every group's cursor starts at the offset of its mailbox region
+__global__ void __launch_bounds__(256) k2_init_group_cursors(Build2Args a) {
+  const uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t p = (uint64_t) grp << GROUP_SHIFT;
+  if (p < a.V) a.cursor[grp] = a.bptr[p];
+}
+
 // pass D-B: stream the coarsely sorted entries into the mailbox region of
 // their destination GROUP of 2^GROUP_SHIFT positions (k2_resolve sorts a
 // segment's mail by line in shared memory).  One cursor per group: few enough
@@ -353,8 +360,7 @@ __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
 #pragma unroll
     for (int k = 0; k < ILP; k++)
       if (pc[k] != UNSET) {
-        const uint32_t grp = pc[k] >> GROUP_SHIFT;
-        at[k] = a.bptr[grp << GROUP_SHIFT] + atomicAdd(&a.cursor[grp], 1u);
+        at[k] = atomicAdd(&a.cursor[pc[k] >> GROUP_SHIFT], 1u);     // cursors start at the group's offset
       }
 #pragma unroll
     for (int k = 0; k < ILP; k++)
@@ -662,6 +668,8 @@ int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
   if (nseg == 0) return 0;
   {
     KernelTimer t_("k2_deliver", s);
+    const uint32_t ngrp = (a.V >> GROUP_SHIFT) + 1;
+    k2_init_group_cursors<<<(ngrp + 255) / 256, 256, 0, s>>>(a);
     k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
   }
   KernelTimer t_("k2_resolve", s);
