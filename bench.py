@@ -312,6 +312,13 @@ def run_b200_arm(args, pkg):
                              "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
                 "kernels_ms_per_step": {k: round(v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}}
     roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
+    # DRAM bytes of that kernel from the committed `ncu --set full` capture of the same workload
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if world == 1 and os.path.exists(tp):
+        tr = json.load(open(tp))
+        if tr.get("workload") == args.workload and tr.get("vertices") == Vn:
+            roofline["traffic"] = tr.get("dram_bytes_per_launch", {}).get(dom[0].split("(")[0])
+            roofline["traffic_source"] = tr.get("source")
 
     cb, _, _ = cpu_reference_leg(pkg, args.workload, args.cpu_sample_vertices, args.line_order)
     line = {"metric": METRIC, "value": E_all / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
