@@ -212,8 +212,8 @@ __device__ __forceinline__ void for_each_window(const GraphArgs &g, StageA stage
   const uint32_t nbatch = (nwin + 31u) / 32u;
   for (uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5); b < nbatch; b += gridDim.x * WARPS) {
     const uint32_t w0 = b * 32u;
-    const uint32_t ws = w0 + lane <= nwin ? g.win_start[w0 + lane] : 0u;
-    const uint32_t wlast = w0 + 32u <= nwin ? g.win_start[w0 + 32u] : 0u;   // same address in every lane
+    const uint32_t ws = w0 + lane <= nwin ? __ldcs(g.win_start + w0 + lane) : 0u;
+    const uint32_t wlast = w0 + 32u <= nwin ? __ldcs(g.win_start + w0 + 32u) : 0u;   // same address in every lane
     const uint32_t cnt = nwin - w0 < 32u ? nwin - w0 : 32u;
     for (uint32_t k = 0; k < cnt; k += U) {
       decltype(stageA(0u, 0u)) st[U];
@@ -415,12 +415,13 @@ __global__ void __launch_bounds__(32 * WARPS, 4) k4_pairs(FilterArgs a) {
       t.n = n;
       const bool valid = lane < n;
       const uint32_t s = start + lane;
-      t.sp = valid ? g.srcp[s] : NONE;
-      t.dst = valid ? g.dst[s] : 0u;
-      t.fl = valid ? g.flags[s] : 0u;
-      t.me.dist = valid ? g.dist[s] : 0;
-      t.me.std_dev = valid ? g.std_dev[s] : 0.f;
-      t.es = (valid && !a.fused_repeats) ? g.estate[s] : (uint8_t) 0;
+      // slot columns are read once: evict-first, so that the gathered tables stay in L2
+      t.sp = valid ? __ldcs(g.srcp + s) : NONE;
+      t.dst = valid ? __ldcs(g.dst + s) : 0u;
+      t.fl = valid ? __ldcs(g.flags + s) : 0u;
+      t.me.dist = valid ? __ldcs(g.dist + s) : 0;
+      t.me.std_dev = valid ? __ldcs(g.std_dev + s) : 0.f;
+      t.es = (valid && !a.fused_repeats) ? __ldcs(g.estate + s) : (uint8_t) 0;
       return t;
     },
     [&](PairsState &t) {
@@ -820,9 +821,9 @@ __global__ void __launch_bounds__(32 * WARPS, 6) k4_fire_dense(FilterArgs a, uin
       t.n = n;
       const bool valid = lane < n;
       const uint32_t s = start + lane;
-      t.sp = valid ? g.srcp[s] : NONE;
-      t.dst = valid ? g.dst[s] : 0u;
-      t.fl = valid ? g.flags[s] : 0u;
+      t.sp = valid ? __ldcs(g.srcp + s) : NONE;
+      t.dst = valid ? __ldcs(g.dst + s) : 0u;
+      t.fl = valid ? __ldcs(g.flags + s) : 0u;
       return t;
     },
     [&](DenseState &t) {
@@ -922,9 +923,9 @@ __device__ __forceinline__ void final_state(const FilterArgs &a, uint32_t s, uin
     if (me > ti) ti = me;
   }
   if (tp < 0 && ti < 0) {
-    if (a.fused_repeats) g.estate[s] = ((own | ru) & VR_REP) ? GIS_REPEAT : GIS_UNVISITED;
+    if (a.fused_repeats) __stcs(g.estate + s, (uint8_t) (((own | ru) & VR_REP) ? GIS_REPEAT : GIS_UNVISITED));
   } else {
-    g.estate[s] = ti >= tp ? GIS_INCONSISTENT : GIS_POLYMORPHIC;
+    __stcs(g.estate + s, (uint8_t) (ti >= tp ? GIS_INCONSISTENT : GIS_POLYMORPHIC));
   }
 }
 
@@ -942,9 +943,9 @@ __global__ void __launch_bounds__(32 * WARPS, 6) k4_finalize(FilterArgs a) {
       t.n = n;
       const bool valid = lane < n;
       const uint32_t s = start + lane;
-      t.sp = valid ? g.srcp[s] : NONE;
-      t.dst = valid ? g.dst[s] : 0u;
-      t.fl = valid ? g.flags[s] : 0u;
+      t.sp = valid ? __ldcs(g.srcp + s) : NONE;
+      t.dst = valid ? __ldcs(g.dst + s) : 0u;
+      t.fl = valid ? __ldcs(g.flags + s) : 0u;
       return t;
     },
     [&](FinalState &t) {
