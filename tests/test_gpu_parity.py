@@ -208,3 +208,56 @@ def test_line_shaped_input_and_states_by_eid(pkg, synth):
     _cmp(rb, ra, "line-shaped input")
     assert np.array_equal(b.edge_states(), ra["estate"])
     assert np.array_equal(a.edge_states(), ra["estate"])
+
+
+def test_full_size_properties_c3(pkg, synth):
+    """BASELINE.json's human-scale graph at full size (10^7 contigs, 8*10^7 edges), where the
+    oracle is too slow: size-independent properties of the result, and the two independent
+    build algorithms (line-ordered and general sort-based) against each other."""
+    import torch
+    t = synth.generate_torch("c3_human", device="cuda")
+    V, R = int(t["seq_len"].shape[0]), int(t["root"].shape[0])
+
+    def run(force_general):
+        g = pkg.ScaffoldGraphB200(force_general=force_general)
+        g.set_vertices_device(V, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
+        g.set_records_device(R, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
+                             t["std_dev"].data_ptr(), t["flags"].data_ptr())
+        g.pipeline()
+        e, vs, st = g.edges(), g.vstate(), g.stats()
+        again = None
+        if not force_general:
+            g.pipeline()                                   # idempotent on the same inputs
+            again = (g.edge_states(), g.vstate())
+        g.close()
+        order = np.argsort(e["eid"], kind="stable")
+        return {k: v[order] for k, v in e.items()}, vs, st, again
+
+    e, vs, st, again = run(False)
+    assert st["line_ordered_build"] == 1
+    E = e["eid"].shape[0]
+    assert E % 2 == 0 and np.array_equal(e["eid"], np.arange(E, dtype=np.uint32))
+    assert np.array_equal(again[0], e["estate"]) and np.array_equal(again[1], vs)
+    # edges come in mutually reverse pairs 2k / 2k+1 (parser.c:374-377)
+    assert np.array_equal(e["src"][0::2], e["dst"][1::2]) and np.array_equal(e["dst"][0::2], e["src"][1::2])
+    # mark_repeats closed form (algorithms.c:160-166, 61-87)
+    astat, cn = t["astat"].cpu().numpy(), t["copy_num"].cpu().numpy()
+    pred = (astat <= np.float32(20.0)) | (cn < np.float32(0.3))
+    assert np.array_equal(vs == 3, pred)
+    assert not np.any((vs == 1) & pred)
+    touched = pred[e["src"]] | pred[e["dst"]]
+    assert np.all(e["estate"][touched] != 0)
+    assert np.all(touched[e["estate"] == 3])
+    # every edge at a polymorphic contig is marked (mark_vertex, algorithms.c:76-87)
+    poly = vs == 1
+    at_poly = poly[e["src"]] | poly[e["dst"]]
+    assert np.all(np.isin(e["estate"][at_poly], (1, 2)))
+    assert set(np.unique(e["estate"]).tolist()) <= {0, 1, 2, 3}
+    # the general build is a different algorithm; same graph, same marks
+    e2, vs2, st2, _ = run(True)
+    assert st2["line_ordered_build"] == 0
+    for k in ("src", "dst", "dist", "std_dev", "flags", "estate"):
+        assert np.array_equal(e[k], e2[k]), k
+    assert np.array_equal(vs, vs2)
+    del t
+    torch.cuda.empty_cache()
