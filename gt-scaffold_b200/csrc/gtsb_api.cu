@@ -547,10 +547,13 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   c->stats.poly_sweeps = 0;
   if (nprop) {
     for (;;) {
-      CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
-      launch_poly_sweep(a, nprop, s);
-      c->stats.kernel_launches += 3;
-      c->stats.poly_sweeps++;
+      // a few sweeps per host synchronisation; converged when the last one changed nothing
+      for (int k = 0; k < POLY_SWEEPS_PER_SYNC; k++) {
+        CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
+        launch_poly_sweep(a, nprop, s);
+        c->stats.kernel_launches += 3;
+        c->stats.poly_sweeps++;
+      }
       if (read_counters(c) != 0) return -1;
       if (!c->h_counters[CNT_POLY_CHANGED]) break;
       if (c->stats.poly_sweeps > V + 2) return fail(c, "gtsb_filter: polyTime sweeps did not converge");

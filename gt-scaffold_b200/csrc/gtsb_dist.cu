@@ -606,10 +606,12 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
     FilterArgs pa = a;
     pa.proposals = D->prop_all.as<uint2>();
     for (;;) {
-      CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
-      launch_poly_sweep(pa, nprop, s);
-      c->stats.kernel_launches += 3;
-      c->stats.poly_sweeps++;
+      for (int k = 0; k < POLY_SWEEPS_PER_SYNC; k++) {
+        CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
+        launch_poly_sweep(pa, nprop, s);
+        c->stats.kernel_launches += 3;
+        c->stats.poly_sweeps++;
+      }
       if (read_counters(c) != 0) return -1;
       if (!c->h_counters[CNT_POLY_CHANGED]) break;
       if (c->stats.poly_sweeps > Vg + 2) return fail(c, "gtsb_filter: polyTime sweeps did not converge");

@@ -208,7 +208,8 @@ void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out,
 // covers n_max >= it, so that several rounds can be queued between two host synchronisations
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, const uint32_t *n_in_dev, uint32_t n_max,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
-constexpr int FIRE_ROUNDS_PER_SYNC = 3;
+constexpr int FIRE_ROUNDS_PER_SYNC = 4;
+constexpr int POLY_SWEEPS_PER_SYNC = 4;
 void launch_vres(const FilterArgs &a, cudaStream_t s);          // final per-vertex facts (+ POLYMORPHIC vertex marks)
 void launch_finalize(const FilterArgs &a, cudaStream_t s);      // final edge states; needs every neighbour's vres
 // cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)
