@@ -187,9 +187,18 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   uint32_t *s_ctg = s_nown + SEG_LINES + 4;
   uint8_t *s_line = reinterpret_cast<uint8_t *>(s_ctg + SEG_REC_CAP);
   __shared__ uint32_t s_bounds[MAX_RANKS + 1], s_rcnt[MAX_RANKS];
+  // 256-bit Bloom filter per line over its neighbours: a line whose records all hit distinct
+  // bits has no repeated neighbour, and the quadratic duplicate scan is skipped for it
+  __shared__ uint32_t s_bloom[SEG_LINES][8];
+  __shared__ uint8_t s_maydup[SEG_LINES];
   Seg g;
   const bool ok = seg_open(a, blockIdx.x, g, s_ls);
-  for (uint32_t j = threadIdx.x; j < SEG_LINES; j += blockDim.x) s_nown[j] = 0;
+  for (uint32_t j = threadIdx.x; j < SEG_LINES; j += blockDim.x) {
+    s_nown[j] = 0;
+    s_maydup[j] = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s_bloom[j][w] = 0;
+  }
   for (uint32_t j = threadIdx.x; j < (uint32_t) a.nranks; j += blockDim.x) {
     s_rcnt[j] = 0;
     s_bounds[j + 1] = a.rank_bounds[j + 1];
@@ -197,6 +206,11 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   if (ok) {
     seg_lines(a, g, s_ls, s_line);
     for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) s_ctg[r] = a.ctg[g.rec0 + r];
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
+      const uint32_t j = s_line[r], h = (s_ctg[r] * 2654435761u) >> 24;
+      if (atomicOr(&s_bloom[j][h >> 5], 1u << (h & 31u)) & (1u << (h & 31u))) s_maydup[j] = 1;
+    }
     __syncthreads();
     for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) {
       const uint32_t j = s_line[r], c = s_ctg[r];
@@ -211,11 +225,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
       } else {
         pc = a.pos[c];
         bool first = true, dup = false;
-        for (uint32_t t = s_ls[j] - g.rec0; t < s_ls[j + 1] - g.rec0; t++)
-          if (s_ctg[t] == c && t != r) {
-            dup = true;
-            first &= t > r;
-          }
+        if (s_maydup[j])
+          for (uint32_t t = s_ls[j] - g.rec0; t < s_ls[j + 1] - g.rec0; t++)
+            if (s_ctg[t] == c && t != r) {
+              dup = true;
+              first &= t > r;
+            }
         rf = (uint8_t) ((a.pos_base + p < pc ? RF_UP : 0u) | (first ? RF_FIRST : 0u) | (c < me ? RF_LT : 0u) |
                         (dup ? RF_DUP : 0u));
         if ((rf & RF_CREATOR) == RF_CREATOR) {
