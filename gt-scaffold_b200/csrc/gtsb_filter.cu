@@ -405,10 +405,10 @@ struct PairsState {
   uint8_t es;
 };
 
-__global__ void __launch_bounds__(32 * WARPS, 4) k4_pairs(FilterArgs a) {
+__global__ void __launch_bounds__(32 * WARPS, 6) k4_pairs(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
-  for_each_window<2>(g,
+  for_each_window<1>(g,
     [&](uint32_t start, uint32_t n) {
       PairsState t;
       t.start = start;
