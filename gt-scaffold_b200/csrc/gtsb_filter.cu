@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(32 * WARPS, 6) k4_fire_dense(FilterArgs a, uin
   const uint32_t lane = lane_id();
   __shared__ uint32_t s_q[WARPS][WarpQueue::QCAP];
   WarpQueue q{s_q[threadIdx.x >> 5], 0u};
-  for_each_window<4>(g,
+  for_each_window<2>(g,
     [&](uint32_t start, uint32_t n) {
       DenseState t;
       t.start = start;
@@ -936,7 +936,7 @@ struct FinalState {
 __global__ void __launch_bounds__(32 * WARPS, 6) k4_finalize(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
-  for_each_window<4>(g,
+  for_each_window<2>(g,
     [&](uint32_t start, uint32_t n) {
       FinalState t;
       t.start = start;
