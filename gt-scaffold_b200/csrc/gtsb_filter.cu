@@ -807,14 +807,14 @@ struct DenseState {
   uint32_t start, n, sp, dst, fl, st, su;
 };
 
-__global__ void __launch_bounds__(32 * WARPS, 6) k4_fire_dense(FilterArgs a, uint32_t *__restrict__ work_out,
+__global__ void __launch_bounds__(32 * WARPS, 8) k4_fire_dense(FilterArgs a, uint32_t *__restrict__ work_out,
                                                              uint32_t *__restrict__ n_out) {
   const GraphArgs &g = a.g;
   const volatile uint8_t *fstat = a.fstat;
   const uint32_t lane = lane_id();
   __shared__ uint32_t s_q[WARPS][WarpQueue::QCAP];
   WarpQueue q{s_q[threadIdx.x >> 5], 0u};
-  for_each_window<2>(g,
+  for_each_window<1>(g,
     [&](uint32_t start, uint32_t n) {
       DenseState t;
       t.start = start;
@@ -933,10 +933,10 @@ struct FinalState {
   uint32_t start, n, sp, dst, fl, own, ru;
 };
 
-__global__ void __launch_bounds__(32 * WARPS, 6) k4_finalize(FilterArgs a) {
+__global__ void __launch_bounds__(32 * WARPS, 8) k4_finalize(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
-  for_each_window<2>(g,
+  for_each_window<1>(g,
     [&](uint32_t start, uint32_t n) {
       FinalState t;
       t.start = start;
