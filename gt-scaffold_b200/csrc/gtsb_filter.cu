@@ -405,7 +405,7 @@ struct PairsState {
   uint8_t es;
 };
 
-__global__ void __launch_bounds__(32 * WARPS, 6) k4_pairs(FilterArgs a) {
+__global__ void __launch_bounds__(32 * WARPS, 8) k4_pairs(FilterArgs a) {
   const GraphArgs &g = a.g;
   const uint32_t lane = lane_id();
   for_each_window<1>(g,
