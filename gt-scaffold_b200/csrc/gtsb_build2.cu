@@ -340,8 +340,14 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     e.w = __float_as_uint(s_std[r]);
     const uint32_t b = bin_of(pc);
     const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
-    a.tmp_ent[at] = e;
-    a.tmp_dest[at] = pc;
+    if (a.peer_ent == nullptr) {
+      a.tmp_ent[at] = e;
+      a.tmp_dest[at] = pc;
+    } else {                                        // the receiving rank's memory
+      const long long to = (long long) at + a.peer_shift[b];
+      a.peer_ent[b][to] = e;
+      a.peer_dest[b][to] = pc;
+    }
   }
 }
 

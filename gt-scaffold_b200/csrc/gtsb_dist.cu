@@ -80,8 +80,12 @@ const char *load_nccl() {
 
 struct DistState {
   ncclComm_t comm = nullptr;
-  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage;
+  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage, peer_tab, handles;
   uint32_t *h_small = nullptr;     // pinned, world * SMALL_N words
+  // every rank's receive buffers, opened through CUDA IPC (peer memory over NVLink)
+  void *peer_ptr[MAX_RANKS][2] = {};
+  cudaIpcMemHandle_t peer_handle[MAX_RANKS][2] = {};
+  bool peers_open = false;
 };
 constexpr int SMALL_N = MAX_RANKS + 8;
 
@@ -220,6 +224,37 @@ __global__ void k_edges(GraphArgs g, const uint32_t *__restrict__ eid_in, uint32
   flags[s] = g.flags[s] & 0x0Fu;
 }
 
+// (re)open every rank's receive buffers; collective
+int open_peer_buffers(gtsb_context *c) {
+  DistState *D = static_cast<DistState *>(c->dstate);
+  const int N = c->world, me = c->rank;
+  cudaIpcMemHandle_t mine[2];
+  CK(cudaIpcGetMemHandle(&mine[0], D->rx_ent.p));
+  CK(cudaIpcGetMemHandle(&mine[1], D->rx_dest.p));
+  const size_t hb = 2 * sizeof(cudaIpcMemHandle_t);
+  ENSURE(D->handles, hb * MAX_RANKS);
+  std::vector<cudaIpcMemHandle_t> all(2 * (size_t) N);
+  CK(cudaMemcpyAsync(D->handles.as<char>() + hb * me, mine, hb, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(D->handles.as<char>() + hb * me, D->handles.p, hb, ncclUint8, D->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), D->handles.p, hb * N, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < N; r++)
+    for (int k = 0; k < 2; k++) {
+      if (r == me) {
+        D->peer_ptr[r][k] = k == 0 ? D->rx_ent.p : D->rx_dest.p;
+        continue;
+      }
+      if (D->peer_ptr[r][k] != nullptr && memcmp(&D->peer_handle[r][k], &all[2 * r + k], sizeof(cudaIpcMemHandle_t)) == 0)
+        continue;
+      if (D->peer_ptr[r][k] != nullptr) CK(cudaIpcCloseMemHandle(D->peer_ptr[r][k]));
+      D->peer_ptr[r][k] = nullptr;
+      CK(cudaIpcOpenMemHandle(&D->peer_ptr[r][k], all[2 * r + k], cudaIpcMemLazyEnablePeerAccess));
+      D->peer_handle[r][k] = all[2 * r + k];
+    }
+  D->peers_open = true;
+  return 0;
+}
+
 }  // namespace gtsbd
 
 using namespace gtsbd;
@@ -230,7 +265,11 @@ void dist_release(gtsb_context *c) {
   DistState *D = static_cast<DistState *>(c->dstate);
   if (D == nullptr) return;
   if (D->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(D->comm);
-  for (DevBuf *b : {&D->small, &D->bounds, &D->rank_cnt, &D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage})
+  for (int r = 0; r < c->world; r++)
+    for (int k = 0; k < 2; k++)
+      if (r != c->rank && D->peer_ptr[r][k] != nullptr) cudaIpcCloseMemHandle(D->peer_ptr[r][k]);
+  for (DevBuf *b : {&D->small, &D->bounds, &D->rank_cnt, &D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage,
+                    &D->peer_tab, &D->handles})
     if (b->owned && b->p != nullptr) cudaFree(b->p);
   if (D->h_small != nullptr) cudaFreeHost(D->h_small);
   delete D;
@@ -429,27 +468,46 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     CK(cudaStreamSynchronize(s));
     return 0;
   }();
-  if (exchange(c, rc, "classify", mine, N + 1, all) != 0) return -1;
+  // besides the counts every rank tells how much mail its receive buffers hold now, so that all
+  // ranks know who is about to reallocate them (the peers then have to reopen them)
+  const uint64_t rx_cap = D->peers_open ? D->rx_dest.cap / 4 : 0;
+  mine[N + 1] = (uint32_t) (rx_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : rx_cap);
+  if (exchange(c, rc, "classify", mine, N + 2, all) != 0) return -1;
+  const int W = N + 2;
   uint64_t k_base = 0, n_creators = 0;
   for (int r = 0; r < N; r++) {
-    if (r < me) k_base += all[(size_t) r * (N + 1)];
-    n_creators += all[(size_t) r * (N + 1)];
+    if (r < me) k_base += all[(size_t) r * W];
+    n_creators += all[(size_t) r * W];
   }
   if (2 * n_creators >= 0xFFFFFFF0ull) return fail(c, "too many edges for 32-bit edge ids");
   a.k_base = (uint32_t) k_base;
   std::vector<uint64_t> s_off(N + 1, 0), r_off(N + 1, 0);
   for (int r = 0; r < N; r++) {
-    s_off[r + 1] = s_off[r] + all[(size_t) me * (N + 1) + 1 + r];      // what I send to r
-    r_off[r + 1] = r_off[r] + all[(size_t) r * (N + 1) + 1 + me];      // what r sends to me
+    s_off[r + 1] = s_off[r] + all[(size_t) me * W + 1 + r];      // what I send to r
+    r_off[r + 1] = r_off[r] + all[(size_t) r * W + 1 + me];      // what r sends to me
   }
   const uint64_t M = r_off[N];                                         // mail for my rows
+  bool reopen = false;
+  std::vector<long long> shift(N, 0);
+  for (int r = 0; r < N; r++) {
+    uint64_t Mr = 0, before_me = 0;                                    // r's mail; the part from ranks before me
+    for (int h = 0; h < N; h++) {
+      if (h < me) before_me += all[(size_t) h * W + 1 + r];
+      Mr += all[(size_t) h * W + 1 + r];
+    }
+    reopen |= Mr + 1 > (uint64_t) all[(size_t) r * W + N + 1];
+    shift[r] = (long long) before_me - (long long) s_off[r];
+  }
   tr.mark(me, "classify+exchange");
 
-  // ---- messages grouped by destination rank, then the exchange
-  c->stats.kernel_launches += launch_b2_partition(a, s);
+  // ---- receive buffers, then the messages: k2_partition stores every rank's mail straight into
+  // that rank's buffers (peer memory over NVLink) while it computes the next ones
   rc = [&]() -> int {
-    ENSURE(D->rx_ent, (M + 1) * sizeof(uint4));
-    ENSURE(D->rx_dest, (M + 1) * 4);
+    // 1/8 headroom: the buffers, and with them the peers' mappings, survive small changes
+    if (D->rx_dest.cap / 4 < M + 1 || !D->peers_open) {
+      ENSURE(D->rx_ent, (M + M / 8 + 16) * sizeof(uint4));
+      ENSURE(D->rx_dest, (M + M / 8 + 16) * 4);
+    }
     ENSURE(c->bucket, (M + 1) * sizeof(uint4));
     ENSURE(c->bucket_line, M + 16);
     const uint64_t max_rows = (M + mine[0] + 1) / 2 + 1;               // slots = mail + own creators
@@ -457,24 +515,33 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
     ENSURE(c->corrections, (size_t) corr_cap * sizeof(uint4));
     a.corrections_cap = corr_cap;
+    ENSURE(D->peer_tab, MAX_RANKS * 24);
     return 0;
   }();
   if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
+  if (reopen && open_peer_buffers(c) != 0) return -1;
   {
-    KernelTimer t_("nccl_alltoall_mail", s);
-    NK(g_nccl.GroupStart());
+    char tab[MAX_RANKS * 24];
+    void **pe = reinterpret_cast<void **>(tab), **pd = pe + MAX_RANKS;
+    long long *ps = reinterpret_cast<long long *>(pd + MAX_RANKS);
     for (int r = 0; r < N; r++) {
-      const size_t ns = (size_t) (s_off[r + 1] - s_off[r]), nr = (size_t) (r_off[r + 1] - r_off[r]);
-      if (ns) {
-        NK(g_nccl.Send(a.tmp_ent + s_off[r], ns * 16, ncclUint8, r, D->comm, s));
-        NK(g_nccl.Send(a.tmp_dest + s_off[r], ns, ncclUint32, r, D->comm, s));
-      }
-      if (nr) {
-        NK(g_nccl.Recv(D->rx_ent.as<uint4>() + r_off[r], nr * 16, ncclUint8, r, D->comm, s));
-        NK(g_nccl.Recv(D->rx_dest.as<uint32_t>() + r_off[r], nr, ncclUint32, r, D->comm, s));
-      }
+      pe[r] = D->peer_ptr[r][0];
+      pd[r] = D->peer_ptr[r][1];
+      ps[r] = shift[r];
     }
-    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(D->peer_tab.p, tab, sizeof tab, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));                                      // tab lives on this stack frame
+    a.peer_ent = reinterpret_cast<uint4 *const *>(D->peer_tab.p);
+    a.peer_dest = reinterpret_cast<uint32_t *const *>(D->peer_tab.as<char>() + MAX_RANKS * 8);
+    a.peer_shift = reinterpret_cast<const long long *>(D->peer_tab.as<char>() + MAX_RANKS * 16);
+  }
+  // nobody may overwrite a receive buffer its owner is still reading (previous step): the classify
+  // exchange above already ordered every rank behind every rank's previous step
+  c->stats.kernel_launches += launch_b2_partition(a, s);
+  {
+    // all mail has landed once every rank's partition kernel is complete: a stream-ordered barrier
+    KernelTimer t_("nccl_barrier_mail", s);
+    NK(g_nccl.AllReduce(D->small.p, D->small.p, 1, ncclUint32, ncclSum, D->comm, s));
   }
 
   tr.mark(me, "partition+alltoall");

@@ -68,6 +68,11 @@ struct Build2Args {
   uint32_t *rank_cnt;                       // [nranks] mail this rank sends to every rank
   const uint4 *mail_ent;                    // the stream k2_deliver reads (tmp_ent, or what the ranks sent us)
   const uint32_t *mail_dest;
+  // partitioned build: k2_partition stores each rank's mail straight into that rank's receive
+  // buffers over NVLink (peer memory); entry `at` of my send order goes to index at + peer_shift[r]
+  uint4 *const *peer_ent;                   // [nranks] (nullptr: write tmp_ent / tmp_dest)
+  uint32_t *const *peer_dest;
+  const long long *peer_shift;
   int sm_count;
   uint32_t coarse_shift, corrections_cap;
   const uint32_t *root, *ctg;
