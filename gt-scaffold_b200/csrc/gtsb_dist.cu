@@ -10,7 +10,8 @@
 //
 //   build   position table id -> position          allreduce(min), 4 B/vertex
 //           contig ids by position                  allgatherv,     4 B/vertex
-//           mail (creator -> twin row)              all-to-all,     20 B/pair
+//           mail (creator -> twin row)              remote stores from k2_partition into the
+//                                                   owner's receive buffers (CUDA IPC), 20 B/pair
 //           reverse-flag corrections                allgatherv,     rare
 //   filter  packed neighbour facts vinfo            allgatherv,     8 B/vertex
 //           polymorphic proposals                   allgatherv,     8 B/proposal;
