@@ -88,10 +88,24 @@ __global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V, uin
   uint32_t heads = 0, c = 0;
   uint32_t prev = (base > 0 && base <= R) ? root[base - 1] : UNSET;
   uint32_t mine[ITEMS];
+  // the thread's 16 records: four 16-byte loads when the tile is whole and aligned
+  if (base + ITEMS <= R && (reinterpret_cast<uintptr_t>(root + base) & 15u) == 0) {
+    const uint4 *v = reinterpret_cast<const uint4 *>(root + base);
+#pragma unroll
+    for (int q = 0; q < ITEMS / 4; q++) {
+      const uint4 x = __ldcs(v + q);
+      mine[4 * q] = x.x;
+      mine[4 * q + 1] = x.y;
+      mine[4 * q + 2] = x.z;
+      mine[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) mine[k] = base + k < R ? root[base + k] : UNSET;
+  }
 #pragma unroll
   for (int k = 0; k < ITEMS; k++) {
     const uint64_t i = base + k;
-    mine[k] = i < R ? root[i] : UNSET;
     if (i < R && (i == 0 || mine[k] != prev)) {
       heads |= 1u << k;
       c++;
