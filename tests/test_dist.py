@@ -85,3 +85,21 @@ def test_partitioned_pipeline_matches_the_oracle():
     out = r.stdout.decode()
     assert r.returncode == 0, out[-3000:]
     assert out.count("-> OK") >= 5, out[-3000:]
+
+
+def test_chunk_fractions_and_lines_of(pkg):
+    for world in (1, 2, 5, 8):
+        fr = pkg.api.chunk_fractions(world)
+        assert fr[0] == 0.0 and fr[-1] == 1.0 and all(a < b for a, b in zip(fr[:-1], fr[1:]))
+        widths = np.diff(fr)
+        assert all(a >= b - 1e-12 for a, b in zip(widths[:-1], widths[1:]))      # later chunks are not longer
+        # equal shares of the weight 1 + g x
+        g = pkg.api.MAIL_WEIGHT
+        share = [(b - a) + g * (b * b - a * a) / 2 for a, b in zip(fr[:-1], fr[1:])]
+        assert np.allclose(share, share[0])
+    assert pkg.api.chunk_fractions(4, 0.0) == [0.0, 0.25, 0.5, 0.75, 1.0]
+    root = np.array([7, 7, 7, 2, 9, 9, 7], np.uint32)
+    lr, ls = pkg.api.lines_of(root)
+    assert lr.tolist() == [7, 2, 9, 7] and ls.tolist() == [0, 3, 4, 6, 7]
+    lr, ls = pkg.api.lines_of(root[:0])
+    assert len(lr) == 0 and ls.tolist() == [0]
