@@ -20,7 +20,26 @@ sys.path.insert(0, HERE)
 
 PARAMS = dict(copy_num_cutoff=0.3, astat_cutoff=20.0, use_copy_num=True, pcutoff=0.01, cncutoff=1.5, ocutoff=400)
 
+def _one_record(S):
+    """One link listed on one line only: all but one rank hold no records at all."""
+    z = S.tiny_dense(5, 1, 3)
+    return S.ScaffoldInput(z.seq_len, z.astat, z.copy_num, z.root[:1], z.ctg[:1], z.dist[:1], z.std_dev[:1],
+                           z.num_pairs[:1], z.flags[:1])
+
+
+def _one_line(S):
+    """One line with two links: rank 0 holds every record, the other ranks only receive mail
+    (the neighbours have no line of their own: their rows live on the last rank)."""
+    import numpy as np
+    z = S.tiny_dense(5, 1, 3)
+    u32 = lambda *a: np.array(a, np.uint32)
+    return S.ScaffoldInput(z.seq_len, z.astat, z.copy_num, u32(2, 2), u32(0, 4), np.array([100, 120], np.int32),
+                           np.array([5.0, 7.5], np.float32), u32(10, 12), np.array([3, 1], np.uint8))
+
+
 CASES = {
+    "one_record": _one_record,
+    "one_line": _one_line,
     "tiny": lambda S: S.generate("c2_bacterial", V=40, seed=5, mean_pairs=3.0),
     "small_shuffled": lambda S: S.generate("c2_bacterial", V=3000, seed=11),
     "small_id_order": lambda S: S.generate("c2_bacterial", V=3000, seed=12, line_order="id"),
@@ -56,7 +75,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("gt-scaffold_b200")
     import oracle_lib as O
-    cases = sys.argv[1:] or ["tiny", "small_shuffled", "small_id_order", "mirror", "c2"]
+    cases = sys.argv[1:] or ["one_record", "one_line", "tiny", "small_shuffled", "small_id_order", "mirror", "c2"]
     ok = True
     for name in cases:
         inp = CASES[name](pkg.synth)
