@@ -248,12 +248,14 @@ def run_b200_arm(args, pkg):
     n_lines = int(line_root_h.shape[0])
 
     def e2e_step():
-        g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
-                                           host["copy_num"].data_ptr()))
-        g2.V = Vn
+        # records first: the vertex attributes are needed last (by the filter) and their copy,
+        # like that of dist/std_dev/flags, runs on the context's copy stream under the first kernels
         g2._ck(g2.L.gtsb_set_record_lines_host(g2.h, n_lines, line_root_h.data_ptr(), line_start_h.data_ptr(), Rn,
                                                host["ctg"].data_ptr(), host["dist"].data_ptr(),
                                                host["std_dev"].data_ptr(), host["flags"].data_ptr()))
+        g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
+                                           host["copy_num"].data_ptr()))
+        g2.V = Vn
         g2.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
                     P["cncutoff"], P["ocutoff"])
         g2._ck(g2.L.gtsb_get_vertex_states(g2.h, vstate_h.data_ptr()))

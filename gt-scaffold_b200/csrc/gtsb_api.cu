@@ -125,19 +125,48 @@ __global__ void k_pack_vattr(uint32_t V, const uint32_t *__restrict__ seq_len,
   }
 }
 
-int vertices_common(gtsb_context *c, uint64_t V) {
+int await_vertices(gtsb_context *c) {
+  if (c->vertices_pending) {
+    CK(cudaStreamWaitEvent(c->stream, c->ev_vertices, 0));
+    c->vertices_pending = false;
+  }
+  return 0;
+}
+
+int await_records(gtsb_context *c) {
+  if (c->records_pending) {
+    CK(cudaStreamWaitEvent(c->stream, c->ev_records, 0));
+    c->records_pending = false;
+  }
+  return 0;
+}
+
+// the copy stream may only start once the main stream is done with the buffers it overwrites
+int copy_stream_follows_main(gtsb_context *c) {
+  CK(cudaEventRecord(c->ev_order, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
+  return 0;
+}
+
+int vertices_common(gtsb_context *c, uint64_t V, cudaStream_t on) {
   if (V > GTSB_MAX_VERTICES) return fail(c, "too many vertices (%llu > %u)", (unsigned long long) V,
                                          GTSB_MAX_VERTICES);
   c->V = V;
   ENSURE(c->vattr, V * sizeof(VAttr));
   if (V) {
-    k_pack_vattr<<<(uint32_t) ((V + 255) / 256), 256, 0, c->stream>>>(
+    k_pack_vattr<<<(uint32_t) ((V + 255) / 256), 256, 0, on>>>(
         (uint32_t) V, c->seq_len_in.as<uint32_t>(), c->copy_num_in.as<float>(), c->vattr.as<VAttr>());
     c->stats.kernel_launches++;
   }
   ENSURE(c->vstate, V);
   ENSURE(c->rep_pred, V);
-  CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, c->stream));   // GIS_UNVISITED, graph.c:129
+  CK(cudaMemsetAsync(c->vstate.p, 0, V ? V : 1, on));   // GIS_UNVISITED, graph.c:129
+  if (on != c->stream) {
+    CK(cudaEventRecord(c->ev_vertices, on));
+    c->vertices_pending = true;
+  } else {
+    c->vertices_pending = false;
+  }
   c->have_vertices = true;
   c->have_graph = false;
   return 0;
@@ -320,6 +349,8 @@ int do_build_lines(gtsb_context *c) {
 
   if (ensure_windows(c, V, 2 * R) != 0) return -1;
   c->stats.kernel_launches += launch_build2_lines(a, s);
+  c->stats.kernel_launches += launch_build2_classify(a, s);
+  if (await_records(c) != 0) return -1;          // dist/std_dev/flags may still be on their way (copy stream)
   c->stats.kernel_launches += launch_build2_rows(a, s);
   {
     GraphArgs g{};
@@ -363,6 +394,7 @@ int do_build(gtsb_context *c) {
   }
   c->line_layout = false;
   c->csr_exported = false;
+  if (await_records(c) != 0) return -1;
 
   ENSURE(c->cnt, (V + 1) * 4);
   ENSURE(c->bptr, (V + 1) * 4);
@@ -464,6 +496,7 @@ int do_build(gtsb_context *c) {
 int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_cn) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_mark_repeats: no graph (call gtsb_build or gtsb_set_graph_host)");
+  if (await_vertices(c) != 0) return -1;
   c->csr_exported = false;
   FilterArgs a{};
   a.g = graph_args(c);
@@ -517,6 +550,7 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
               float cn_cutoff = 0.f, float astat_cutoff = 0.f, int use_cn = 0) {
   ProfScope ps_(c);
   if (!c->have_graph) return fail(c, "gtsb_filter: no graph (call gtsb_build or gtsb_set_graph_host)");
+  if (await_vertices(c) != 0) return -1;
   if (get_ambig(c, pcutoff) != 0) return -1;
   c->csr_exported = false;
   const uint64_t V = c->V, E = c->E;
@@ -662,6 +696,10 @@ int gtsb_create(gtsb_context **out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_vertices, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_records, cudaEventDisableTiming) != cudaSuccess) { delete c; return -1; }
   if (cudaMallocHost(&c->h_counters, CNT_NUM * sizeof(uint32_t)) != cudaSuccess) { delete c; return -1; }
   if (cudaMalloc(&c->counters.p, CNT_NUM * sizeof(uint32_t)) != cudaSuccess) { delete c; return -1; }
   c->counters.cap = CNT_NUM * sizeof(uint32_t);
@@ -674,6 +712,7 @@ void gtsb_destroy(gtsb_context *c) {
   if (c == nullptr) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   dist_release(c);
   DevBuf *bufs[] = {&c->vattr, &c->astat, &c->seq_len_in, &c->copy_num_in, &c->root, &c->ctg, &c->dist,
                     &c->std_dev, &c->flags, &c->row_ptr, &c->dst, &c->edist, &c->estd, &c->eflags,
@@ -693,6 +732,9 @@ void gtsb_destroy(gtsb_context *c) {
     if (t->b) cudaEventDestroy(t->b);
   }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t e : {c->ev_order, c->ev_vertices, c->ev_records})
+    if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -730,28 +772,31 @@ int gtsb_set_vertices_host(gtsb_context *c, uint64_t V, const uint32_t *seq_len,
   ENSURE(c->seq_len_in, V * 4);
   ENSURE(c->copy_num_in, V * 4);
   ENSURE(c->astat, V * 4);
+  if (copy_stream_follows_main(c) != 0) return -1;
   if (V) {
-    CK(cudaMemcpyAsync(c->seq_len_in.p, seq_len, V * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->copy_num_in.p, copy_num, V * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->astat.p, astat, V * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->seq_len_in.p, seq_len, V * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->copy_num_in.p, copy_num, V * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->astat.p, astat, V * 4, cudaMemcpyHostToDevice, c->copy_stream));
   }
-  return vertices_common(c, V);
+  return vertices_common(c, V, c->copy_stream);
 }
 
 int gtsb_set_vertices_device(gtsb_context *c, uint64_t V, const uint32_t *seq_len, const float *astat,
                              const float *copy_num) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (c->vertices_pending) CK(cudaStreamSynchronize(c->copy_stream));
   adopt(c->seq_len_in, seq_len);
   adopt(c->copy_num_in, copy_num);
   adopt(c->astat, astat);
-  return vertices_common(c, V);
+  return vertices_common(c, V, c->stream);
 }
 
 int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, const uint32_t *ctg,
                           const int32_t *dist, const float *std_dev, const uint8_t *flags) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (await_records(c) != 0) return -1;      // an earlier late copy into the same buffers
   DevBuf *bs[] = {&c->root, &c->ctg, &c->dist, &c->std_dev, &c->flags};
   for (DevBuf *b : bs)
     if (!b->owned) *b = DevBuf();
@@ -797,9 +842,13 @@ int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line
                                                                         c->root.as<uint32_t>());
     c->stats.kernel_launches++;
     CK(cudaMemcpyAsync(c->ctg.p, ctg, R * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->dist.p, dist, R * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->std_dev.p, std_dev, R * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->flags.p, flags, R, cudaMemcpyHostToDevice, c->stream));
+    // first needed by k2_partition: the line starts and the classification run under this copy
+    if (copy_stream_follows_main(c) != 0) return -1;
+    CK(cudaMemcpyAsync(c->std_dev.p, std_dev, R * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->flags.p, flags, R, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->dist.p, dist, R * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_records, c->copy_stream));
+    c->records_pending = true;
   }
   c->R = R;
   c->have_records = true;
@@ -811,6 +860,10 @@ int gtsb_set_records_device(gtsb_context *c, uint64_t R, const uint32_t *root, c
                             const int32_t *dist, const float *std_dev, const uint8_t *flags) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (c->records_pending) {                  // a late copy may still write the buffers adopt() frees
+    CK(cudaStreamSynchronize(c->copy_stream));
+    c->records_pending = false;
+  }
   adopt(c->root, root);
   adopt(c->ctg, ctg);
   adopt(c->dist, dist);
@@ -828,6 +881,7 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
                         const float *copy_num, const uint8_t *vstate, const uint8_t *estate) {
   if (c == nullptr) return -1;
   if (gtsb_set_vertices_host(c, V, seq_len, astat, copy_num) != 0) return -1;
+  if (await_vertices(c) != 0 || await_records(c) != 0) return -1;
   if (E >= 0xFFFFFFF0ull) return fail(c, "too many edges");
   cudaStream_t s = c->stream;
   ENSURE(c->row_ptr, (V + 1) * 4);
@@ -912,6 +966,7 @@ uint64_t gtsb_nof_edges(const gtsb_context *c) { return c ? c->E : 0; }
 int gtsb_get_vertex_states(gtsb_context *c, uint8_t *vstate) {
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
+  if (await_vertices(c) != 0) return -1;
   if (c->V && vstate) CK(cudaMemcpyAsync(vstate, c->vstate.p, c->V, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;

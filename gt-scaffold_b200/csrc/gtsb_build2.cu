@@ -719,12 +719,17 @@ int launch_b2_apply_corrections(const Build2Args &a, const uint4 *list, uint32_t
   return 1;
 }
 
-int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
+// classification and the two scans: need the line starts and the ctg column only
+int launch_build2_classify(const Build2Args &a, cudaStream_t s) {
   int n = launch_b2_classify(a, s);
   exclusive_scan<uint32_t>(a.cnt_in, a.V, a.bptr, a.scan_scratch, s);
   exclusive_scan<uint32_t>(a.nown, a.V, a.k0, a.scan_scratch, s);
-  n += 6;
-  n += launch_b2_partition(a, s);
+  return n + 6;
+}
+
+// mail and rows: need every record column
+int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
+  int n = launch_b2_partition(a, s);
   n += launch_b2_deliver_resolve(a, s);
   KernelTimer t_("k2_corrections", s);
   k2_corrections<<<64, 128, 0, s>>>(a, a.corrections, a.counters + CNT_CORRECTIONS, 0u);

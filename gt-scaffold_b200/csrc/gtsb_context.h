@@ -78,6 +78,13 @@ struct gtsb_context {
   std::vector<double> prof_ms;
   std::vector<uint32_t> prof_calls;
 
+  // host inputs that are needed late (vertex attributes: first by the filter; dist/std_dev/flags
+  // of line-shaped records: first by k2_partition) are copied on a second stream, so that the
+  // kernels before that point overlap the copy; a consumer waits for the event first
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_order = nullptr, ev_vertices = nullptr, ev_records = nullptr;
+  bool vertices_pending = false, records_pending = false;
+
   // rank-partitioned graph (gtsb_dist.cu); world == 1: single device
   int rank = 0, world = 1;
   void *dstate = nullptr;            // DistState of gtsb_dist.cu
@@ -101,6 +108,8 @@ int get_ambig(gtsb_context *c, float pcutoff);
 int ensure_windows(gtsb_context *c, uint64_t V, uint64_t max_edges);
 int ensure_rows(gtsb_context *c, uint64_t R);
 int ensure_filter_buffers(gtsb_context *c, uint64_t Vg, uint64_t E, gtsb::FilterArgs &a);
+int await_vertices(gtsb_context *c);      // the main stream waits for late copies (no host sync)
+int await_records(gtsb_context *c);
 
 struct ProfScope {                      // routes KernelTimer to the context's profiler while alive
   gtsb_context *c;

@@ -538,6 +538,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   }
   // nobody may overwrite a receive buffer its owner is still reading (previous step): the classify
   // exchange above already ordered every rank behind every rank's previous step
+  if (await_records(c) != 0) return -1;          // dist/std_dev/flags may still be on their way (copy stream)
   c->stats.kernel_launches += launch_b2_partition(a, s);
   {
     // all mail has landed once every rank's partition kernel is complete: a stream-ordered barrier
@@ -624,6 +625,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   std::vector<uint32_t> all;
   FilterArgs a{};
   int rc = [&]() -> int {
+    if (await_vertices(c) != 0) return -1;
     if (ensure_filter_buffers(c, Vg, c->E, a) != 0) return -1;
     CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
     CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (Vg + 1) * 4, s));

@@ -97,7 +97,8 @@ struct Build2Args {
   uint8_t *eflags;
 };
 int launch_build2_lines(const Build2Args &a, cudaStream_t s);
-int launch_build2_rows(const Build2Args &a, cudaStream_t s);
+int launch_build2_classify(const Build2Args &a, cudaStream_t s);   // needs line starts + ctg only
+int launch_build2_rows(const Build2Args &a, cudaStream_t s);       // needs every record column
 // the same passes one at a time, for the rank-partitioned build (gtsb_dist.cu)
 int launch_b2_head_counts(const Build2Args &a, cudaStream_t s);     // -> tile_off[ntiles] = number of lines
 int launch_b2_head_write(const Build2Args &a, cudaStream_t s);

@@ -208,6 +208,17 @@ def test_line_shaped_input_and_states_by_eid(pkg, synth):
     _cmp(rb, ra, "line-shaped input")
     assert np.array_equal(b.edge_states(), ra["estate"])
     assert np.array_equal(a.edge_states(), ra["estate"])
+    # records before vertices, twice in a row on one context (what bench.py's e2e leg does: the
+    # late columns and the vertex attributes travel on the copy stream under the first kernels)
+    for rep in range(2):
+        b.set_record_lines(line_root, line_start, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+        b.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+        b.pipeline()
+        assert np.array_equal(b.edge_states(), ra["estate"]) and np.array_equal(b.vstate(), ra["vstate"])
+    # and a flat record upload right after a line-shaped one
+    b.set_records(inp.root, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+    b.pipeline()
+    _cmp(b.result(), ra, "flat after line-shaped")
 
 
 def test_full_size_properties_c3(pkg, synth):
