@@ -28,6 +28,12 @@
 // Anything outside the fast path's preconditions -- a root on several lines, a
 // link listed only on the LATER line, very long lines, oversized segments --
 // raises a flag and gtsb_build reruns the general path of gtsb_build.cu.
+//
+// The same kernels build one rank's rows of a graph partitioned over the GPUs
+// of a box (gtsb_dist.cu): positions are then global (pos_base = the rank's
+// first position), creator ranks start at k_base, k2_classify counts mail per
+// destination RANK, k2_partition stores it into the owning rank's receive
+// buffers, and k2_deliver reads what the ranks sent here.
 #include "gtsb_common.cuh"
 #include "gtsb_scan.cuh"
 #include "gtsb_kernels.h"
