@@ -16,9 +16,15 @@ KEYS = ("src", "dst", "dist", "std_dev", "flags", "row_ptr", "adj_eid", "vstate"
 DEFAULT = dict(cn_cut=0.3, a_cut=20.0, use_cn=True, pc=0.01, cnc=1.5, oc=400)
 
 
+def _bits(a):
+    """floats are compared bit for bit (NaN == NaN, -0.0 != 0.0)"""
+    a = np.asarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
 def _cmp(got, exp, what=""):
     for k in KEYS:
-        if not np.array_equal(got[k], exp[k]):
+        if not np.array_equal(_bits(got[k]), _bits(exp[k])):
             bad = np.nonzero(np.asarray(got[k]) != np.asarray(exp[k]))[0] if got[k].shape == exp[k].shape else []
             raise AssertionError(f"{what}: {k} differs at {len(bad)} positions, first {bad[:8]}; "
                                  f"got {np.asarray(got[k])[bad[:8]]} exp {np.asarray(exp[k])[bad[:8]]}")
@@ -272,3 +278,28 @@ def test_full_size_properties_c3(pkg, synth):
     assert np.array_equal(vs, vs2)
     del t
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_special_values(pkg, synth, seed):
+    """NaN / inf / zero / denormal std_dev and copy numbers, NaN a-statistics, extreme
+    distances and contig lengths: the float compares and the i64 interval arithmetic must
+    fall the reference's way (algorithms.c:174-246, parser.c:362)."""
+    rng = np.random.default_rng(100 + seed)
+    inp = synth.tiny_dense(14, 70, 6000 + seed)
+    sd = inp.std_dev.copy()
+    specials = np.array([np.nan, np.inf, 0.0, -0.0, 1e-40, 3.4e38, -1.0], np.float32)
+    idx = rng.choice(len(sd), size=len(sd) // 3, replace=False)
+    sd[idx] = specials[rng.integers(0, len(specials), len(idx))]
+    dist = inp.dist.copy()
+    idx = rng.choice(len(dist), size=len(dist) // 5, replace=False)
+    dist[idx] = rng.choice(np.array([-2**31 + 1, 2**31 - 1, 0, -1, 2**30], np.int64), len(idx)).astype(np.int32)
+    cn = inp.copy_num.copy()
+    cn[rng.integers(0, len(cn), 4)] = np.array([np.nan, np.inf, -1.0, 0.0], np.float32)
+    astat = inp.astat.copy()
+    astat[rng.integers(0, len(astat), 2)] = np.array([np.nan, -np.inf], np.float32)
+    seq_len = inp.seq_len.copy()
+    seq_len[rng.integers(0, len(seq_len), 3)] = np.array([2**31 - 1, 1, 2**30], np.uint32)
+    bad = synth.ScaffoldInput(seq_len, astat, cn, inp.root, inp.ctg, dist, sd, inp.num_pairs, inp.flags)
+    _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)])
+    _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)], force_general=True)
