@@ -681,17 +681,24 @@ __global__ void __launch_bounds__(128) k4_fire_redo(FilterArgs a, const uint32_t
         if (ok0 && !(pt[j] <= v_id)) ok_mask |= 1u << k;      // U(e), see slot_unmarked
       }
     }
-    long long mx[2] = {0, 0};
-    for (uint32_t x = 0; x + 1 < d; x++) {
+    // only "some pair overlaps by more than ocutoff" matters per direction: stop at the first hit
+    uint32_t gb = 0;
+    for (uint32_t x = 0; x + 1 < d && gb != 3u; x++) {
       if (!((ok_mask >> x) & 1u)) continue;
       const uint32_t sx = (sense_mask >> x) & 1u;
-      for (uint32_t y = x + 1; y < d; y++) {
-        if (!((ok_mask >> y) & 1u) || ((sense_mask >> y) & 1u) != sx) continue;
-        const long long ov = interval_overlap(dist[x], len[x], dist[y], len[y]);
-        if (ov > mx[sx]) mx[sx] = ov;
+      if ((gb >> sx) & 1u) continue;
+      // partners: later slots of the same direction that are still unmarked
+      uint32_t cand = ok_mask & (sx ? sense_mask : ~sense_mask) & (x == 31u ? 0u : (0xFFFFFFFFu << (x + 1u)));
+      if (d < 32u) cand &= (1u << d) - 1u;
+      while (cand) {
+        const uint32_t y = (uint32_t) __ffs(cand) - 1u;
+        cand &= cand - 1u;
+        if (interval_overlap(dist[x], len[x], dist[y], len[y]) > a.ocutoff) {
+          gb |= 1u << sx;
+          break;
+        }
       }
     }
-    const uint32_t gb = (mx[0] > a.ocutoff ? 1u : 0u) | (mx[1] > a.ocutoff ? 2u : 0u);
     a.gbits[p] = (uint8_t) gb;
     a.fstat[p] = (uint8_t) (FS_DECIDED_ALL & ~(gb << 2));
   }
