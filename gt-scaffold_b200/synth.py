@@ -277,6 +277,33 @@ def tiny_dense(V: int, n_pairs: int, seed: int, *, repeats: float = 0.12,
 # random streams differ from the numpy generator (and between devices); parity
 # tests always feed ONE set of arrays to both the CUDA path and the oracle.
 
+def special_values(seed: int, V: int = 14, n_pairs: int = 70) -> ScaffoldInput:
+    """tiny_dense with the values the float compares and the i64 interval
+    arithmetic are most likely to get wrong: NaN / inf / signed zero / denormal /
+    negative std_dev, NaN and infinite copy numbers and a-statistics, distances
+    at the int32 limits, contig lengths up to 2^31-1 (algorithms.c:174-246,
+    parser.c:362)."""
+    rng = np.random.default_rng(100 + seed)
+    inp = tiny_dense(V, n_pairs, 6000 + seed)
+    sd = inp.std_dev.copy()
+    specials = np.array([np.nan, np.inf, 0.0, -0.0, 1e-40, 3.4e38, -1.0], np.float32)
+    idx = rng.choice(len(sd), size=len(sd) // 3, replace=False)
+    sd[idx] = specials[rng.integers(0, len(specials), len(idx))]
+    dist = inp.dist.copy()
+    idx = rng.choice(len(dist), size=len(dist) // 5, replace=False)
+    dist[idx] = rng.choice(np.array([-2**31 + 1, 2**31 - 1, 0, -1, 2**30], np.int64),
+                           len(idx)).astype(np.int32)
+    cn = inp.copy_num.copy()
+    cn[rng.integers(0, len(cn), 4)] = np.array([np.nan, np.inf, -1.0, 0.0], np.float32)
+    astat = inp.astat.copy()
+    astat[rng.integers(0, len(astat), 2)] = np.array([np.nan, -np.inf], np.float32)
+    seq_len = inp.seq_len.copy()
+    seq_len[rng.integers(0, len(seq_len), 3)] = np.array([2**31 - 1, 1, 2**30], np.uint32)
+    return ScaffoldInput(seq_len, astat, cn, inp.root, inp.ctg, dist, sd, inp.num_pairs,
+                         inp.flags, name="special_values",
+                         meta={"V": V, "records": len(dist), "seed": seed})
+
+
 def generate_torch(name: str = "c3_human", V: int | None = None, *, device="cuda",
                    mean_pairs: float | None = None, seed: int | None = None,
                    line_order: str = "shuffled", one_sided_frac: float = 0.0,

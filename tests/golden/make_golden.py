@@ -13,7 +13,9 @@ diff_*.npz     differential vectors: adversarial small graphs
                (synth.tiny_dense) pushed through the COMPILED REFERENCE
                (build -> mark_repeats -> filter); inputs and every output array.
                They pin the pairwise filter logic, which the reference's own
-               goldens never exercise.
+               goldens never exercise.  diff_g..i carry
+               NaN / inf / denormal std_dev, NaN copy numbers and a-statistics
+               and distances at the int32 limits (synth.special_values).
 """
 import importlib
 import os
@@ -42,6 +44,12 @@ DIFF_CASES = [
     ("diff_d", 14, 60, 104, 0.01, 1.5, -1, 0.3, 20.0, 0),
     ("diff_e", 40, 300, 105, 0.2, 2.5, 50, 0.5, 19.5, 1),
     ("diff_f", 200, 900, 106, 0.01, 1.5, 400, 0.3, 20.0, 1),
+]
+# the same through synth.special_values (NaN / inf / denormal std_dev, extreme distances)
+SPECIAL_CASES = [
+    ("diff_g", 14, 70, 0, 0.01, 1.5, 400, 0.3, 20.0, 1),
+    ("diff_h", 24, 150, 1, 0.05, 2.0, 100, 0.5, 19.5, 1),
+    ("diff_i", 16, 90, 2, 0.01, 1.5, -5, 0.3, 20.0, 0),
 ]
 
 
@@ -81,8 +89,9 @@ def make_c1():
 
 
 def make_diff():
-    for (name, V, pairs, seed, pc, cnc, oc, cn_cut, a_cut, use_cn) in DIFF_CASES:
-        inp = synth.tiny_dense(V, pairs, seed)
+    cases = [(c, synth.tiny_dense(c[1], c[2], c[3])) for c in DIFF_CASES] + \
+            [(c, synth.special_values(c[3], V=c[1], n_pairs=c[2])) for c in SPECIAL_CASES]
+    for (name, V, pairs, seed, pc, cnc, oc, cn_cut, a_cut, use_cn), inp in cases:
         g = O.RefGraph.build(inp)
         built = g.result()
         g.mark_repeats(cn_cut, a_cut, use_copy_num=bool(use_cn))

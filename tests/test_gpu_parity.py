@@ -128,7 +128,7 @@ def test_committed_differential_vectors(pkg, synth, path):
     r = g.result()
     for k, zk in [("src", "e_src"), ("dst", "e_dst"), ("dist", "e_dist"), ("std_dev", "e_std"),
                   ("flags", "e_flags"), ("row_ptr", "row_ptr"), ("adj_eid", "adj_eid")]:
-        assert np.array_equal(r[k], z[zk]), k
+        assert np.array_equal(_bits(r[k]), _bits(z[zk])), k
     g.mark_repeats(float(cn_cut), float(a_cut), bool(use_cn))
     r = g.result()
     assert np.array_equal(r["vstate"], z["rep_vstate"]) and np.array_equal(r["estate"], z["rep_estate"])
@@ -285,21 +285,6 @@ def test_special_values(pkg, synth, seed):
     """NaN / inf / zero / denormal std_dev and copy numbers, NaN a-statistics, extreme
     distances and contig lengths: the float compares and the i64 interval arithmetic must
     fall the reference's way (algorithms.c:174-246, parser.c:362)."""
-    rng = np.random.default_rng(100 + seed)
-    inp = synth.tiny_dense(14, 70, 6000 + seed)
-    sd = inp.std_dev.copy()
-    specials = np.array([np.nan, np.inf, 0.0, -0.0, 1e-40, 3.4e38, -1.0], np.float32)
-    idx = rng.choice(len(sd), size=len(sd) // 3, replace=False)
-    sd[idx] = specials[rng.integers(0, len(specials), len(idx))]
-    dist = inp.dist.copy()
-    idx = rng.choice(len(dist), size=len(dist) // 5, replace=False)
-    dist[idx] = rng.choice(np.array([-2**31 + 1, 2**31 - 1, 0, -1, 2**30], np.int64), len(idx)).astype(np.int32)
-    cn = inp.copy_num.copy()
-    cn[rng.integers(0, len(cn), 4)] = np.array([np.nan, np.inf, -1.0, 0.0], np.float32)
-    astat = inp.astat.copy()
-    astat[rng.integers(0, len(astat), 2)] = np.array([np.nan, -np.inf], np.float32)
-    seq_len = inp.seq_len.copy()
-    seq_len[rng.integers(0, len(seq_len), 3)] = np.array([2**31 - 1, 1, 2**30], np.uint32)
-    bad = synth.ScaffoldInput(seq_len, astat, cn, inp.root, inp.ctg, dist, sd, inp.num_pairs, inp.flags)
+    bad = synth.special_values(seed)
     _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)])
     _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)], force_general=True)
