@@ -35,6 +35,7 @@ EXPORTS = [
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
     "gtsb_set_record_lines_host", "gtsb_get_edge_states",
+    "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records",
 ]
 
 
@@ -211,6 +212,37 @@ class ScaffoldGraphB200:
              np.ascontiguousarray(std_dev, np.float32), np.ascontiguousarray(flags, np.uint8)]
         self._ck(self.L.gtsb_set_record_lines_host(self.h, a[0].shape[0], _ptr(a[0]), _ptr(a[1]), a[2].shape[0],
                                                    *[_ptr(x) for x in a[2:]]))
+
+    # ---- .de text on the device (parser.c:323-388)
+    def set_vertex_names(self, names):
+        """Contig headers in vertex id order (list of bytes): the lookup table of
+        gt_scaffolder_graph_get_vertex."""
+        off = np.zeros(len(names) + 1, np.uint64)
+        if len(names):
+            off[1:] = np.cumsum([len(x) for x in names], dtype=np.uint64)
+        blob = b"".join(names)
+        self._ck(self.L.gtsb_set_vertex_names_host(self.h, C.c_uint64(len(names)), blob, _ptr(off)))
+
+    def parse_de(self, text: bytes):
+        """-> (irregular bits, nof_records).  irregular != 0: the text is outside the canonical
+        spelling, nothing was set, tokenise on the host."""
+        R = C.c_uint64(0)
+        irr = C.c_uint32(0)
+        self._ck(self.L.gtsb_parse_de_host(self.h, text, C.c_uint64(len(text)), C.byref(R), C.byref(irr)))
+        self.R = int(R.value)
+        return int(irr.value), int(R.value)
+
+    def records(self, num_pairs: bool = True):
+        """The records the context holds, file order."""
+        R = self.R
+        rec = dict(root=np.zeros(R, np.uint32), ctg=np.zeros(R, np.uint32), dist=np.zeros(R, np.int32),
+                   std_dev=np.zeros(R, np.float32), flags=np.zeros(R, np.uint8))
+        if num_pairs:
+            rec["num_pairs"] = np.zeros(R, np.uint32)
+        self._ck(self.L.gtsb_get_records(self.h, _ptr(rec["root"]), _ptr(rec["ctg"]), _ptr(rec["dist"]),
+                                         _ptr(rec["std_dev"]), _ptr(rec["flags"]),
+                                         _ptr(rec["num_pairs"]) if num_pairs else None))
+        return rec
 
     def edge_states(self):
         """estate indexed by eid (graph->edges[] order)."""

@@ -724,7 +724,9 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
                     &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line, &c->line_root, &c->line_start,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
-                    &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg};
+                    &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg,
+                    &c->p_names, &c->p_name_off, &c->p_slots, &c->p_flags, &c->p_text, &c->p_chunk_cnt,
+                    &c->p_chunk_off, &c->p_line_end, &c->p_line_cnt, &c->p_line_off, &c->num_pairs};
   for (DevBuf *b : bufs) release(*b);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (Timer *t : {&c->t_build, &c->t_rep, &c->t_filter}) {
@@ -814,6 +816,7 @@ int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, con
   }
   c->R = R;
   c->have_records = true;
+  c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;
 }
@@ -852,6 +855,7 @@ int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line
   }
   c->R = R;
   c->have_records = true;
+  c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;
 }
@@ -871,6 +875,7 @@ int gtsb_set_records_device(gtsb_context *c, uint64_t R, const uint32_t *root, c
   adopt(c->flags, flags);
   c->R = R;
   c->have_records = true;
+  c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;
 }

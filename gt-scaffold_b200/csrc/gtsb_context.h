@@ -67,6 +67,11 @@ struct gtsb_context {
   // filter work
   DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, dirty;
   uint32_t n_big_rows = 0, max_deg = 0;
+  // .de text on the device (gtsb_parse.cu)
+  DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,
+      p_line_cnt, p_line_off, num_pairs;
+  uint64_t names_V = 0, names_mask = 0;
+  bool have_names = false, have_num_pairs = false;
 
   uint32_t *h_counters = nullptr;   // pinned
   gtsb_stats stats{};

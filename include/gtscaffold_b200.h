@@ -90,6 +90,31 @@ int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_e
                         const float *astat, const float *copy_num, const uint8_t *vstate,
                         const uint8_t *estate);
 
+/* ---- .de text on the device: the record loop of gt_scaffolder_parser_read_distances
+   (gt_scaffolder_parser.c:323-388) -- 1024-byte fgets pieces, last character dropped,
+   ' '-separated tokens, "%[^>,],%ld,%ld,%f" records, ';' switching the direction, unknown
+   roots skipping the line and unknown partners the record.  Header -> vertex id is
+   gt_scaffolder_graph_get_vertex (gt_scaffolder_graph.c:187-216) as a device hash table
+   over the headers handed in once: names = the headers of vertex 0..V-1 back to back
+   (no terminators), name_off[V+1] their offsets.
+   gtsb_parse_de_host leaves the records in the context as gtsb_set_records_* would
+   (gtsb_build follows) and keeps their pair counts for gtsb_get_records.  It accepts
+   the canonical spelling of records only (csrc/gtsb_parse_core.h); for any other text
+   it returns 0 with *irregular != 0 (GTSB_IRR_* bits) and NO records set -- the caller
+   then tokenises on the host with the C library's sscanf, as the reference does. */
+#define GTSB_IRR_NUL      1u   /* NUL byte in the text */
+#define GTSB_IRR_TOKEN    2u   /* "header,..." token that is not a canonical record */
+#define GTSB_IRR_RANGE    4u   /* distance outside int32 / pair count outside uint32 */
+#define GTSB_IRR_FLOAT    8u   /* std_dev the device cannot prove it rounds as strtof does */
+int gtsb_set_vertex_names_host(gtsb_context *ctx, uint64_t nof_vertices, const char *names,
+                               const uint64_t *name_off);
+int gtsb_parse_de_host(gtsb_context *ctx, const char *text, uint64_t text_bytes,
+                       uint64_t *nof_records, uint32_t *irregular);
+/* the records held by the context, file order (NULL pointers are skipped); num_pairs
+   only after gtsb_parse_de_host */
+int gtsb_get_records(gtsb_context *ctx, uint32_t *root, uint32_t *ctg, int32_t *dist,
+                     float *std_dev, uint8_t *flags, uint32_t *num_pairs);
+
 /* ---- the hot path */
 int gtsb_build(gtsb_context *ctx);
 int gtsb_mark_repeats(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff,

@@ -13,15 +13,17 @@
  * removecycles, makescaffold, write_scaffold) reads the `state` fields and
  * adjacency lists this file fills, exactly as it reads the reference's.
  *
- * Host text handling stays host C: FASTA goes
- * through the reference's own gt_scaffolder_parser_count_contigs /
- * _read_contigs, `.de` validation through its _count_distances; the `.de`
- * and `.astat` tokenisers below only turn text into integer records with the
- * same tokenising rules (1024-byte fgets, last character dropped, ' ' tokens,
- * "%[^>,],%ld,%ld,%f" records, ';' switches the direction: parser.c:323-388,
- * algorithms.c:118-149).  All graph work happens on the GPU; there is no CPU
- * fallback -- a missing device or a CUDA error is reported the reference's
- * way (-1 + GtError) or, for the void filter, printed and aborted.
+ * FASTA goes through the reference's own gt_scaffolder_parser_count_contigs /
+ * _read_contigs, `.de` validation through its _count_distances (host C,
+ * SURVEY.md section 2, rows 2-3).  The `.de` record loop (parser.c:323-388:
+ * 1024-byte fgets, last character dropped, ' ' tokens, "%[^>,],%ld,%ld,%f"
+ * records, ';' switches the direction) runs on the device for files in the
+ * canonical spelling (gtsb_parse_de_host); a file the device refuses -- or
+ * every file with GTSB_TOKENISER=host in the environment -- is tokenised by
+ * read_de_records below with the C library's sscanf.  The `.astat` tokeniser
+ * (algorithms.c:118-149) is host C.  All graph work happens on the GPU; there
+ * is no CPU fallback -- a missing device or a CUDA error is reported the
+ * reference's way (-1 + GtError) or, for the void filter, printed and aborted.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -170,6 +172,74 @@ static int read_de_records(const char *filename, const GtScaffolderGraph *graph,
   return 0;
 }
 
+/* `.de` text -> records on the device.  *on_device = false on return 0 means
+   the device refused the text (outside the canonical spelling) and nothing
+   was set; the caller tokenises on the host.  The pair counts come back for
+   GtScaffolderGraphEdge.num_pairs; the other columns stay on the device. */
+static int device_de_records(gtsb_context *c, const char *filename, const GtScaffolderGraph *graph,
+                             B200Records *recs, bool *on_device, GtError *err)
+{
+  FILE *fp = fopen(filename, "rb");
+  char *text = NULL, *names = NULL;
+  uint64_t *name_off = NULL, nof_records = 0, bytes = 0;
+  uint32_t irregular = 0, *pairs = NULL;
+  long size;
+  GtUword i;
+  int had_err = 0;
+
+  *on_device = false;
+  if (fp == NULL) {
+    gt_error_set(err, " can not read distance file %s ", filename);
+    return -1;
+  }
+  if (fseek(fp, 0, SEEK_END) != 0 || (size = ftell(fp)) < 0 || fseek(fp, 0, SEEK_SET) != 0) {
+    fclose(fp);
+    return 0;                                   /* not seekable: host tokeniser */
+  }
+  text = gt_malloc((size_t) size + 1);
+  if (fread(text, 1, (size_t) size, fp) != (size_t) size) {
+    gt_error_set(err, " can not read distance file %s ", filename);
+    had_err = -1;
+  }
+  fclose(fp);
+
+  if (had_err == 0) {
+    name_off = gt_malloc((graph->nof_vertices + 1) * sizeof (*name_off));
+    for (i = 0; i < graph->nof_vertices; i++) {
+      name_off[i] = bytes;
+      bytes += gt_str_length(graph->vertices[i].header_seq);
+    }
+    name_off[graph->nof_vertices] = bytes;
+    names = gt_malloc(bytes + 1);
+    for (i = 0; i < graph->nof_vertices; i++)
+      memcpy(names + name_off[i], gt_str_get(graph->vertices[i].header_seq),
+             name_off[i + 1] - name_off[i]);
+    if (gtsb_set_vertex_names_host(c, graph->nof_vertices, names, name_off) != 0 ||
+        gtsb_parse_de_host(c, text, (uint64_t) size, &nof_records, &irregular) != 0) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      had_err = -1;
+    }
+  }
+  if (had_err == 0 && irregular == 0) {
+    pairs = gt_malloc((nof_records + 1) * sizeof (*pairs));
+    if (gtsb_get_records(c, NULL, NULL, NULL, NULL, NULL, pairs) != 0) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      had_err = -1;
+    } else {
+      recs->num_pairs = gt_malloc((nof_records + 1) * sizeof (*recs->num_pairs));
+      for (bytes = 0; bytes < nof_records; bytes++)
+        recs->num_pairs[bytes] = pairs[bytes];
+      recs->n = recs->cap = nof_records;
+      *on_device = true;
+    }
+  }
+  gt_free(pairs);
+  gt_free(names);
+  gt_free(name_off);
+  gt_free(text);
+  return had_err;
+}
+
 /* ------------------------------------------------------------------ vertices */
 
 typedef struct {
@@ -221,6 +291,7 @@ int gt_scaffolder_graph_new_from_file(GtScaffolderGraph **graph_par,
   GtUword nof_contigs = 0, upper_bound = 0;
   B200Records recs;
   B200Vertices vert;
+  bool on_device = false;
   int had_err;
 
   memset(&recs, 0, sizeof recs);
@@ -252,7 +323,17 @@ int gt_scaffolder_graph_new_from_file(GtScaffolderGraph **graph_par,
     graph->edges = gt_malloc(sizeof (*graph->edges) * upper_bound);
     graph->nof_edges = 0;
     graph->max_nof_edges = upper_bound;
-    had_err = read_de_records(dist_filename, graph, &recs, err);
+    {
+      const char *tokeniser = getenv("GTSB_TOKENISER");
+      gtsb_context *c = b200_context();
+      if (c != NULL && !(tokeniser != NULL && strcmp(tokeniser, "host") == 0))
+        had_err = device_de_records(c, dist_filename, graph, &recs, &on_device, err);
+      if (had_err == 0 && !on_device)
+        had_err = read_de_records(dist_filename, graph, &recs, err);
+      if (had_err == 0 && getenv("GTSB_VERBOSE") != NULL)
+        fprintf(stderr, "gt_scaffolder (B200): %s tokenised on the %s\n", dist_filename,
+                on_device ? "device" : "host");
+    }
   }
   if (had_err == 0)
     had_err = vertices_flatten(graph, &vert, err);
@@ -273,7 +354,8 @@ int gt_scaffolder_graph_new_from_file(GtScaffolderGraph **graph_par,
     if (had_err == 0 &&
         (gtsb_want_win_rec(c, 1) != 0 ||
          gtsb_set_vertices_host(c, V, vert.seq_len, vert.astat, vert.copy_num) != 0 ||
-         gtsb_set_records_host(c, recs.n, recs.root, recs.ctg, recs.dist, recs.std_dev, recs.flags) != 0 ||
+         (!on_device &&
+          gtsb_set_records_host(c, recs.n, recs.root, recs.ctg, recs.dist, recs.std_dev, recs.flags) != 0) ||
          gtsb_build(c) != 0)) {
       gt_error_set(err, "%s", gtsb_error(c));
       had_err = -1;

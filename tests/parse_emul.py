@@ -1,0 +1,64 @@
+"""TEST INFRASTRUCTURE: the `.de` tokeniser's stage functions
+(gt-scaffold_b200/csrc/gtsb_parse_core.h, the bodies of the kernels in
+gtsb_parse.cu) compiled for the host and run as plain loops
+(tests/emul/parse_emul.cpp).  Used by tests/test_parse.py to check the token
+rules against the compiled reference where there is no GPU, and to generate
+the `.de` texts both the emulation and the device path are tested on."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "parse_emul.cpp")
+CORE = os.path.join(HERE, "..", "gt-scaffold_b200", "csrc", "gtsb_parse_core.h")
+OUT = os.path.join(HERE, "emul", "_build", "libparse_emul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        if (not os.path.exists(OUT)
+                or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
+            # -ffp-contract=off: the float rule divides, it must not be fused with anything
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                            "-o", OUT, SRC], check=True)
+        _lib = C.CDLL(OUT)
+        _lib.emul_canonical_float.restype = C.c_uint32
+    return _lib
+
+
+def pack_names(names):
+    """list of bytes (vertex id order) -> (blob, offsets) as the C ABI takes them"""
+    off = np.zeros(len(names) + 1, np.uint64)
+    if names:
+        off[1:] = np.cumsum([len(x) for x in names], dtype=np.uint64)
+    return b"".join(names), off
+
+
+def parse(names, text, order=0):
+    """-> (irregular bits, dict of record arrays or None)"""
+    L = lib()
+    blob, off = pack_names(names)
+    R = C.c_uint64(0)
+    irr = C.c_uint32(0)
+    L.emul_parse_de(C.c_uint64(len(names)), blob, off.ctypes.data_as(C.c_void_p), text,
+                    C.c_uint64(len(text)), C.c_int(order), C.byref(R), C.byref(irr))
+    if irr.value:
+        return irr.value, None
+    n = R.value
+    rec = dict(root=np.zeros(n, np.uint32), ctg=np.zeros(n, np.uint32), dist=np.zeros(n, np.int32),
+               std_dev=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8),
+               num_pairs=np.zeros(n, np.uint32))
+    L.emul_fetch(*[rec[k].ctypes.data_as(C.c_void_p)
+                   for k in ("root", "ctg", "dist", "std_dev", "flags", "num_pairs")])
+    return 0, rec
+
+
+def canonical_float(s: bytes):
+    out = C.c_float(0)
+    r = lib().emul_canonical_float(s, C.c_uint32(len(s)), C.byref(out))
+    return r, out.value

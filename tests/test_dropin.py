@@ -23,8 +23,14 @@ needs_bin = pytest.mark.skipif(not os.path.exists(B200_TESTX),
                                reason="integration/_build/test_b200.x not built (needs /root/reference)")
 
 
-def _run(exe, args, cwd):
-    return subprocess.run([exe] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+def _run(exe, args, cwd, tokeniser=None):
+    """tokeniser: None = the binding's default (`.de` records tokenised on the device),
+    "host" = GTSB_TOKENISER=host (read_de_records in the binding)"""
+    env = dict(os.environ, GTSB_VERBOSE="1")
+    env.pop("GTSB_TOKENISER", None)
+    if tokeniser is not None:
+        env["GTSB_TOKENISER"] = tokeniser
+    return subprocess.run([exe] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
 
 
 @needs_bin
@@ -41,9 +47,10 @@ def test_binding_refuses_without_a_device(tmp_path):
 
 @pytest.mark.gpu
 @needs_bin
-def test_config1_goldens_through_the_binding(tmp_path):
+@pytest.mark.parametrize("tokeniser", [None, "host"])
+def test_config1_goldens_through_the_binding(tmp_path, tokeniser):
     r = _run(B200_TESTX, ["scaffold", f"{C1}/contigs.fa", f"{C1}/libPE.de", f"{C1}/libPE.astat", "false"],
-             tmp_path)
+             tmp_path, tokeniser)
     assert r.returncode == 0, r.stderr.decode()
     for s in STAGES:
         got = (tmp_path / f"gt_scaffolder_algorithms_test_{s}.dot").read_bytes()
@@ -56,10 +63,10 @@ def test_config1_goldens_through_the_binding(tmp_path):
 @pytest.mark.gpu
 @needs_bin
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("case", ["tiny0", "tiny1", "tiny2", "c2_small", "c2_mirror"])
+@pytest.mark.parametrize("case", ["tiny0", "tiny1", "tiny2", "tiny3_exponent", "c2_small", "c2_mirror"])
 def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth):
     if case.startswith("tiny"):
-        k = int(case[4:])
+        k = int(case[4])
         inp = synth.tiny_dense(12 + 3 * k, 40 + 10 * k, 8100 + k)
     elif case == "c2_small":
         inp = synth.generate("c2_bacterial", V=4000)
@@ -70,17 +77,29 @@ def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth):
     data = tmp_path / "in"
     data.mkdir()
     fa, de, astat = O.write_text_inputs(inp, str(data))
+    irregular = case.endswith("exponent")
+    if irregular:
+        # a spelling sscanf reads and the device tokeniser refuses: the binding must notice
+        # and tokenise this file on the host
+        text = open(de, "rb").read()
+        assert b",40 " in text
+        open(de, "wb").write(text.replace(b",40 ", b",4e1 "))
     outs = {}
-    for name, exe in (("ref", O.REF_TESTX), ("b200", B200_TESTX)):
+    for name, exe, tok in (("ref", O.REF_TESTX, None), ("b200", B200_TESTX, None),
+                           ("b200_host_tokeniser", B200_TESTX, "host")):
         d = tmp_path / name
         d.mkdir()
-        r = _run(exe, ["scaffold", fa, de, astat, "false"], d)
+        r = _run(exe, ["scaffold", fa, de, astat, "false"], d, tok)
         assert r.returncode == 0, (name, r.stderr.decode()[-500:])
+        if name != "ref":
+            where = b"host" if (tok == "host" or irregular) else b"device"
+            assert b"tokenised on the " + where in r.stderr, (name, r.stderr.decode()[-500:])
         outs[name] = d
     changed = False
     for f in OUTPUTS:
-        a, b = (outs["ref"] / f).read_bytes(), (outs["b200"] / f).read_bytes()
-        assert a == b, f"{case}: {f} differs"
+        a = (outs["ref"] / f).read_bytes()
+        for name in ("b200", "b200_host_tokeniser"):
+            assert a == (outs[name] / f).read_bytes(), f"{case}: {f} differs ({name})"
     a = (outs["ref"] / OUTPUTS[0]).read_bytes()
     b = (outs["ref"] / OUTPUTS[1]).read_bytes()
     changed = a != b
