@@ -321,18 +321,20 @@ def best_oracle():
 def write_text_inputs(inp, directory, write_seq=True):
     """ScaffoldInput -> (fasta, de, astat) files the reference's own parser can
     read.  Headers 'c%010d' sort in id order.  Lines longer than the
-    reference's 1024-byte buffer are the caller's problem (parser.c:30,323)."""
+    reference's 1024-byte buffer are the caller's problem (parser.c:30,323).
+    write_seq=False: the .de only."""
     V = inp.nof_vertices
     fa = os.path.join(directory, "contigs.fa")
     de = os.path.join(directory, "lib.de")
     astat = os.path.join(directory, "lib.astat")
-    with open(fa, "w") as f:
-        for v in range(V):
-            f.write(">c%010d %d 0\n" % (v, inp.seq_len[v]))
-            f.write("A" * int(inp.seq_len[v]) + "\n")
-    with open(astat, "w") as f:
-        for v in range(V):
-            f.write("c%010d\t%d\t0\t0\t%.9g\t%.9g\n" % (v, inp.seq_len[v], inp.copy_num[v], inp.astat[v]))
+    if write_seq:
+        with open(fa, "w") as f:
+            for v in range(V):
+                f.write(">c%010d %d 0\n" % (v, inp.seq_len[v]))
+                f.write("A" * int(inp.seq_len[v]) + "\n")
+        with open(astat, "w") as f:
+            for v in range(V):
+                f.write("c%010d\t%d\t0\t0\t%.9g\t%.9g\n" % (v, inp.seq_len[v], inp.copy_num[v], inp.astat[v]))
     with open(de, "w") as f:
         i, R = 0, inp.nof_records
         while i < R:
