@@ -98,6 +98,9 @@ def load_library():
     L.gtsb_get_edges.argtypes = [vp, C.POINTER(u64)] + [vp] * 7
     L.gtsb_set_record_lines_host.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
     L.gtsb_get_edge_states.argtypes = [vp, vp]
+    L.gtsb_set_vertex_names_host.argtypes = [vp, u64, C.c_char_p, vp]
+    L.gtsb_parse_de_host.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
+    L.gtsb_get_records.argtypes = [vp] * 7
     _lib = L
     return L
 

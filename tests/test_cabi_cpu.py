@@ -28,6 +28,13 @@ def test_library_exports_every_declared_symbol(pkg):
     assert sorted(pkg.api.EXPORTS) == names
 
 
+def test_every_entry_point_has_ctypes_prototypes(pkg):
+    """a pointer passed without argtypes is cut to a C int"""
+    L = pkg.load_library()
+    for n in pkg.api.EXPORTS:
+        assert getattr(L, n).argtypes is not None, n
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device the product path must refuse, not degrade."""
     import torch
