@@ -35,7 +35,7 @@ EXPORTS = [
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
     "gtsb_set_record_lines_host", "gtsb_get_edge_states",
-    "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records",
+    "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     L.gtsb_set_vertex_names_host.argtypes = [vp, u64, C.c_char_p, vp]
     L.gtsb_parse_de_host.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.gtsb_get_records.argtypes = [vp] * 7
+    L.gtsb_parse_astat_host.argtypes = [vp, C.c_char_p, u64, vp, vp, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -234,6 +235,16 @@ class ScaffoldGraphB200:
         self._ck(self.L.gtsb_parse_de_host(self.h, text, C.c_uint64(len(text)), C.byref(R), C.byref(irr)))
         self.R = int(R.value)
         return int(irr.value), int(R.value)
+
+    def parse_astat(self, text: bytes, astat, copy_num):
+        """-> (irregular bits, astat, copy_num): copies of the inputs with the .astat text applied
+        (algorithms.c:118-149); irregular != 0: untouched, read the file on the host."""
+        a = np.array(astat, np.float32)
+        cn = np.array(copy_num, np.float32)
+        irr = C.c_uint32(0)
+        self._ck(self.L.gtsb_parse_astat_host(self.h, text, C.c_uint64(len(text)), _ptr(a), _ptr(cn),
+                                              C.byref(irr)))
+        return int(irr.value), a, cn
 
     def records(self, num_pairs: bool = True):
         """The records the context holds, file order."""

@@ -726,7 +726,8 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
                     &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg,
                     &c->p_names, &c->p_name_off, &c->p_slots, &c->p_flags, &c->p_text, &c->p_chunk_cnt,
-                    &c->p_chunk_off, &c->p_line_end, &c->p_line_cnt, &c->p_line_off, &c->num_pairs};
+                    &c->p_chunk_off, &c->p_line_end, &c->p_line_cnt, &c->p_line_off, &c->num_pairs,
+                    &c->p_last, &c->p_astat, &c->p_copy_num};
   for (DevBuf *b : bufs) release(*b);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (Timer *t : {&c->t_build, &c->t_rep, &c->t_filter}) {

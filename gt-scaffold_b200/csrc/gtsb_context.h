@@ -69,9 +69,9 @@ struct gtsb_context {
   uint32_t n_big_rows = 0, max_deg = 0;
   // .de text on the device (gtsb_parse.cu)
   DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,
-      p_line_cnt, p_line_off, num_pairs;
+      p_line_cnt, p_line_off, num_pairs, p_last, p_astat, p_copy_num;
   uint64_t names_V = 0, names_mask = 0;
-  bool have_names = false, have_num_pairs = false;
+  bool have_names = false, names_dup = false, have_num_pairs = false;
 
   uint32_t *h_counters = nullptr;   // pinned
   gtsb_stats stats{};

@@ -9,6 +9,9 @@
 //   kp_walk<false>    one thread per physical line: number of records
 //   exclusive_scan    first record index of every line
 //   kp_walk<true>     the same walk, records written in file order
+// and, for `.astat` text (algorithms.c:118-149), on the same line index
+//   kp_astat<false>   one thread per line: per contig, the offset of the last line naming it
+//   kp_astat<true>    that line writes the contig's a-statistic and copy number
 //
 // The walk is a byte loop per thread over its own line; neighbouring threads hold neighbouring
 // lines, so a warp's loads fall into one window of a few KB that L1 keeps.
@@ -57,6 +60,15 @@ __global__ void __launch_bounds__(128) kp_walk(const char *__restrict__ text, co
   }
 }
 
+template <bool APPLY>
+__global__ void __launch_bounds__(128) kp_astat(const char *__restrict__ text, const uint64_t *__restrict__ line_end,
+                                                uint64_t nlines, NameTable t, uint64_t *last, float *astat,
+                                                float *copy_num, uint32_t *irregular) {
+  const uint64_t l = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+  walk_astat_line<APPLY>(text, l ? line_end[l - 1] : 0, line_end[l], t, last, astat, copy_num, irregular);
+}
+
 inline uint32_t blocks_for(uint64_t n, uint32_t threads) { return (uint32_t) ((n + threads - 1) / threads); }
 
 }  // namespace gtsbparse
@@ -96,43 +108,30 @@ int gtsb_set_vertex_names_host(gtsb_context *c, uint64_t V, const char *names, c
   CK(cudaMemcpyAsync(&irregular, c->p_flags.p, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
-  if (irregular & IRR_DUP_NAME)
-    return fail(c, "gtsb_set_vertex_names_host: two contigs carry the same header");
+  // two contigs with one header: which of them bsearch finds is the C library's business, the
+  // texts of this graph are left to the host (every parse call reports GTSB_IRR_DUP_NAME)
+  c->names_dup = (irregular & IRR_DUP_NAME) != 0;
   c->names_V = V;
   c->have_names = true;
   return 0;
 }
 
-int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *nof_records,
-                       uint32_t *irregular_out) {
-  if (c == nullptr) return -1;
-  CK(cudaSetDevice(c->device));
-  if (!c->have_names) return fail(c, "gtsb_parse_de_host: vertex names not set");
-  if (nof_records == nullptr || irregular_out == nullptr || (n && text == nullptr))
-    return fail(c, "gtsb_parse_de_host: null argument");
-  if (c->world > 1) return fail(c, "gtsb_parse_de_host: single-device contexts only");
-  // line and record counts are 32-bit sums over the text: every line and every record takes
-  // a byte at least, so below 4 GiB none of them can wrap
-  if (n >= (1ull << 32)) return fail(c, "gtsb_parse_de_host: text of 4 GiB or more");
-  if (await_records(c) != 0) return -1;
-  ProfScope prof(c);
-  cudaStream_t s = c->stream;
-  *nof_records = 0;
-  *irregular_out = 0;
-  c->have_records = false;
-  c->have_graph = false;
+}  // extern "C"
 
+namespace gtsbparse {
+
+// text -> device, physical lines indexed: c->p_line_end[l] = offset one past line l
+static int index_lines(gtsb_context *c, const char *text, uint64_t n, uint64_t *nlines_out) {
+  cudaStream_t s = c->stream;
   const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
   ENSURE(c->p_text, n + 8);
   ENSURE(c->p_chunk_cnt, nchunks + 1);
   ENSURE(c->p_chunk_off, (nchunks + 2) * 4);
-  ENSURE(c->scan_scratch, scan_scratch_elems(nchunks > c->R ? nchunks : c->R) * 4);
+  ENSURE(c->scan_scratch, scan_scratch_elems(nchunks) * 4);
   uint32_t *flags = c->p_flags.as<uint32_t>();
   CK(cudaMemsetAsync(flags, 0, 16, s));
   if (n) CK(cudaMemcpyAsync(c->p_text.p, text, n, cudaMemcpyHostToDevice, s));
   const char *d_text = c->p_text.as<char>();
-
-  // physical lines
   uint32_t newlines = 0;
   if (nchunks) {
     {
@@ -148,11 +147,7 @@ int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *
   }
   const bool open_end = n != 0 && text[n - 1] != '\n';       // last line without '\n'
   const uint64_t nlines = (uint64_t) newlines + (open_end ? 1 : 0);
-  if (nlines >= 0xFFFFFFF0ull) return fail(c, "gtsb_parse_de_host: too many lines");
   ENSURE(c->p_line_end, (nlines + 1) * 8);
-  ENSURE(c->p_line_cnt, (nlines + 1) * 4);
-  ENSURE(c->p_line_off, (nlines + 2) * 4);
-  ENSURE(c->scan_scratch, scan_scratch_elems(nlines > nchunks ? nlines : nchunks) * 4);
   uint64_t *line_end = c->p_line_end.as<uint64_t>();
   if (newlines) {
     GTSB_TIMED("kp_line_ends", s);
@@ -161,6 +156,49 @@ int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *
     c->stats.kernel_launches++;
   }
   if (open_end) CK(cudaMemcpyAsync(line_end + newlines, &n, 8, cudaMemcpyHostToDevice, s));
+  *nlines_out = nlines;
+  return 0;
+}
+
+static int parse_preamble(gtsb_context *c, const char *what, const char *text, uint64_t n) {
+  if (!c->have_names) return fail(c, "%s: vertex names not set", what);
+  if (n && text == nullptr) return fail(c, "%s: null argument", what);
+  if (c->world > 1) return fail(c, "%s: single-device contexts only", what);
+  // line and record counts are 32-bit sums over the text: every line and every record takes
+  // a byte at least, so below 4 GiB none of them can wrap
+  if (n >= (1ull << 32)) return fail(c, "%s: text of 4 GiB or more", what);
+  return 0;
+}
+
+}  // namespace gtsbparse
+
+extern "C" {
+
+int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *nof_records,
+                       uint32_t *irregular_out) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (nof_records == nullptr || irregular_out == nullptr) return fail(c, "gtsb_parse_de_host: null argument");
+  if (parse_preamble(c, "gtsb_parse_de_host", text, n) != 0) return -1;
+  if (await_records(c) != 0) return -1;
+  ProfScope prof(c);
+  cudaStream_t s = c->stream;
+  *nof_records = 0;
+  *irregular_out = 0;
+  c->have_records = false;
+  c->have_graph = false;
+  if (c->names_dup) {
+    *irregular_out = IRR_DUP_NAME;
+    return 0;
+  }
+  uint64_t nlines = 0;
+  if (index_lines(c, text, n, &nlines) != 0) return -1;
+  ENSURE(c->p_line_cnt, (nlines + 1) * 4);
+  ENSURE(c->p_line_off, (nlines + 2) * 4);
+  ENSURE(c->scan_scratch, scan_scratch_elems(nlines) * 4);
+  const char *d_text = c->p_text.as<char>();
+  const uint64_t *line_end = c->p_line_end.as<uint64_t>();
+  uint32_t *flags = c->p_flags.as<uint32_t>();
 
   // records per line, then the records
   const NameTable t{c->p_names.as<char>(), c->p_name_off.as<uint64_t>(), c->p_slots.as<uint64_t>(),
@@ -209,6 +247,65 @@ int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *
   c->have_num_pairs = true;
   c->stats.nof_records = R;
   *nof_records = R;
+  return 0;
+}
+
+int gtsb_parse_astat_host(gtsb_context *c, const char *text, uint64_t n, float *astat, float *copy_num,
+                          uint32_t *irregular_out) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (irregular_out == nullptr) return fail(c, "gtsb_parse_astat_host: null argument");
+  if (parse_preamble(c, "gtsb_parse_astat_host", text, n) != 0) return -1;
+  const uint64_t V = c->names_V;
+  if (V && (astat == nullptr || copy_num == nullptr)) return fail(c, "gtsb_parse_astat_host: null argument");
+  ProfScope prof(c);
+  cudaStream_t s = c->stream;
+  *irregular_out = 0;
+  if (c->names_dup) {
+    *irregular_out = IRR_DUP_NAME;
+    return 0;
+  }
+  uint64_t nlines = 0;
+  if (index_lines(c, text, n, &nlines) != 0) return -1;
+  ENSURE(c->p_last, (V + 1) * 8);
+  ENSURE(c->p_astat, (V + 1) * 4);
+  ENSURE(c->p_copy_num, (V + 1) * 4);
+  CK(cudaMemsetAsync(c->p_last.p, 0, (V + 1) * 8, s));
+  if (V) {
+    CK(cudaMemcpyAsync(c->p_astat.p, astat, V * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->p_copy_num.p, copy_num, V * 4, cudaMemcpyHostToDevice, s));
+  }
+  const NameTable t{c->p_names.as<char>(), c->p_name_off.as<uint64_t>(), c->p_slots.as<uint64_t>(),
+                    c->names_mask};
+  uint32_t *flags = c->p_flags.as<uint32_t>();
+  uint32_t irregular = 0;
+  if (nlines) {
+    GTSB_TIMED("kp_astat(last line)", s);
+    kp_astat<false><<<blocks_for(nlines, 128), 128, 0, s>>>(c->p_text.as<char>(), c->p_line_end.as<uint64_t>(),
+                                                           nlines, t, c->p_last.as<uint64_t>(),
+                                                           c->p_astat.as<float>(), c->p_copy_num.as<float>(), flags);
+    c->stats.kernel_launches++;
+  }
+  CK(cudaMemcpyAsync(&irregular, flags, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (irregular) {                     // nothing is touched: the caller reads this file on the host
+    *irregular_out = irregular;
+    return 0;
+  }
+  if (nlines) {
+    GTSB_TIMED("kp_astat(apply)", s);
+    kp_astat<true><<<blocks_for(nlines, 128), 128, 0, s>>>(c->p_text.as<char>(), c->p_line_end.as<uint64_t>(),
+                                                          nlines, t, c->p_last.as<uint64_t>(),
+                                                          c->p_astat.as<float>(), c->p_copy_num.as<float>(), flags);
+    c->stats.kernel_launches++;
+  }
+  if (V) {
+    CK(cudaMemcpyAsync(astat, c->p_astat.p, V * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(copy_num, c->p_copy_num.p, V * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -199,7 +199,8 @@ GTSB_HD void chunk_line_ends(const char *text, uint64_t n, uint64_t i, uint32_t 
 GTSB_HD bool is_digit(char c) { return c >= '0' && c <= '9'; }
 
 // ['-'] 1..18 digits followed by `stop`; returns the index after `stop`, 0 if not canonical
-GTSB_HD uint32_t canonical_int(const char *t, uint32_t i, uint32_t n, bool allow_minus, int64_t *out) {
+GTSB_HD uint32_t canonical_int(const char *t, uint32_t i, uint32_t n, bool allow_minus, int64_t *out,
+                               char stop = ',') {
   bool neg = false;
   if (allow_minus && i < n && t[i] == '-') {
     neg = true;
@@ -212,7 +213,7 @@ GTSB_HD uint32_t canonical_int(const char *t, uint32_t i, uint32_t n, bool allow
     v = v * 10u + (uint64_t) (t[i] - '0');
     i++;
   }
-  if (digits == 0 || i >= n || t[i] != ',') return 0;
+  if (digits == 0 || i >= n || t[i] != stop) return 0;
   *out = neg ? -(int64_t) v : (int64_t) v;
   return i + 1;
 }
@@ -339,6 +340,90 @@ GTSB_HD uint32_t walk_line(const char *text, uint64_t s, uint64_t e, const NameT
     }
   }
   return count;
+}
+
+// ---- `.astat` lines (algorithms.c:118-149) ------------------------------------------
+// fgets pieces as above; every piece must give
+//   sscanf("%s\t%ld\t%ld\t%ld\t%f\t%f") == 6      (header, three counts, copy number, a-statistic)
+// or the reference stops with an error; a known header gets the two values, the last
+// line of a contig wins.  Canonical spelling: header of non-blank characters at the
+// start of the line, ONE '\t' between fields, ['-'] 1..18 digits for the counts,
+// ['-'] digits ['.' digits*] for the two values (float rule above), nothing after the
+// last one.  Everything else -- including what the reference would reject -- is
+// IRREGULAR and left to the host loop.
+
+struct AstatLine {
+  uint32_t v;             // vertex or NOT_FOUND
+  float copy_num, astat;
+};
+
+GTSB_HD uint32_t signed_float_field(const char *t, uint32_t i, uint32_t end, float *out) {
+  bool neg = false;
+  if (i < end && t[i] == '-') {
+    neg = true;
+    i++;
+  }
+  const uint32_t bad = canonical_float(t, i, end, out);
+  if (bad) return bad;
+  if (neg) *out = -*out;
+  return 0;
+}
+
+// 0 ok, else IRR_* bits
+GTSB_HD uint32_t parse_astat_piece(const char *t, uint32_t n, const NameTable &tab, AstatLine *out) {
+  uint32_t h = 0;
+  while (h < n && t[h] != '\t') {
+    const char c = t[h];
+    if (c == ' ' || c == '\n' || c == '\v' || c == '\f' || c == '\r') return IRR_TOKEN;
+    h++;
+  }
+  if (h == 0 || h == n) return IRR_TOKEN;
+  uint32_t i = h + 1;
+  int64_t ignored;
+  for (int k = 0; k < 3; k++) {
+    i = canonical_int(t, i, n, true, &ignored, '\t');
+    if (i == 0) return IRR_TOKEN;
+  }
+  uint32_t e = i;
+  while (e < n && t[e] != '\t') e++;
+  if (e == n) return IRR_TOKEN;
+  uint32_t bad = signed_float_field(t, i, e, &out->copy_num);
+  if (bad) return bad;
+  bad = signed_float_field(t, e + 1, n, &out->astat);
+  if (bad) return bad;
+  out->v = table_lookup(tab, t, h);
+  return 0;
+}
+
+GTSB_HD void max64(uint64_t *addr, uint64_t val) {
+#if defined(__CUDA_ARCH__)
+  atomicMax((unsigned long long *) addr, (unsigned long long) val);
+#else
+  if (*addr < val) *addr = val;
+#endif
+}
+
+// One physical line [s, e).  APPLY = false: last[v] = max(piece offset + 1) over the pieces
+// naming v; APPLY = true: the piece that holds that maximum writes its values.
+template <bool APPLY>
+GTSB_HD void walk_astat_line(const char *text, uint64_t s, uint64_t e, const NameTable &tab, uint64_t *last,
+                             float *astat, float *copy_num, uint32_t *irregular) {
+  for (uint64_t p = s; p < e;) {
+    const uint64_t piece_end = p + PIECE < e ? p + PIECE : e;
+    AstatLine a;
+    const uint32_t bad = parse_astat_piece(text + p, (uint32_t) (piece_end - 1 - p), tab, &a);
+    if (bad) {
+      flag_or(irregular, bad);
+    } else if (a.v != NOT_FOUND) {
+      if (!APPLY) {
+        max64(last + a.v, p + 1);
+      } else if (last[a.v] == p + 1) {
+        astat[a.v] = a.astat;                                 // algorithms.c:140-141
+        copy_num[a.v] = a.copy_num;
+      }
+    }
+    p = piece_end;
+  }
 }
 
 }  // namespace gtsbp

@@ -105,11 +105,21 @@ int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_e
 #define GTSB_IRR_NUL      1u   /* NUL byte in the text */
 #define GTSB_IRR_TOKEN    2u   /* "header,..." token that is not a canonical record */
 #define GTSB_IRR_RANGE    4u   /* distance outside int32 / pair count outside uint32 */
-#define GTSB_IRR_FLOAT    8u   /* std_dev the device cannot prove it rounds as strtof does */
+#define GTSB_IRR_FLOAT    8u   /* a value the device cannot prove it rounds as strtof does */
+#define GTSB_IRR_DUP_NAME 16u  /* two contigs with one header (bsearch's choice is unspecified) */
 int gtsb_set_vertex_names_host(gtsb_context *ctx, uint64_t nof_vertices, const char *names,
                                const uint64_t *name_off);
 int gtsb_parse_de_host(gtsb_context *ctx, const char *text, uint64_t text_bytes,
                        uint64_t *nof_records, uint32_t *irregular);
+/* .astat text: the line loop of gt_scaffolder_graph_mark_repeats
+   (gt_scaffolder_algorithms.c:118-149, sscanf "%s\t%ld\t%ld\t%ld\t%f\t%f" == 6 per line).
+   astat / copy_num: one value per vertex of the names set, in and out -- the entries of
+   contigs the text names are overwritten (last line wins, as the sequential loop has it),
+   the others keep their value.  Canonical lines only (single tabs, plain decimals);
+   *irregular != 0: nothing was touched, read the file on the host -- that includes every
+   text the reference would reject with "Invalid record". */
+int gtsb_parse_astat_host(gtsb_context *ctx, const char *text, uint64_t text_bytes, float *astat,
+                          float *copy_num, uint32_t *irregular);
 /* the records held by the context, file order (NULL pointers are skipped); num_pairs
    only after gtsb_parse_de_host */
 int gtsb_get_records(gtsb_context *ctx, uint32_t *root, uint32_t *ctg, int32_t *dist,

@@ -172,6 +172,47 @@ static int read_de_records(const char *filename, const GtScaffolderGraph *graph,
   return 0;
 }
 
+/* whole file into memory; NULL if it cannot be read that way */
+static char *slurp(const char *filename, uint64_t *bytes)
+{
+  FILE *fp = fopen(filename, "rb");
+  char *text = NULL;
+  long size;
+  if (fp == NULL)
+    return NULL;
+  if (fseek(fp, 0, SEEK_END) == 0 && (size = ftell(fp)) >= 0 && fseek(fp, 0, SEEK_SET) == 0) {
+    text = gt_malloc((size_t) size + 1);
+    if (fread(text, 1, (size_t) size, fp) != (size_t) size) {
+      gt_free(text);
+      text = NULL;
+    }
+    *bytes = (uint64_t) size;
+  }
+  fclose(fp);
+  return text;
+}
+
+/* the vertices' headers, id order -> the device's gt_scaffolder_graph_get_vertex */
+static int device_vertex_names(gtsb_context *c, const GtScaffolderGraph *graph)
+{
+  uint64_t *name_off = gt_malloc((graph->nof_vertices + 1) * sizeof (*name_off)), bytes = 0;
+  char *names;
+  GtUword i;
+  int rc;
+  for (i = 0; i < graph->nof_vertices; i++) {
+    name_off[i] = bytes;
+    bytes += gt_str_length(graph->vertices[i].header_seq);
+  }
+  name_off[graph->nof_vertices] = bytes;
+  names = gt_malloc(bytes + 1);
+  for (i = 0; i < graph->nof_vertices; i++)
+    memcpy(names + name_off[i], gt_str_get(graph->vertices[i].header_seq), name_off[i + 1] - name_off[i]);
+  rc = gtsb_set_vertex_names_host(c, graph->nof_vertices, names, name_off);
+  gt_free(names);
+  gt_free(name_off);
+  return rc;
+}
+
 /* `.de` text -> records on the device.  *on_device = false on return 0 means
    the device refused the text (outside the canonical spelling) and nothing
    was set; the caller tokenises on the host.  The pair counts come back for
@@ -179,46 +220,18 @@ static int read_de_records(const char *filename, const GtScaffolderGraph *graph,
 static int device_de_records(gtsb_context *c, const char *filename, const GtScaffolderGraph *graph,
                              B200Records *recs, bool *on_device, GtError *err)
 {
-  FILE *fp = fopen(filename, "rb");
-  char *text = NULL, *names = NULL;
-  uint64_t *name_off = NULL, nof_records = 0, bytes = 0;
+  uint64_t nof_records = 0, bytes = 0, r;
   uint32_t irregular = 0, *pairs = NULL;
-  long size;
-  GtUword i;
+  char *text = slurp(filename, &bytes);
   int had_err = 0;
 
   *on_device = false;
-  if (fp == NULL) {
-    gt_error_set(err, " can not read distance file %s ", filename);
-    return -1;
-  }
-  if (fseek(fp, 0, SEEK_END) != 0 || (size = ftell(fp)) < 0 || fseek(fp, 0, SEEK_SET) != 0) {
-    fclose(fp);
-    return 0;                                   /* not seekable: host tokeniser */
-  }
-  text = gt_malloc((size_t) size + 1);
-  if (fread(text, 1, (size_t) size, fp) != (size_t) size) {
-    gt_error_set(err, " can not read distance file %s ", filename);
+  if (text == NULL)
+    return 0;                                   /* let the host tokeniser report it */
+  if (device_vertex_names(c, graph) != 0 ||
+      gtsb_parse_de_host(c, text, bytes, &nof_records, &irregular) != 0) {
+    gt_error_set(err, "%s", gtsb_error(c));
     had_err = -1;
-  }
-  fclose(fp);
-
-  if (had_err == 0) {
-    name_off = gt_malloc((graph->nof_vertices + 1) * sizeof (*name_off));
-    for (i = 0; i < graph->nof_vertices; i++) {
-      name_off[i] = bytes;
-      bytes += gt_str_length(graph->vertices[i].header_seq);
-    }
-    name_off[graph->nof_vertices] = bytes;
-    names = gt_malloc(bytes + 1);
-    for (i = 0; i < graph->nof_vertices; i++)
-      memcpy(names + name_off[i], gt_str_get(graph->vertices[i].header_seq),
-             name_off[i + 1] - name_off[i]);
-    if (gtsb_set_vertex_names_host(c, graph->nof_vertices, names, name_off) != 0 ||
-        gtsb_parse_de_host(c, text, (uint64_t) size, &nof_records, &irregular) != 0) {
-      gt_error_set(err, "%s", gtsb_error(c));
-      had_err = -1;
-    }
   }
   if (had_err == 0 && irregular == 0) {
     pairs = gt_malloc((nof_records + 1) * sizeof (*pairs));
@@ -227,15 +240,53 @@ static int device_de_records(gtsb_context *c, const char *filename, const GtScaf
       had_err = -1;
     } else {
       recs->num_pairs = gt_malloc((nof_records + 1) * sizeof (*recs->num_pairs));
-      for (bytes = 0; bytes < nof_records; bytes++)
-        recs->num_pairs[bytes] = pairs[bytes];
+      for (r = 0; r < nof_records; r++)
+        recs->num_pairs[r] = pairs[r];
       recs->n = recs->cap = nof_records;
       *on_device = true;
     }
   }
   gt_free(pairs);
-  gt_free(names);
-  gt_free(name_off);
+  gt_free(text);
+  return had_err;
+}
+
+/* `.astat` text -> vertex->astat / vertex->copy_num on the device
+   (algorithms.c:118-149).  *on_device = false on return 0: the device refused
+   the text (not in the canonical spelling, or a record the reference would
+   reject) and nothing was touched; the host loop reads it and reports. */
+static int device_astat(gtsb_context *c, const char *filename, GtScaffolderGraph *graph, bool *on_device,
+                        GtError *err)
+{
+  uint64_t bytes = 0;
+  uint32_t irregular = 0;
+  char *text = slurp(filename, &bytes);
+  float *astat, *copy_num;
+  GtUword i;
+  int had_err = 0;
+
+  *on_device = false;
+  if (text == NULL)
+    return 0;
+  astat = gt_malloc((graph->nof_vertices + 1) * sizeof (*astat));
+  copy_num = gt_malloc((graph->nof_vertices + 1) * sizeof (*copy_num));
+  for (i = 0; i < graph->nof_vertices; i++) {
+    astat[i] = graph->vertices[i].astat;
+    copy_num[i] = graph->vertices[i].copy_num;
+  }
+  if (device_vertex_names(c, graph) != 0 ||
+      gtsb_parse_astat_host(c, text, bytes, astat, copy_num, &irregular) != 0) {
+    gt_error_set(err, "%s", gtsb_error(c));
+    had_err = -1;
+  } else if (irregular == 0) {
+    for (i = 0; i < graph->nof_vertices; i++) {
+      graph->vertices[i].astat = astat[i];
+      graph->vertices[i].copy_num = copy_num[i];
+    }
+    *on_device = true;
+  }
+  gt_free(astat);
+  gt_free(copy_num);
   gt_free(text);
   return had_err;
 }
@@ -541,9 +592,21 @@ int gt_scaffolder_graph_mark_repeats(const char *filename,
                                      GtError *err)
 {
   const bool have_file = strlen(filename) != 0;
+  bool on_device = false;
   int had_err = 0;
 
   if (have_file) {
+    const char *tokeniser = getenv("GTSB_TOKENISER");
+    gtsb_context *c = b200_context();
+    if (c != NULL && !(tokeniser != NULL && strcmp(tokeniser, "host") == 0))
+      had_err = device_astat(c, filename, graph, &on_device, err);
+    if (had_err != 0)
+      return had_err;
+    if (getenv("GTSB_VERBOSE") != NULL)
+      fprintf(stderr, "gt_scaffolder (B200): %s tokenised on the %s\n", filename,
+              on_device ? "device" : "host");
+  }
+  if (have_file && !on_device) {
     /* `.astat` text -> per-vertex attributes, algorithms.c:118-149 */
     char line[B200_LINE + 1], hdr[B200_LINE + 1];
     FILE *fp = fopen(filename, "rb");

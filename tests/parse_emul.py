@@ -58,6 +58,19 @@ def parse(names, text, order=0):
     return 0, rec
 
 
+def parse_astat(names, text, astat, copy_num, order=0):
+    """-> (irregular bits, astat, copy_num) -- copies of the inputs with the text applied"""
+    L = lib()
+    blob, off = pack_names(names)
+    a = np.array(astat, np.float32)
+    cn = np.array(copy_num, np.float32)
+    irr = C.c_uint32(0)
+    L.emul_parse_astat(C.c_uint64(len(names)), blob, off.ctypes.data_as(C.c_void_p), text,
+                       C.c_uint64(len(text)), C.c_int(order), a.ctypes.data_as(C.c_void_p),
+                       cn.ctypes.data_as(C.c_void_p), C.byref(irr))
+    return irr.value, a, cn
+
+
 def canonical_float(s: bytes):
     out = C.c_float(0)
     r = lib().emul_canonical_float(s, C.c_uint32(len(s)), C.byref(out))

@@ -389,6 +389,122 @@ def test_degenerate_texts():
     assert irr == 0 and len(rec["root"]) == 0
 
 
+# ------------------------------------------------------------------------ .astat, CPU
+
+VALUE_SPELLINGS = [b"1.009161", b"5061.884949", b"0.990243", b"-12.25", b"0", b"-0", b"20", b"20.0",
+                   b"0.3", b"0.299999", b"19.999999", b"-0.000001", b"123456.789", b"33.1", b"7"]
+
+
+class Invalid(Exception):
+    pass
+
+
+def make_astat(seed, V=40, lines=70):
+    rng = np.random.default_rng(5000 + seed)
+    names = make_names(rng, V)
+    out = []
+    for _ in range(lines):
+        known = rng.random() > 0.15
+        hdr = names[int(rng.integers(0, V))] if known else [b"zz_unknown", b"c", b"contig-"][int(rng.integers(0, 3))]
+        ints = [b"%d" % int(rng.choice([-3, 0, 17, 25387, 10**12])) for _ in range(3)]
+        cn = VALUE_SPELLINGS[int(rng.integers(0, len(VALUE_SPELLINGS)))]
+        a = VALUE_SPELLINGS[int(rng.integers(0, len(VALUE_SPELLINGS)))]
+        out.append(b"\t".join([hdr] + ints + [cn, a]))
+    return names, b"\n".join(out) + b"\n"
+
+
+def astat_model(names, text, astat, copy_num):
+    """algorithms.c:118-149 around the C library's sscanf"""
+    ids = {n: i for i, n in enumerate(names)}
+    a, cn = np.array(astat, np.float32), np.array(copy_num, np.float32)
+    hdr = C.create_string_buffer(2048)
+    n1, n2, n3, f1, f2 = C.c_long(0), C.c_long(0), C.c_long(0), C.c_float(0), C.c_float(0)
+    pos, n = 0, len(text)
+    while pos < n:
+        nl = text.find(b"\n", pos, pos + 1023)
+        end = nl + 1 if nl >= 0 else min(pos + 1023, n)
+        line = text[pos:end - 1]
+        pos = end
+        if libc.sscanf(line, b"%s\t%ld\t%ld\t%ld\t%f\t%f", hdr, C.byref(n1), C.byref(n2), C.byref(n3),
+                       C.byref(f1), C.byref(f2)) != 6:
+            raise Invalid()
+        if hdr.value in ids:
+            a[ids[hdr.value]] = f2.value
+            cn[ids[hdr.value]] = f1.value
+    return a, cn
+
+
+def same_floats(x, y):
+    assert np.array_equal(np.asarray(x, np.float32).view(np.uint32), np.asarray(y, np.float32).view(np.uint32))
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_astat_emulation_equals_reference(seed, tmp_path, synth):
+    """values the compiled reference's gt_scaffolder_graph_mark_repeats leaves in the vertices"""
+    names, text = make_astat(seed)
+    fa, de, path = str(tmp_path / "c.fa"), str(tmp_path / "l.de"), str(tmp_path / "l.astat")
+    write_fasta(fa, names)
+    with open(de, "wb") as f:
+        f.write(names[0] + b" " + names[1] + b"+,10,5,1.5 ;\n")
+    with open(path, "wb") as f:
+        f.write(text)
+    ref = O.RefGraph.from_files(fa, de)
+    before = ref.vertices()
+    ref.mark_repeats(0.3, 20.0, astat_file=path)
+    after = ref.vertices()
+    irr, a, cn = PE.parse_astat(names, text, before["astat"], before["copy_num"], order=seed % 2)
+    assert irr == 0
+    same_floats(a, after["astat"])
+    same_floats(cn, after["copy_num"])
+    assert not np.array_equal(after["astat"], before["astat"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_astat_fuzzed_texts_are_read_like_sscanf_or_refused(seed):
+    rng = np.random.default_rng(4242 + seed)
+    accepted = refused = 0
+    fuzz = b"0123456789\t\t\t..--  \n\nex+_A"
+    for it in range(300):
+        names, text = make_astat(100 * seed + it, V=6, lines=5)
+        b = bytearray(text)
+        for _ in range(int(rng.integers(0, 4))):
+            kind, p = rng.random(), int(rng.integers(0, len(b)))
+            if kind < 0.6:
+                b[p] = fuzz[int(rng.integers(0, len(fuzz)))]
+            elif kind < 0.8:
+                del b[p]
+            else:
+                b.insert(p, fuzz[int(rng.integers(0, len(fuzz)))])
+        text = bytes(b)
+        a0, c0 = rng.random(6).astype(np.float32), rng.random(6).astype(np.float32)
+        irr, a, cn = PE.parse_astat(names, text, a0, c0, order=it & 1)
+        if irr:
+            refused += 1
+            same_floats(a, a0)                                    # untouched
+            same_floats(cn, c0)
+            continue
+        accepted += 1
+        ea, ecn = astat_model(names, text, a0, c0)                # must not raise Invalid
+        same_floats(a, ea)
+        same_floats(cn, ecn)
+    assert accepted > 30 and refused > 30
+
+
+def test_c1_testdata_astat():
+    c1 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1")
+    names = sorted(line[1:].split()[0] for line in open(os.path.join(c1, "contigs.fa"), "rb")
+                   if line.startswith(b">"))
+    text = open(os.path.join(c1, "libPE.astat"), "rb").read()
+    z = np.zeros(len(names), np.float32)
+    irr, a, cn = PE.parse_astat(names, text, z, z)
+    assert irr == 0
+    ea, ecn = astat_model(names, text, z, z)
+    same_floats(a, ea)
+    same_floats(cn, ecn)
+    assert (a != 0).sum() > 10
+
+
 # ------------------------------------------------------------------------------- GPU
 
 def device_parse(pkg, names, text):
@@ -438,8 +554,11 @@ def test_device_refuses_irregular_texts(pkg, text, bits):
 @pytest.mark.gpu
 def test_device_refuses_duplicate_headers(pkg):
     g = pkg.ScaffoldGraphB200()
-    with pytest.raises(RuntimeError, match="same header"):
-        g.set_vertex_names([b"A", b"B", b"B"])
+    g.set_vertex_names([b"A", b"B", b"B"])
+    assert g.parse_de(b"A B+,1,2,3.0\n")[0] == 16
+    assert g.parse_astat(b"A\t1\t2\t3\t1.0\t2.0\n", np.zeros(3), np.zeros(3))[0] == 16
+    g.set_vertex_names([b"A", b"B", b"C"])                       # a good table replaces it
+    assert g.parse_de(b"A B+,1,2,3.0\n") == (0, 1)
 
 
 @pytest.mark.gpu
@@ -481,4 +600,58 @@ def test_device_text_to_filtered_graph(pkg, synth, tmp_path, name, V):
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, f"parse_profile_{name}.json"), "w") as f:
+            json.dump(report, f, indent=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_device_astat_equals_emulation(pkg, seed):
+    names, text = make_astat(seed, V=50 + 400 * seed, lines=80 + 900 * seed)
+    rng = np.random.default_rng(seed)
+    a0, c0 = rng.random(len(names)).astype(np.float32), rng.random(len(names)).astype(np.float32)
+    g = pkg.ScaffoldGraphB200()
+    g.set_vertex_names(names)
+    irr, a, cn = g.parse_astat(text, a0, c0)
+    eirr, ea, ecn = PE.parse_astat(names, text, a0, c0)
+    assert irr == 0 and eirr == 0
+    same_floats(a, ea)
+    same_floats(cn, ecn)
+    # refusals leave the values alone
+    for bad in (text[:-1], text.replace(b"\t", b" ", 1), text + b"x\n", b"\n" + text):
+        irr, a, cn = g.parse_astat(bad, a0, c0)
+        assert irr == PE.parse_astat(names, bad, a0, c0)[0] != 0
+        same_floats(a, a0)
+        same_floats(cn, c0)
+    irr, a, cn = g.parse_astat(b"", a0, c0)
+    assert irr == 0
+    same_floats(a, a0)
+
+
+@pytest.mark.gpu
+def test_device_astat_at_size(pkg, synth):
+    """every contig once, in shuffled order, plus repeated lines: 3*10^5 lines"""
+    V = 300_000
+    inp = synth.generate("c3_human", V=V, max_deg=30)
+    rng = np.random.default_rng(3)
+    order = np.concatenate([rng.permutation(V), rng.integers(0, V, V // 10)])
+    lines = [b"c%010d\t%d\t0\t0\t%.6f\t%.6f" % (v, inp.seq_len[v], inp.copy_num[v], inp.astat[v] + (i >= V))
+             for i, v in enumerate(order)]
+    text = b"\n".join(lines) + b"\n"
+    names = [b"c%010d" % v for v in range(V)]
+    g = pkg.ScaffoldGraphB200()
+    g.set_vertex_names(names)
+    z = np.zeros(V, np.float32)
+    g.parse_astat(text, z, z)
+    g.set_profile(True)
+    irr, a, cn = g.parse_astat(text, z, z)
+    prof = {k: round(v[0], 4) for k, v in g.profile().items()}
+    eirr, ea, ecn = PE.parse_astat(names, text, z, z)
+    assert irr == 0 and eirr == 0
+    same_floats(a, ea)
+    same_floats(cn, ecn)
+    report = dict(contigs=V, lines=len(lines), text_bytes=len(text), kernel_ms=prof)
+    print("\n[astat]", json.dumps(report))
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parse_profile_astat.json"), "w") as f:
             json.dump(report, f, indent=1)
