@@ -616,12 +616,20 @@ def test_device_astat_equals_emulation(pkg, seed):
     assert irr == 0 and eirr == 0
     same_floats(a, ea)
     same_floats(cn, ecn)
-    # refusals leave the values alone
-    for bad in (text[:-1], text.replace(b"\t", b" ", 1), text + b"x\n", b"\n" + text):
+    # edited texts: refused by both (values left alone) or read alike
+    refused = 0
+    for bad in (text[:-1], text[:-3], text.replace(b"\t", b" ", 1), text + b"x\n", b"\n" + text,
+                text.replace(b"\n", b"\n\n", 1), text.replace(b"\t", b"\t\t", 1)):
         irr, a, cn = g.parse_astat(bad, a0, c0)
-        assert irr == PE.parse_astat(names, bad, a0, c0)[0] != 0
-        same_floats(a, a0)
-        same_floats(cn, c0)
+        eirr, ea, ecn = PE.parse_astat(names, bad, a0, c0)
+        assert irr == eirr
+        same_floats(a, ea)
+        same_floats(cn, ecn)
+        if irr:
+            refused += 1
+            same_floats(a, a0)
+            same_floats(cn, c0)
+    assert refused >= 5
     irr, a, cn = g.parse_astat(b"", a0, c0)
     assert irr == 0
     same_floats(a, a0)
