@@ -36,6 +36,7 @@ EXPORTS = [
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
     "gtsb_set_record_lines_host", "gtsb_get_edge_states",
     "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
+    "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host",
 ]
 
 
@@ -102,6 +103,8 @@ def load_library():
     L.gtsb_parse_de_host.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.gtsb_get_records.argtypes = [vp] * 7
     L.gtsb_parse_astat_host.argtypes = [vp, C.c_char_p, u64, vp, vp, C.POINTER(C.c_uint32)]
+    L.gtsb_dot_vertex_lines_host.argtypes = [vp, i32, u64, u64, vp, C.c_char_p, u64, C.POINTER(u64)]
+    L.gtsb_dot_edge_lines_host.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp, C.c_char_p, u64, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -245,6 +248,30 @@ class ScaffoldGraphB200:
         self._ck(self.L.gtsb_parse_astat_host(self.h, text, C.c_uint64(len(text)), _ptr(a), _ptr(cn),
                                               C.byref(irr)))
         return int(irr.value), a, cn
+
+    # ---- .dot text (graph.c:269-343)
+    def dot_vertex_lines(self, vstate, first: int = 0, scaffold_only: bool = False, names_bytes: int = 0):
+        """The vertex lines of gt_scaffolder_graph_print_generic / _print_scaffold for vertices
+        [first, first + len(vstate)) of the names set.  names_bytes: bytes of their headers."""
+        vs = np.ascontiguousarray(vstate, np.uint8)
+        cap = 64 * len(vs) + names_bytes + 16
+        out = C.create_string_buffer(cap)
+        n = C.c_uint64(0)
+        self._ck(self.L.gtsb_dot_vertex_lines_host(self.h, int(scaffold_only), first, len(vs), _ptr(vs), out,
+                                                   cap, C.byref(n)))
+        return out.raw[:n.value]
+
+    def dot_edge_lines(self, src, dst, dist, estate, sense, scaffold_only: bool = False):
+        """The edge lines, edges in graph->edges[] order."""
+        a = [np.ascontiguousarray(src, np.uint32), np.ascontiguousarray(dst, np.uint32),
+             np.ascontiguousarray(dist, np.int32), np.ascontiguousarray(estate, np.uint8),
+             np.ascontiguousarray(sense, np.uint8)]
+        cap = 105 * len(a[0]) + 16
+        out = C.create_string_buffer(cap)
+        n = C.c_uint64(0)
+        self._ck(self.L.gtsb_dot_edge_lines_host(self.h, int(scaffold_only), len(a[0]), *[_ptr(x) for x in a],
+                                                 out, cap, C.byref(n)))
+        return out.raw[:n.value]
 
     def records(self, num_pairs: bool = True):
         """The records the context holds, file order."""

@@ -727,7 +727,8 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg,
                     &c->p_names, &c->p_name_off, &c->p_slots, &c->p_flags, &c->p_text, &c->p_chunk_cnt,
                     &c->p_chunk_off, &c->p_line_end, &c->p_line_cnt, &c->p_line_off, &c->num_pairs,
-                    &c->p_last, &c->p_astat, &c->p_copy_num};
+                    &c->p_last, &c->p_astat, &c->p_copy_num, &c->f_state, &c->f_sense, &c->f_src, &c->f_dst,
+                    &c->f_dist, &c->f_len, &c->f_off, &c->f_out};
   for (DevBuf *b : bufs) release(*b);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (Timer *t : {&c->t_build, &c->t_rep, &c->t_filter}) {

@@ -70,6 +70,7 @@ struct gtsb_context {
   // .de text on the device (gtsb_parse.cu)
   DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,
       p_line_cnt, p_line_off, num_pairs, p_last, p_astat, p_copy_num;
+  DevBuf f_state, f_sense, f_src, f_dst, f_dist, f_len, f_off, f_out;     // .dot lines (gtsb_format.cu)
   uint64_t names_V = 0, names_mask = 0;
   bool have_names = false, names_dup = false, have_num_pairs = false;
 

@@ -26,10 +26,12 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef GTSB_HD
 #if defined(__CUDACC__)
 #define GTSB_HD __host__ __device__ __forceinline__
 #else
 #define GTSB_HD inline
+#endif
 #endif
 
 namespace gtsbp {

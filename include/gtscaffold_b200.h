@@ -125,6 +125,19 @@ int gtsb_parse_astat_host(gtsb_context *ctx, const char *text, uint64_t text_byt
 int gtsb_get_records(gtsb_context *ctx, uint32_t *root, uint32_t *ctg, int32_t *dist,
                      float *std_dev, uint8_t *flags, uint32_t *num_pairs);
 
+/* ---- .dot text from graph arrays: the lines gt_scaffolder_graph_print_generic and
+   gt_scaffolder_graph_print_scaffold write (gt_scaffolder_graph.c:269-343) between
+   "digraph {\n" and "}\n", in item order.  scaffold_only != 0: the print_scaffold lines
+   (items in state GTSB_SCAFFOLD only, no colour).  Vertices [first, first + count) of the
+   names set (gtsb_set_vertex_names_host) with vstate[count]; edges as parallel arrays in
+   graph->edges[] order.  At most 2^25 items per call; out must hold the text (bytes <= cap
+   is checked; 64 + header bytes per vertex and 105 bytes per edge always suffice). */
+int gtsb_dot_vertex_lines_host(gtsb_context *ctx, int scaffold_only, uint64_t first, uint64_t count,
+                               const uint8_t *vstate, char *out, uint64_t cap, uint64_t *bytes);
+int gtsb_dot_edge_lines_host(gtsb_context *ctx, int scaffold_only, uint64_t count, const uint32_t *src,
+                             const uint32_t *dst, const int32_t *dist, const uint8_t *estate,
+                             const uint8_t *sense, char *out, uint64_t cap, uint64_t *bytes);
+
 /* ---- the hot path */
 int gtsb_build(gtsb_context *ctx);
 int gtsb_mark_repeats(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff,

@@ -8,6 +8,9 @@
  *   gt_scaffolder_graph_mark_repeats    (gt_scaffolder_algorithms.h:36-40, body algorithms.c:90-170)
  *   gt_scaffolder_graph_filter          (gt_scaffolder_algorithms.h:43-46, body algorithms.c:261-343)
  *
+ * and gt_scaffolder_graph_print (gt_scaffolder_graph.h:149-151, body
+ * graph.c:246-304), whose lines are formatted on the device,
+ *
  * over the array-level C ABI of include/gtscaffold_b200.h.  GtScaffolderGraph
  * keeps its layout; everything downstream (gt_scaffolder_graph_print,
  * removecycles, makescaffold, write_scaffold) reads the `state` fields and
@@ -674,4 +677,106 @@ void gt_scaffolder_graph_filter(GtScaffolderGraph *graph,
       graph_fetch_states(c, graph, &f) != 0)
     b200_die("gt_scaffolder_graph_filter");
   flat_free(&f);
+}
+
+/* ------------------------------------------------------------------ print */
+
+#define B200_PRINT_CHUNK ((GtUword) 1 << 24)   /* items per device call (the ABI takes 2^25) */
+
+/* gt_scaffolder_graph_print (graph.c:246-266) around gt_scaffolder_graph_print_generic
+   (graph.c:269-304): same file, the vertex and edge lines formatted on the device in
+   chunks, written in order. */
+int gt_scaffolder_graph_print(const GtScaffolderGraph *g, const char *filename, GtError *err)
+{
+  gtsb_context *c;
+  FILE *fp;
+  GtUword first, i, names_bytes;
+  uint64_t cap = 0, bytes;
+  char *out = NULL;
+  uint8_t *state = NULL, *sense = NULL;
+  uint32_t *src = NULL, *dst = NULL;
+  int32_t *dist = NULL;
+  int had_err = 0;
+
+  gt_assert(g != NULL);
+  c = b200_context();
+  if (c == NULL) {
+    gt_error_set(err, "no CUDA device available (the B200 path has no CPU fallback)");
+    return -1;
+  }
+  fp = fopen(filename, "w");
+  if (fp == NULL) {
+    gt_error_set(err, "cannot open file '%s' for writing", filename);
+    return -1;
+  }
+  if (device_vertex_names(c, g) != 0)
+    had_err = -1;
+  fputs("digraph {\n", fp);
+
+  state = gt_malloc(B200_PRINT_CHUNK);
+  for (first = 0; had_err == 0 && first < g->nof_vertices; first += B200_PRINT_CHUNK) {
+    const GtUword n = g->nof_vertices - first < B200_PRINT_CHUNK ? g->nof_vertices - first : B200_PRINT_CHUNK;
+    names_bytes = 0;
+    for (i = 0; i < n; i++) {
+      state[i] = (uint8_t) g->vertices[first + i].state;
+      names_bytes += gt_str_length(g->vertices[first + i].header_seq);
+    }
+    if (64 * n + names_bytes > cap) {
+      cap = 64 * n + names_bytes;
+      out = gt_realloc(out, cap);
+    }
+    if (gtsb_dot_vertex_lines_host(c, 0, first, n, state, out, cap, &bytes) != 0)
+      had_err = -1;
+    else if (fwrite(out, 1, bytes, fp) != bytes)
+      had_err = -2;
+  }
+
+  if (had_err == 0 && g->nof_edges > 0) {
+    const GtUword m = g->nof_edges < B200_PRINT_CHUNK ? g->nof_edges : B200_PRINT_CHUNK;
+    src = gt_malloc(m * sizeof (*src));
+    dst = gt_malloc(m * sizeof (*dst));
+    dist = gt_malloc(m * sizeof (*dist));
+    sense = gt_malloc(m);
+    if (105 * m > cap) {
+      cap = 105 * m;
+      out = gt_realloc(out, cap);
+    }
+  }
+  for (first = 0; had_err == 0 && first < g->nof_edges; first += B200_PRINT_CHUNK) {
+    const GtUword n = g->nof_edges - first < B200_PRINT_CHUNK ? g->nof_edges - first : B200_PRINT_CHUNK;
+    for (i = 0; i < n; i++) {
+      const GtScaffolderGraphEdge *e = g->edges + first + i;
+      if (e->dist > INT32_MAX || e->dist < INT32_MIN) {
+        gt_error_set(err, "distance " GT_WD " does not fit the device's 32-bit distance column", e->dist);
+        had_err = -3;
+        break;
+      }
+      src[i] = (uint32_t) (e->start - g->vertices);
+      dst[i] = (uint32_t) (e->end - g->vertices);
+      dist[i] = (int32_t) e->dist;
+      state[i] = (uint8_t) e->state;
+      sense[i] = e->sense ? 1 : 0;
+    }
+    if (had_err != 0)
+      break;
+    if (gtsb_dot_edge_lines_host(c, 0, n, src, dst, dist, state, sense, out, cap, &bytes) != 0)
+      had_err = -1;
+    else if (fwrite(out, 1, bytes, fp) != bytes)
+      had_err = -2;
+  }
+  if (had_err == 0)
+    fputs("}\n", fp);
+  if (fclose(fp) != 0 && had_err == 0)
+    had_err = -2;
+  if (had_err == -1)
+    gt_error_set(err, "%s", gtsb_error(c));
+  else if (had_err == -2)
+    gt_error_set(err, "cannot write to file '%s'", filename);
+  gt_free(out);
+  gt_free(state);
+  gt_free(sense);
+  gt_free(src);
+  gt_free(dst);
+  gt_free(dist);
+  return had_err != 0 ? -1 : 0;
 }

@@ -223,6 +223,21 @@ int refdrv_print(const GtScaffolderGraph *g, const char *filename)
   return rc;
 }
 
+/* graph.c:310-343; defined there, declared in no header */
+void gt_scaffolder_graph_print_scaffold(const GtScaffolderGraph *g, GtFile *f);
+
+int refdrv_print_scaffold(const GtScaffolderGraph *g, const char *filename)
+{
+  GtError *err = gt_error_new();
+  GtFile *f = gt_file_new(filename, "w", err);
+  if (f != NULL) {
+    gt_scaffolder_graph_print_scaffold(g, f);
+    gt_file_delete(f);
+  }
+  gt_error_delete(err);
+  return f != NULL ? 0 : -1;
+}
+
 /* downstream host stages (out of the hot path) for the .dot/.scaf checks */
 void refdrv_removecycles(GtScaffolderGraph *g) { gt_scaffolder_removecycles(g); }
 void refdrv_makescaffold(GtScaffolderGraph *g) { gt_scaffolder_makescaffold(g); }

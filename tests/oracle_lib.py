@@ -67,6 +67,8 @@ def ref_lib():
         L.refdrv_new_from_file.restype = C.c_void_p
         L.refdrv_new_from_file.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
         L.refdrv_print.argtypes = [C.c_void_p, C.c_char_p]
+        if hasattr(L, "refdrv_print_scaffold"):
+            L.refdrv_print_scaffold.argtypes = [C.c_void_p, C.c_char_p]
         L.refdrv_removecycles.argtypes = [C.c_void_p]
         L.refdrv_makescaffold.argtypes = [C.c_void_p]
         L.refdrv_write_scaffold.argtypes = [C.c_void_p, C.c_char_p]
@@ -220,6 +222,10 @@ class RefGraph(_Common):
 
     def print_dot(self, path):
         return self.L.refdrv_print(self.h, path.encode())
+
+    def print_scaffold_dot(self, path):
+        """gt_scaffolder_graph_print_scaffold (graph.c:310-343)"""
+        return self.L.refdrv_print_scaffold(self.h, path.encode())
 
     def removecycles(self):
         self.L.refdrv_removecycles(self.h)

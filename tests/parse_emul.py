@@ -11,8 +11,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "emul", "parse_emul.cpp")
-CORE = os.path.join(HERE, "..", "gt-scaffold_b200", "csrc", "gtsb_parse_core.h")
+CSRC = os.path.join(HERE, "..", "gt-scaffold_b200", "csrc")
+SRCS = [os.path.join(HERE, "emul", "parse_emul.cpp"), os.path.join(HERE, "emul", "format_emul.cpp")]
+CORES = [os.path.join(CSRC, "gtsb_parse_core.h"), os.path.join(CSRC, "gtsb_format_core.h")]
 OUT = os.path.join(HERE, "emul", "_build", "libparse_emul.so")
 _lib = None
 
@@ -22,10 +23,10 @@ def lib():
     if _lib is None:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         if (not os.path.exists(OUT)
-                or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
+                or os.path.getmtime(OUT) < max(os.path.getmtime(f) for f in SRCS + CORES)):
             # -ffp-contract=off: the float rule divides, it must not be fused with anything
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                            "-o", OUT, SRC], check=True)
+                            "-o", OUT] + SRCS, check=True)
         _lib = C.CDLL(OUT)
         _lib.emul_canonical_float.restype = C.c_uint32
     return _lib
@@ -75,3 +76,31 @@ def canonical_float(s: bytes):
     out = C.c_float(0)
     r = lib().emul_canonical_float(s, C.c_uint32(len(s)), C.byref(out))
     return r, out.value
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def dot_vertex_lines(names, vstate, first=0, scaffold_only=False):
+    """.dot lines of vertices [first, first + len(vstate)) -> bytes (None: state out of range)"""
+    blob, off = pack_names(names)
+    vs = np.ascontiguousarray(vstate, np.uint8)
+    cap = 64 * len(vs) + len(blob) + 16
+    out = C.create_string_buffer(cap)
+    n = C.c_uint64(0)
+    rc = lib().emul_dot_vertex_lines(C.c_int(int(scaffold_only)), C.c_uint64(first), C.c_uint64(len(vs)), _vp(vs),
+                                     blob, _vp(off), out, C.c_uint64(cap), C.byref(n))
+    return None if rc else out.raw[:n.value]
+
+
+def dot_edge_lines(src, dst, dist, estate, sense, scaffold_only=False):
+    a = [np.ascontiguousarray(src, np.uint32), np.ascontiguousarray(dst, np.uint32),
+         np.ascontiguousarray(dist, np.int32), np.ascontiguousarray(estate, np.uint8),
+         np.ascontiguousarray(sense, np.uint8)]
+    cap = 105 * len(a[0]) + 16
+    out = C.create_string_buffer(cap)
+    n = C.c_uint64(0)
+    rc = lib().emul_dot_edge_lines(C.c_int(int(scaffold_only)), C.c_uint64(len(a[0])), *[_vp(x) for x in a],
+                                   out, C.c_uint64(cap), C.byref(n))
+    return None if rc else out.raw[:n.value]
