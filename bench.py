@@ -44,43 +44,69 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """nvidia-smi clocks + throttle reasons during the timed region.  The query loop is
+    started before the warm-up, start() returns once its first row has arrived (nvidia-smi
+    needs a few hundred ms to come up), and every row is stamped on arrival; the rows that fall
+    between begin() and end() are the ones reported.  A timed region shorter than nvidia-smi's
+    loop period can miss them all: then the rows of the warm-up (the same load) and the one
+    right after the region are used and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            deadline = time.monotonic() + 3.0          # first row = the loop is up (not timed)
+            while not self.rows and time.monotonic() < deadline:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.end()
+        if not any(self.t0 <= t <= self.t1 + 0.02 for t, _ in list(self.rows)):
+            n = len(self.rows)                   # nothing inside: wait for the next row
+            deadline = time.monotonic() + 0.5
+            while len(self.rows) == n and time.monotonic() < deadline:
+                time.sleep(0.01)
         self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        good = [(t, r) for t, r in list(self.rows) if len(r) >= 9 and r[1].isdigit()]
+        rows = [r for t, r in good if self.t0 <= t <= self.t1 + 0.02]
+        window = "timed region"
+        if not rows:
+            rows = [r for t, r in good]
+            window = "warm-up .. right after the timed region (region shorter than the sampling period)"
+        sm = sorted(int(r[1]) for r in rows)
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 _emit = print
@@ -203,18 +229,20 @@ def run_b200_arm(args, pkg):
         torch.cuda.synchronize(dev)
 
     set_device_inputs()
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     launches0 = g.stats()["kernel_launches"]
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     barrier()
+    sampler.end()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     st = g.stats()
