@@ -2,7 +2,7 @@
  *
  * Array-level entry points: plain pointers and sizes, no GenomeTools and no
  * torch types.  They are what the reference's three hot-path functions bind to
- * (the binding itself is include/gtscaffold_dropin.h + INTEGRATION.md):
+ * (the binding itself is integration/gt_scaffolder_b200.c):
  *
  *   gtsb_build         <- the insert/dedup loop of
  *                         gt_scaffolder_parser_read_distances
@@ -13,6 +13,13 @@
  *                         (gt_scaffolder_algorithms.c:160-166, 61-87)
  *   gtsb_filter        <- gt_scaffolder_graph_filter
  *                         (gt_scaffolder_algorithms.c:261-343, 174-258)
+ *
+ * and, on either side of that path,
+ *
+ *   gtsb_parse_de_host     <- the .de record loop (gt_scaffolder_parser.c:323-388)
+ *   gtsb_parse_astat_host  <- the .astat line loop (gt_scaffolder_algorithms.c:118-149)
+ *   gtsb_dot_*_lines_host  <- gt_scaffolder_graph_print_generic / _print_scaffold
+ *                             (gt_scaffolder_graph.c:269-343)
  *
  * All functions return 0 on success and -1 on error (message: gtsb_error), the
  * reference's own convention (gt_scaffolder_algorithms.c:112-113).  There is no
