@@ -34,7 +34,9 @@ PARAMS = [(0.01, 1.5, 400, 0.3, 20.0, True), (0.2, 2.5, 0, 0.5, 20.0, True)]
 
 def sequences(kind):
     """kind: 'one_line' (all records under one root, sense block first: what a .de line is),
-    'runs' (each root's records contiguous), 'any'."""
+    'lines' (each root's records contiguous, and no link that only the later of its two
+    lines lists: what the line-ordered build accepts), 'runs' (each root's records
+    contiguous), 'any'."""
     n = len(ALPHABET)
     out = [(a,) for a in range(n)]
     out += list(itertools.product(range(n), repeat=2))
@@ -53,12 +55,23 @@ def sequences(kind):
             last = r
         return True
 
+    def no_orphan(seq):
+        line_of = {}
+        for a in seq:
+            line_of.setdefault(ALPHABET[a][0], len(line_of))
+        listed = {(ALPHABET[a][0], ALPHABET[a][1]) for a in seq}
+        for r, c in listed:
+            if c in line_of and line_of[c] < line_of[r] and (c, r) not in listed:
+                return False
+        return True
+
     def one_line(seq):
         roots = {ALPHABET[a][0] for a in seq}
         senses = [ALPHABET[a][2] for a in seq]
         return len(roots) == 1 and senses == sorted(senses, reverse=True)
 
-    return [s for s in out if (one_line(s) if kind == "one_line" else runs_ok(s))]
+    keep = {"one_line": one_line, "runs": runs_ok, "lines": lambda q: runs_ok(q) and no_orphan(q)}[kind]
+    return [s for s in out if keep(s)]
 
 
 def components(synth, kind):
@@ -124,7 +137,7 @@ def test_restatement_equals_reference_on_every_small_case(kind, synth):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["one_line", "runs", "any"])
+@pytest.mark.parametrize("kind", ["one_line", "lines", "runs", "any"])
 def test_cuda_path_equals_oracle_on_every_small_case(pkg, synth, kind):
     inp = components(synth, kind)
     for params in PARAMS:
