@@ -146,7 +146,7 @@ def test_cuda_path_equals_oracle_on_every_small_case(pkg, synth, kind):
         for force_general in (False, True):
             g = pkg.ScaffoldGraphB200.new_from_records(inp, force_general=force_general)
             st = g.stats()
-            if kind == "one_line" and not force_general:
+            if kind in ("one_line", "lines") and not force_general:
                 assert st["line_ordered_build"] == 1, st            # the fast path is the one tested
             g.mark_repeats(cn_cut, a_cut, use_cn)
             g.filter(pc, cnc, oc)
