@@ -170,17 +170,39 @@ void ora_mark_repeats(OraGraph *g, int use_copy_num, float copy_num_cutoff,
 /* algorithms.c:174-193, with C's implicit conversions written out:
    float = long - long; float arithmetic for the variance; double for the
    quotient, sqrt and erf; each assignment narrows back to float. */
-int ora_ambiguousorder(int64_t dist1, float std1, int64_t dist2, float std2,
-                       float cutoff)
+int ora_ambiguous_interval(float interval, float cutoff)
 {
-  float expval, variance, interval, prob12, prob21, p_wrong;
-  expval = (float) (dist1 - dist2);
-  variance = 2 * ((std1 * std1) + (std2 * std2));
-  interval = (float) ((0 - expval) / sqrt(variance));
+  float prob12, prob21, p_wrong;                     /* algorithms.c:187-192 */
   prob12 = (float) (0.5 * (1 + erf(interval)));
   prob21 = (float) (1.0 - prob12);
   p_wrong = (float) (1.0 - (prob12 > prob21 ? prob12 : prob21));
   return p_wrong > cutoff;
+}
+
+/* the same for n intervals (tests of the device's threshold form of this decision) */
+void ora_ambiguous_intervals(const float *interval, uint64_t n, float cutoff, uint8_t *out)
+{
+  uint64_t i;
+  for (i = 0; i < n; i++)
+    out[i] = (uint8_t) ora_ambiguous_interval(interval[i], cutoff);
+}
+
+int ora_ambiguousorder(int64_t dist1, float std1, int64_t dist2, float std2,
+                       float cutoff)
+{
+  float expval, variance, interval;
+  expval = (float) (dist1 - dist2);
+  variance = 2 * ((std1 * std1) + (std2 * std2));
+  interval = (float) ((0 - expval) / sqrt(variance));
+  return ora_ambiguous_interval(interval, cutoff);
+}
+
+void ora_ambiguousorders(const int64_t *dist1, const float *std1, const int64_t *dist2, const float *std2,
+                         uint64_t n, float cutoff, uint8_t *out)
+{
+  uint64_t i;
+  for (i = 0; i < n; i++)
+    out[i] = (uint8_t) ora_ambiguousorder(dist1[i], std1[i], dist2[i], std2[i], cutoff);
 }
 
 /* algorithms.c:197-220; the mixed GtWord + GtUword sums wrap mod 2^64 */

@@ -43,6 +43,10 @@ OraGraph *ora_build(uint64_t nof_vertices, const uint64_t *seq_len,
 void ora_mark_repeats(OraGraph *g, int use_copy_num, float copy_num_cutoff,
                       float astat_cutoff);
 void ora_filter(OraGraph *g, float pcutoff, float cncutoff, int64_t ocutoff);
+int ora_ambiguous_interval(float interval, float cutoff);
+void ora_ambiguous_intervals(const float *interval, uint64_t n, float cutoff, uint8_t *out);
+void ora_ambiguousorders(const int64_t *dist1, const float *std1, const int64_t *dist2, const float *std2,
+                         uint64_t n, float cutoff, uint8_t *out);
 int ora_ambiguousorder(int64_t dist1, float std1, int64_t dist2, float std2,
                        float cutoff);
 int64_t ora_overlap(int64_t dist1, uint64_t len1, int64_t dist2, uint64_t len2);

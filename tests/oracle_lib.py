@@ -97,6 +97,10 @@ def port_lib():
         L.ora_build.argtypes = [C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64] + [C.c_void_p] * 6
         L.ora_mark_repeats.argtypes = [C.POINTER(_OraGraph), C.c_int, C.c_float, C.c_float]
         L.ora_filter.argtypes = [C.POINTER(_OraGraph), C.c_float, C.c_float, C.c_int64]
+        L.ora_ambiguousorders.restype = None
+        L.ora_ambiguousorders.argtypes = [C.c_void_p] * 4 + [C.c_uint64, C.c_float, C.c_void_p]
+        L.ora_ambiguous_intervals.restype = None
+        L.ora_ambiguous_intervals.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
         L.ora_ambiguousorder.restype = C.c_int
         L.ora_ambiguousorder.argtypes = [C.c_int64, C.c_float, C.c_int64, C.c_float, C.c_float]
         L.ora_overlap.restype = C.c_int64

@@ -67,3 +67,90 @@ def test_thresholds_reproduce_reference_decision(pkg, cutoff):
         else:
             got = t_neg >= 0 and -interval <= t_neg
         assert bool(exp) == bool(got), (d1, d2, s, interval, t_pos, t_neg)
+
+
+@pytest.mark.parametrize("cutoff", [0.01, 0.2, 0.3, 0.49, 0.4999999, 0.5, 0.0, -0.5, 1e-9, 1e-30, 0.05, 0.25,
+                                    float(np.float32(0.01) + np.float32(1e-9)), 0.999, 7.0])
+def test_thresholds_are_the_exact_step_of_the_reference_decision(pkg, cutoff):
+    """The device decides `|interval| <= t` instead of evaluating erf (gtsb_common.cuh,
+    ambiguous_order); t must be the LAST float for which algorithms.c:187-192 says
+    "ambiguous" -- checked on every float within 5000 ulps of both thresholds, on two million
+    random bit patterns (denormals, huge values, both zeros) and on inf / NaN."""
+    rc, t_pos, t_neg, inf_true = pkg.api.ambig_thresholds(cutoff)
+    assert rc == 0
+    P = O.port_lib()
+    rng = np.random.default_rng(11)
+    parts = [rng.integers(0, 2**32, 2_000_000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+             np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38, -3.4e38], np.float32)]
+    for t, sign in ((t_pos, 1.0), (t_neg, -1.0)):
+        if t >= 0 and np.isfinite(t):
+            b = int(np.float32(t).view(np.uint32))
+            near = np.arange(max(0, b - 5000), min(0x7F7FFFFF, b + 5000) + 1, dtype=np.int64)
+            parts.append((near.astype(np.uint32).view(np.float32) * np.float32(sign)).astype(np.float32))
+    x = np.ascontiguousarray(np.concatenate(parts), np.float32)
+    exp = np.zeros(len(x), np.uint8)
+    P.ora_ambiguous_intervals(x.ctypes.data, len(x), np.float32(cutoff), exp.ctypes.data)
+    neg = np.signbit(x)
+    with np.errstate(invalid="ignore"):
+        got = np.where(neg, (t_neg >= 0) & (-x <= np.float32(t_neg)), (t_pos >= 0) & (x <= np.float32(t_pos)))
+    got = np.where(np.isinf(x), bool(inf_true), got)
+    got = np.where(np.isnan(x), False, got)
+    bad = np.nonzero(got.astype(np.uint8) != exp)[0]
+    assert len(bad) == 0, (cutoff, t_pos, t_neg, inf_true, x[bad[:5]], exp[bad[:5]])
+    if 0 < cutoff < 0.5:
+        assert exp.sum() > 1000 and (exp == 0).sum() > 1000
+
+
+def device_ambiguous_order(d1, s1, d2, s2, t_pos, t_neg, inf_true):
+    """gtsb_common.cuh ambiguous_order, operation by operation in numpy (every CUDA intrinsic
+    there is a correctly rounded IEEE operation, so float32 / float64 numpy gives its bits)."""
+    f32, f64 = np.float32, np.float64
+    with np.errstate(all="ignore"):
+        expval = (d1 - d2).astype(f32)
+        variance = f32(2) * (s1 * s1 + s2 * s2)
+        x = f32(0) - expval
+        neg = x < 0
+        t = np.where(neg, f32(t_neg), f32(t_pos)).astype(f32)
+        c = (t * t).astype(f32)
+        fast = (t < f32(3.0e38)) & (variance > f32(1.0e-30)) & (variance < f32(1.0e30)) & (np.abs(x) < f32(1.0e15))
+        lhs = x * x
+        rhs = c * variance
+        band = rhs * f32(1.0e-5)
+        interval = (x.astype(f64) / np.sqrt(variance.astype(f64))).astype(f32)
+        exact = np.where(neg, -interval <= f32(t_neg), interval <= f32(t_pos))
+        exact = np.where(np.isinf(interval), bool(inf_true), exact)
+        exact = np.where(np.isnan(interval), False, exact)
+        out = np.where(fast & (lhs < rhs - band), True, np.where(fast & (lhs > rhs + band), False, exact))
+        return np.where(t >= 0, out, False)
+
+
+@pytest.mark.parametrize("cutoff", [0.01, 0.2, 0.3, 0.49, 0.5, 0.0, 1e-9, 0.05])
+def test_device_form_of_ambiguous_order_equals_the_reference(pkg, cutoff):
+    """the whole device decision -- squared fast path with its guard band, exact division
+    inside the band -- against algorithms.c:174-193 on pairs aimed at the threshold"""
+    rc, t_pos, t_neg, inf_true = pkg.api.ambig_thresholds(cutoff)
+    P = O.port_lib()
+    rng = np.random.default_rng(5)
+    n = 400_000
+    d1 = rng.integers(-5000, 5000, n).astype(np.int64)
+    s1 = rng.uniform(0.1, 80, n).astype(np.float32)
+    s2 = np.where(rng.random(n) < 0.3, np.float32(0), rng.uniform(0.1, 80, n)).astype(np.float32)
+    # d2 such that interval = -(d1 - d2) / sqrt(2 (s1^2 + s2^2)) lands within 1e-7 .. 1e-2 of +-t
+    t = np.where(rng.random(n) < 0.5, t_pos, -t_neg)
+    t = np.where(np.isfinite(t) & (np.abs(t) < 1e3), t, rng.normal(0, 2, n))
+    eps = rng.choice([0, 1e-7, -1e-7, 1e-6, -1e-6, 2e-5, -2e-5, 1e-3, -1e-3, 1e-2, -1e-2], n)
+    want = t * (1 + eps)
+    d2 = d1 + np.rint(want * np.sqrt(2 * (s1.astype(np.float64) ** 2 + s2.astype(np.float64) ** 2))).astype(np.int64)
+    # plus special values
+    s1[:50] = np.array([0, np.inf, np.nan, 1e-30, 1e30, 1e-20, 3e38, -1.0, 1e19, 1e-19] * 5, np.float32)
+    s2[:25] = 0
+    d2[:10] = d1[:10]
+    d1[10:20] = np.array([2**31 - 1, -2**31, 2**40, -2**40, 0, 1, -1, 2**24 + 1, 10**15, -10**15])
+    exp = np.zeros(n, np.uint8)
+    P.ora_ambiguousorders(d1.ctypes.data, s1.ctypes.data, d2.ctypes.data, s2.ctypes.data, n,
+                          np.float32(cutoff), exp.ctypes.data)
+    got = device_ambiguous_order(d1, s1, d2, s2, t_pos, t_neg, inf_true)
+    bad = np.nonzero(got.astype(np.uint8) != exp)[0]
+    assert len(bad) == 0, (cutoff, len(bad), d1[bad[:4]], d2[bad[:4]], s1[bad[:4]], s2[bad[:4]], exp[bad[:4]])
+    if 0 < cutoff < 0.5:
+        assert 1000 < exp.sum() < n - 1000
