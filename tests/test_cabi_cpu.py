@@ -154,3 +154,35 @@ def test_device_form_of_ambiguous_order_equals_the_reference(pkg, cutoff):
     assert len(bad) == 0, (cutoff, len(bad), d1[bad[:4]], d2[bad[:4]], s1[bad[:4]], s2[bad[:4]], exp[bad[:4]])
     if 0 < cutoff < 0.5:
         assert 1000 < exp.sum() < n - 1000
+
+
+def test_low_copy_number_pruning_never_drops_a_proposing_pair():
+    """k4_pairs_big (gtsb_filter.cu) evaluates only pairs with a member in the `low` list,
+    !(c > cut/2 + |cut/2| * 1e-6 + 1e-30) in float32.  Whenever the reference's test
+    fl(c1 + c2) < cut (algorithms.c:233) holds, the smaller of the two must be in that list."""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    n = 4_000_000
+    cuts = np.concatenate([rng.uniform(-3, 6, n // 2), 10.0 ** rng.uniform(-44, 38, n // 4),
+                           -(10.0 ** rng.uniform(-44, 38, n // 4))]).astype(f32)
+    cuts[:8] = np.array([1.5, 2.5, 0.0, -0.0, np.inf, -np.inf, 3.4e38, 1e-45], f32)
+    half = cuts * f32(0.5)
+    with np.errstate(all="ignore"):
+        bound = half + np.abs(half) * f32(1e-6) + f32(1e-30)
+        # pairs aimed at the boundary: c1 just above / below cut/2, c2 >= c1 so that the sum sits at the cut
+        ulps = rng.integers(-40, 41, n)
+        c1 = (half.view(np.int32) + np.where(half >= 0, ulps, -ulps)).astype(np.int32).view(f32)
+        c1 = np.where(rng.random(n) < 0.2, (half.astype(np.float64) * (1 + rng.normal(0, 3e-6, n))).astype(f32), c1)
+        c2 = (cuts.astype(np.float64) - c1.astype(np.float64)).astype(f32)
+        c2 = (c2.view(np.int32) + rng.integers(-3, 4, n)).astype(np.int32).view(f32)
+        c2 = np.where(rng.random(n) < 0.1, c1, c2)
+        special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, -1e-45, 3.4e38], f32)
+        k = rng.random(n) < 0.02
+        c2 = np.where(k, special[rng.integers(0, 8, n)], c2)
+        lo = np.where(c1 < c2, c1, c2)                    # either order: the list holds slots, not roles
+        lo = np.where(np.isnan(c1) | np.isnan(c2), np.nan, lo).astype(f32)
+        proposes = (c1 + c2) < cuts
+        in_low_1, in_low_2 = ~(c1 > bound), ~(c2 > bound)
+    dropped = proposes & ~(in_low_1 | in_low_2)
+    assert proposes.sum() > n // 10 and (~proposes).sum() > n // 10
+    assert dropped.sum() == 0, (cuts[dropped][:4], c1[dropped][:4], c2[dropped][:4])
