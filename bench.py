@@ -54,11 +54,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, enabled=True):
         self.idx, self.rows, self.proc = gpu_index, [], None
         self.t0 = self.t1 = None
+        self.enabled = enabled                   # only the rank that prints the line samples
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -229,7 +232,7 @@ def run_b200_arm(args, pkg):
         torch.cuda.synchronize(dev)
 
     set_device_inputs()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=(rank == 0))
     sampler.start()
     for _ in range(args.warmup):
         step()
