@@ -2,6 +2,7 @@
 #include "gtsb_context.h"
 #include "gtsb_scan.cuh"
 #include "gtsb_threshold.h"
+#include <stdlib.h>
 
 using namespace gtsb;
 
@@ -139,6 +140,32 @@ int await_records(gtsb_context *c) {
     c->records_pending = false;
   }
   return 0;
+}
+
+void l2_pin(gtsb_context *c, const void *p, size_t bytes) {
+  if (!c->l2_mode || c->l2_persist_max == 0 || p == nullptr || bytes == 0) return;
+  cudaStreamAttrValue v{};
+  const size_t win = bytes < c->l2_window_max ? bytes : c->l2_window_max;
+  v.accessPolicyWindow.base_ptr = const_cast<void *>(p);
+  v.accessPolicyWindow.num_bytes = win;
+  // a window larger than the set-aside keeps a random subset of its lines instead of thrashing
+  const double r = (double) c->l2_persist_max / (double) win;
+  v.accessPolicyWindow.hitRatio = r >= 1.0 ? 1.0f : (float) r;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  c->l2_pinned = true;
+}
+
+void l2_unpin(gtsb_context *c) {
+  if (!c->l2_pinned) return;
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.num_bytes = 0;
+  cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+  c->l2_pinned = false;
 }
 
 // the copy stream may only start once the main stream is done with the buffers it overwrites
@@ -571,7 +598,9 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   CK(cudaMemsetAsync(c->fstat.p, 0x0C, V + 1, s));      // rows without slots: decided, nothing fires
   // phase 1: who proposes whom (+ the static overlap answer of every small row)
   launch_vertex_facts(a, fused ? 1 : 0, cn_cutoff, astat_cutoff, use_cn, s);
+  l2_pin(c, a.vinfo, (size_t) V * sizeof(uint2));
   launch_pairs(a, s);
+  l2_unpin(c);
   c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   if (read_counters(c) != 0) return -1;
   if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
@@ -627,7 +656,9 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
     n_in = n_next;
   }
   launch_vres(a, s);
+  l2_pin(c, a.vres, (size_t) V * 4);
   launch_finalize(a, s);
+  l2_unpin(c);
   c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   CK(cudaGetLastError());
   return 0;
@@ -694,7 +725,27 @@ int gtsb_create(gtsb_context **out, int device) {
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return -1; }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    c->sm_count = prop.multiProcessorCount;
+    const char *e = getenv("GTSB_L2_PIN");
+    c->l2_mode = e != nullptr ? atoi(e) : 1;
+    if (c->l2_mode && prop.persistingL2CacheMaxSize > 0) {
+      // set-aside for persisting lines: a share of L2 the gathered per-vertex tables may keep
+      size_t want = (size_t) prop.persistingL2CacheMaxSize;
+      const char *f = getenv("GTSB_L2_PIN_MB");
+      if (f != nullptr && (size_t) atol(f) * 1048576 < want) want = (size_t) atol(f) * 1048576;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        c->l2_persist_max = want;
+        c->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    if (getenv("GTSB_TRACE") != nullptr)
+      fprintf(stderr, "[gtsb] L2 %d MB, persisting max %d MB, window max %d MB, pin %zu MB\n",
+              prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20,
+              c->l2_persist_max >> 20);
+  }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming) != cudaSuccess ||

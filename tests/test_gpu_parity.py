@@ -280,6 +280,55 @@ def test_full_size_properties_c3(pkg, synth):
     torch.cuda.empty_cache()
 
 
+def _full_size_vs_reference(pkg, synth, name, **kw):
+    """One named config at FULL size: the CUDA path (device-resident inputs, gtsb_pipeline) against
+    the compiled, unmodified reference run on the box's host (oracle/_ref; the C restatement if
+    absent) on the same arrays: every edge attribute and state in graph->edges[] order, the
+    adjacency order of every vertex, every vertex state."""
+    import time
+    import torch
+    t = synth.generate_torch(name, device="cuda", **kw)
+    V, R = int(t["seq_len"].shape[0]), int(t["root"].shape[0])
+    inp = synth.torch_to_input(t)
+    g = pkg.ScaffoldGraphB200()
+    g.set_vertices_device(V, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
+    g.set_records_device(R, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
+                         t["std_dev"].data_ptr(), t["flags"].data_ptr())
+    g.pipeline(*[DEFAULT[k] for k in ("cn_cut", "a_cut", "use_cn", "pc", "cnc", "oc")])
+    got, st = g.result(), g.stats()
+    g.close()
+    del t
+    torch.cuda.empty_cache()
+    t0 = time.time()
+    ref = O.best_oracle().build(inp)
+    ref.mark_repeats(DEFAULT["cn_cut"], DEFAULT["a_cut"], use_copy_num=DEFAULT["use_cn"])
+    ref.filter(DEFAULT["pc"], DEFAULT["cnc"], DEFAULT["oc"])
+    sec = time.time() - t0
+    exp = ref.result()
+    ref.close()
+    print(f"{name}: V={V} R={R} E={len(exp['src'])} reference {sec:.1f} s on one host core; "
+          f"device stats {st}")
+    _cmp(got, exp, name + " at full size")
+    # the filter did real work at this size
+    assert (exp["estate"] == 1).sum() > 0 and (exp["estate"] == 2).sum() > 0 and (exp["vstate"] == 1).sum() > 0
+    return st
+
+
+def test_full_size_c3_vs_reference(pkg, synth):
+    """BASELINE.json config 3 as named: 10^7 contigs, ~8*10^7 directed edges (algorithms.c:261-343
+    and parser.c:357-379 run by the reference itself, ~25 s and ~5 GB on the host)."""
+    st = _full_size_vs_reference(pkg, synth, "c3_human")
+    assert st["nof_vertices"] == 10_000_000 and st["line_ordered_build"] == 1
+
+
+def test_full_size_c4_hubs_vs_reference(pkg, synth):
+    """BASELINE.json config 4 as named: 5*10^6 contigs, power-law degrees with hubs of up to 10^4
+    edges (the reference's O(d^2) paths: find_edge in parser.c:359, the pair loops of
+    algorithms.c:283-320, mark_edge's twin scan :61-73)."""
+    st = _full_size_vs_reference(pkg, synth, "c4_repeat_hubs", max_deg=10_000)
+    assert st["nof_vertices"] == 5_000_000 and st["max_degree"] > 5_000
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_special_values(pkg, synth, seed):
     """NaN / inf / zero / denormal std_dev and copy numbers, NaN a-statistics, extreme
