@@ -33,7 +33,28 @@ UNIT = "edges/s"
 PARAMS = dict(copy_num_cutoff=0.3, astat_cutoff=20.0, use_copy_num=True,     # test.c:35-42
               pcutoff=0.01, cncutoff=1.5, ocutoff=400)
 B_E, B_V = 62, 19       # algorithmic bytes per directed edge / per vertex
-STAGE_BYTES = {"build": 34, "mark_repeats": 5, "filter": 23}
+
+
+def kernel_bytes(name, V, R, E, M):
+    """Compulsory bytes of ONE kernel: every column it must read or write once,
+    V vertices, R records, E slots, M mail entries (= twin-created slots).  None: not a streaming
+    kernel (worklists, fix-point sweeps, collectives)."""
+    n = name.split("(")[0]
+    table = {
+        "k3_lines": 8 * V + 12 * V, "k2_heads": 2 * 4 * R + 12 * V, "k2_lineless": 9 * V,
+        "k3_classify": (4 + 4) * R + (1 + 4) * R,                 # ctg + position gather in, rf + pc out
+        "k3_partition": 14 * R + 20 * M,                          # pc, std_dev, dist, flags, rf in; mail out
+        "k3_fine_hist": 4 * M, "k3_deliver": 20 * M + 17 * M,
+        "k3_resolve": 14 * R + 17 * M + 21 * E + 4 * V,           # records + mail in, slot columns + row_ptr out
+        "k4_pack_windows": 2 * 4 * V + 4 * (E // 26),
+        "k4_vertex_facts": 16 * V + 9 * V,                        # vid, seq_len, copy_num, astat in; vinfo + pred out
+        "k5_pairs": (13 + 8) * E + 4 * V + 8 * V + V,             # slot columns + vinfo gather; row_ptr, own vinfo, gbits
+        "k4_fire_init": 4 * V + 8 * V + 4 * V + 2 * V + 2 * V,
+        "k4_fire_dense": (9 + 1) * E + 2 * V, "k5_fire_dense": (5 + 1) * E + 4 * V + 2 * V,
+        "k4_vres": 4 * V + V + 4 * V,
+        "k4_finalize": (9 + 4) * E + E, "k5_finalize": (5 + 4) * E + E + 4 * V + 4 * V,
+    }
+    return table.get(n)
 
 
 def peaks():
@@ -122,7 +143,65 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_reference_leg(pkg, workload, sample_vertices, line_order, steps=1, warmup=0):
+def device_lines(torch, root):
+    """(line_root, line_start) of a file-ordered root column, on the device (input plumbing)."""
+    R = int(root.shape[0])
+    brk = torch.nonzero(root[1:] != root[:-1]).flatten() + 1
+    start = torch.cat([torch.zeros(1, dtype=brk.dtype, device=brk.device), brk,
+                       torch.tensor([R], dtype=brk.dtype, device=brk.device)]).to(torch.int32)
+    return root[start[:-1].long()].contiguous(), start.contiguous()
+
+
+def parity_check(pkg, torch, dist, rank, world, local, uid, args, ref_result):
+    """The product path (partitioned over `world` ranks when world > 1) on the CPU leg's sample
+    graph against the reference's result on the same arrays: vertex states on every rank, and --
+    merged by eid on rank 0 -- every edge's endpoints, attributes and state."""
+    import numpy as np
+    t = pkg.synth.generate_torch(args.workload, V=args.cpu_sample_vertices, device=torch.device("cuda", local),
+                                 line_order=args.line_order)
+    inp = pkg.synth.torch_to_input(t)
+    g = pkg.ScaffoldGraphB200(device=local)
+    mine = inp
+    if world > 1:
+        g.dist_init(rank, world, uid)
+        mine = pkg.api.shard_lines(inp, world, rank)
+    g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+    g.set_records(mine.root, mine.ctg, mine.dist, mine.std_dev, mine.flags)
+    P = PARAMS
+    g.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"], P["cncutoff"], P["ocutoff"])
+    part, vstate = g.edges(), g.vstate()
+    g.close()
+    parts = [part]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+    if rank != 0:
+        return None
+    e = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    order = np.argsort(e["eid"], kind="stable")
+    bad = []
+    if not np.array_equal(e["eid"][order], np.arange(len(order), dtype=np.uint32)) or len(order) != len(ref_result["src"]):
+        bad.append("eid")
+    else:
+        for k in ("src", "dst", "dist", "std_dev", "flags", "estate"):
+            a = e[k][order]
+            b = ref_result[k]
+            if k == "flags":
+                a = a & 3
+            if k == "std_dev":
+                a, b = a.view(np.uint32), np.asarray(b, np.float32).view(np.uint32)
+            if not np.array_equal(a.astype(np.int64), np.asarray(b).astype(np.int64)):
+                bad.append(k)
+        if not np.array_equal(vstate, ref_result["vstate"]):
+            bad.append("vstate")
+    return {"parity_check": "ok" if not bad else "MISMATCH in " + ",".join(bad),
+            "parity_sample": f"{args.workload} at V={args.cpu_sample_vertices} (E={len(order)}), "
+                             f"{'single device' if world == 1 else 'partitioned over %d ranks' % world} vs the "
+                             "reference's result on the same arrays: every edge by eid (endpoints, dist, std_dev, "
+                             "flags, state) and every vertex state"}
+
+
+def cpu_reference_leg(pkg, workload, sample_vertices, line_order, steps=1, warmup=0, want_result=False):
     """The reference's own C (oracle/_ref) -- or the C port when oracle/_ref is
     absent -- single-threaded on one host core, on a bounded sample."""
     import oracle_lib as O
@@ -140,6 +219,8 @@ def cpu_reference_leg(pkg, workload, sample_vertices, line_order, steps=1, warmu
         g.filter(PARAMS["pcutoff"], PARAMS["cncutoff"], PARAMS["ocutoff"])
         dt = time.perf_counter() - t0
         E = g.E
+        if want_result and it == warmup + steps - 1:
+            cpu_reference_leg.result = g.result()
         g.close()
         if it >= warmup:
             times.append(dt)
@@ -184,12 +265,14 @@ def run_b200_arm(args, pkg):
     # ---- workload.  N = 1: one graph of the named shape.  N > 1: weak scaling on ONE graph of
     # N x that many contigs, its .de lines cut into N chunks (rank r = r-th chunk of the file),
     # rows partitioned accordingly, NCCL exchanges inside gtsb_pipeline.
+    # --scaling strong: ONE graph of the config's size whatever N (BASELINE.json config 5: 10^8 contigs).
     V = args.vertices
     if world == 1:
         t = pkg.synth.generate_torch(args.workload, V=V, device=dev, line_order=args.line_order)
     else:
         Vper = V if V is not None else pkg.synth.CONFIGS[args.workload][1]
-        full = pkg.synth.generate_torch(args.workload, V=Vper * world, device=dev, line_order=args.line_order)
+        Vtot = Vper * world if args.scaling == "weak" else Vper
+        full = pkg.synth.generate_torch(args.workload, V=Vtot, device=dev, line_order=args.line_order)
         Rg = int(full["root"].shape[0])
         fr = pkg.api.chunk_fractions(world)            # later chunks receive more mail: cut them shorter
         cuts = [0]
@@ -216,10 +299,19 @@ def run_b200_arm(args, pkg):
         g.dist_init(rank, world, uid)
     P = PARAMS
 
+    # records in the shape a .de tokeniser leaves them in (one root + first record per line,
+    # parser.c:323-388): what gtsb_parse_de_host produces and what the e2e leg uploads
+    lines = device_lines(torch, t["root"])
+
     def set_device_inputs():
         g.set_vertices_device(Vn, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
-        g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
-                             t["std_dev"].data_ptr(), t["flags"].data_ptr())
+        if world == 1 and args.records == "lines":
+            g.set_record_lines_device(int(lines[0].shape[0]), lines[0].data_ptr(), lines[1].data_ptr(), Rn,
+                                      t["ctg"].data_ptr(), t["dist"].data_ptr(), t["std_dev"].data_ptr(),
+                                      t["flags"].data_ptr())
+        else:
+            g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
+                                 t["std_dev"].data_ptr(), t["flags"].data_ptr())
 
     def step():
         g.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
@@ -324,42 +416,58 @@ def run_b200_arm(args, pkg):
     ms_step, e2e_ms = float(vals[0]), float(vals[1])
     E_all, V_all = float(tot[0]), float(tot[1])
     if rank != 0:
+        parity_check(pkg, torch, dist, rank, world, local, uid, args, None)
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
     alg_bytes = B_E * E_all / world + B_V * Vn / world  # per GPU (mean over the ranks)
+    # The headline fraction is the PIPELINE's: algorithmic bytes of build + mark_repeats + filter
+    # (62 E + 19 V) over the whole device-timed step.  Each kernel is listed with its
+    # OWN compulsory bytes over its own CUDA-event time; `kernel` names the one with the largest time.
+    M = E // 2
+    per_kernel = {}
+    for k, (ms, _calls) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        if k.startswith("PHASE_"):
+            continue
+        b = None if world > 1 else kernel_bytes(k, Vn, Rn, int(E), int(M))
+        per_kernel[k] = {"ms": round(ms, 4)}
+        if b and ms > 0:
+            per_kernel[k].update({"bytes": int(b), "gbs": round(b / (ms * 1e-3) / 1e9, 1),
+                                  "frac": round(b / (ms * 1e-3) / 1e9 / peak, 4)})
     comp = {k: v for k, v in kern.items() if not k.startswith(("nccl_", "PHASE_"))}
     dom = max(comp.items(), key=lambda kv: kv[1][0]) if comp else ("n/a", (float("nan"), 0))
-    stage_of = lambda n: ("mark_repeats" if "repeat" in n else
-                          "filter" if any(x in n for x in ("pairs", "poly", "overlap", "fire", "finalize"))
-                          else "build")
-    dom_bytes = STAGE_BYTES[stage_of(dom[0])] * E      # the stage's compulsory bytes
-    dom_ms = dom[1][0]
-    roofline = {"bound": "hbm", "kernel": dom[0], "stage": stage_of(dom[0]),
-                "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms == dom_ms and dom_ms > 0 else None,
-                "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
-                "kernel_ms_per_step": dom_ms,
-                "pipeline": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms_step * 1e-3) / 1e9,
-                             "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
-                "kernels_ms_per_step": {k: round(v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}}
-    roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
-    # DRAM bytes of that kernel from the committed `ncu --set full` capture of the same workload
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                "what": "pipeline: (62 E + 19 V) bytes / device time of the whole step",
+                "kernel": dom[0], "kernel_ms_per_step": dom[1][0],
+                "kernel_frac": per_kernel.get(dom[0], {}).get("frac"),
+                "traffic": None, "kernels": per_kernel}
+    # DRAM bytes per launch of every kernel from the committed `ncu --set full` capture of this workload
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if world == 1 and os.path.exists(tp):
         tr = json.load(open(tp))
         if tr.get("workload") == args.workload and tr.get("vertices") == Vn:
-            roofline["traffic"] = tr.get("dram_bytes_per_launch", {}).get(dom[0].split("(")[0])
+            per = tr.get("dram_bytes_per_launch", {})
+            roofline["traffic"] = per.get(dom[0].split("(")[0])
+            roofline["traffic_all_kernels"] = tr.get("dram_bytes_per_step")
             roofline["traffic_source"] = tr.get("source")
+            for k in per_kernel:
+                if k.split("(")[0] in per:
+                    per_kernel[k]["dram_bytes"] = per[k.split("(")[0]]
 
-    cb, _, _ = cpu_reference_leg(pkg, args.workload, args.cpu_sample_vertices, args.line_order)
+    cb, _, _ = cpu_reference_leg(pkg, args.workload, args.cpu_sample_vertices, args.line_order, want_result=True)
+    pc = parity_check(pkg, torch, dist, rank, world, local, uid, args, cpu_reference_leg.result)
     line = {"metric": METRIC, "value": E_all / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "u32/i32/f32 (+i64,f64 in the exact slow path)", "data": "synthetic",
             "config": {"workload": args.workload, "vertices_per_gpu": Vn // world, "records_per_gpu": Rn,
                        "edges_per_gpu": int(E), "line_order": args.line_order,
+                       "records": ("line-shaped (root + first record per .de line, 13 B/record + 8 B/line)"
+                                   if world == 1 and args.records == "lines" else "flat (17 B/record)"),
                        "graph": ("one graph" if world == 1 else
                                  f"one graph of {Vn} contigs partitioned over {world} ranks by .de line chunk; "
                                  "NCCL all-to-all (mail) and allgathers (vertex facts) inside the timed step"),
@@ -368,7 +476,9 @@ def run_b200_arm(args, pkg):
             "e2e": {"value": E_all / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
-            "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds")}}
+            "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds",
+                                         "line_ordered_build", "fallback_reason")}}
+    line.update(pc)
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -389,6 +499,10 @@ def main():
     ap.add_argument("--vertices", type=int, default=None, help="override the config's vertex count (per GPU)")
     ap.add_argument("--line-order", default="shuffled", choices=["shuffled", "id"])
     ap.add_argument("--cpu-sample-vertices", type=int, default=2_000_000)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N x the config's contigs in one graph, strong = the config's size whatever N")
+    ap.add_argument("--records", default="lines", choices=["lines", "flat"],
+                    help="device-resident record input of the timed step at N = 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -34,7 +34,7 @@ EXPORTS = [
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
-    "gtsb_set_record_lines_host", "gtsb_get_edge_states",
+    "gtsb_set_record_lines_host", "gtsb_set_record_lines_device", "gtsb_get_edge_states",
     "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
     "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host",
 ]
@@ -98,6 +98,7 @@ def load_library():
     L.gtsb_dist_init.argtypes = [vp, i32, i32, vp]
     L.gtsb_get_edges.argtypes = [vp, C.POINTER(u64)] + [vp] * 7
     L.gtsb_set_record_lines_host.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
+    L.gtsb_set_record_lines_device.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
     L.gtsb_get_edge_states.argtypes = [vp, vp]
     L.gtsb_set_vertex_names_host.argtypes = [vp, u64, C.c_char_p, vp]
     L.gtsb_parse_de_host.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
@@ -298,6 +299,10 @@ class ScaffoldGraphB200:
     def set_records_device(self, R, root_ptr, ctg_ptr, dist_ptr, std_ptr, flags_ptr):
         self._ck(self.L.gtsb_set_records_device(self.h, int(R), root_ptr, ctg_ptr, dist_ptr, std_ptr,
                                                 flags_ptr))
+
+    def set_record_lines_device(self, L, line_root_ptr, line_start_ptr, R, ctg_ptr, dist_ptr, std_ptr, flags_ptr):
+        self._ck(self.L.gtsb_set_record_lines_device(self.h, int(L), line_root_ptr, line_start_ptr, int(R), ctg_ptr,
+                                                     dist_ptr, std_ptr, flags_ptr))
 
     def set_graph(self, row_ptr, dst, dist, std_dev, flags, seq_len, astat, copy_num, vstate, estate):
         a = [np.ascontiguousarray(row_ptr, np.uint32), np.ascontiguousarray(dst, np.uint32),

@@ -285,6 +285,19 @@ int ensure_rows(gtsb_context *c, uint64_t R) {
   return 0;
 }
 
+// root column of records that were handed in as lines (the general build and the
+// rank-partitioned build read it); made on demand
+int ensure_root_column(gtsb_context *c) {
+  if (c->have_root_column || c->R == 0) return 0;
+  if (!c->root.owned) c->root = DevBuf();
+  ENSURE(c->root, c->R * 4);
+  k_expand_roots<<<(uint32_t) ((c->n_lines + 255) / 256), 256, 0, c->stream>>>(
+      (uint32_t) c->n_lines, c->line_root.as<uint32_t>(), c->line_start.as<uint32_t>(), c->root.as<uint32_t>());
+  c->stats.kernel_launches++;
+  c->have_root_column = true;
+  return 0;
+}
+
 // The line-ordered fast path (gtsb_build2.cu).  Returns 1 if the input is
 // outside its preconditions (caller runs the general path), 0 on success.
 int do_build_lines(gtsb_context *c) {
@@ -375,7 +388,14 @@ int do_build_lines(gtsb_context *c) {
   a.eflags = c->eflags.as<uint8_t>();
 
   if (ensure_windows(c, V, 2 * R) != 0) return -1;
-  c->stats.kernel_launches += launch_build2_lines(a, s);
+  if (c->have_lines) {                          // lines handed in as such: no need to find them in a root column
+    a.line_root = c->line_root.as<uint32_t>();
+    a.line_start = c->line_start.as<uint32_t>();
+    a.n_lines = (uint32_t) c->n_lines;
+    c->stats.kernel_launches += launch_b3_lines(a, s);
+  } else {
+    c->stats.kernel_launches += launch_build2_lines(a, s);
+  }
   c->stats.kernel_launches += launch_build2_classify(a, s);
   if (await_records(c) != 0) return -1;          // dist/std_dev/flags may still be on their way (copy stream)
   c->stats.kernel_launches += launch_build2_rows(a, s);
@@ -422,6 +442,7 @@ int do_build(gtsb_context *c) {
   c->line_layout = false;
   c->csr_exported = false;
   if (await_records(c) != 0) return -1;
+  if (ensure_root_column(c) != 0) return -1;
 
   ENSURE(c->cnt, (V + 1) * 4);
   ENSURE(c->bptr, (V + 1) * 4);
@@ -728,7 +749,7 @@ int gtsb_create(gtsb_context **out, int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
     c->sm_count = prop.multiProcessorCount;
     const char *e = getenv("GTSB_L2_PIN");
-    c->l2_mode = e != nullptr ? atoi(e) : 1;
+    c->l2_mode = e != nullptr ? atoi(e) : 0;   // measured slower on C3 (profiles/r02_l2_persistence_experiment.json)
     if (c->l2_mode && prop.persistingL2CacheMaxSize > 0) {
       // set-aside for persisting lines: a share of L2 the gathered per-vertex tables may keep
       size_t want = (size_t) prop.persistingL2CacheMaxSize;
@@ -869,6 +890,8 @@ int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, con
   }
   c->R = R;
   c->have_records = true;
+  c->have_root_column = true;
+  c->have_lines = false;
   c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;
@@ -880,10 +903,10 @@ int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line
   if (c == nullptr) return -1;
   CK(cudaSetDevice(c->device));
   if (R >= 0xFFFFFFF0ull || L > R) return fail(c, "gtsb_set_record_lines_host: bad sizes");
-  DevBuf *bs[] = {&c->root, &c->ctg, &c->dist, &c->std_dev, &c->flags};
+  if (await_records(c) != 0) return -1;      // an earlier late copy into the same buffers
+  DevBuf *bs[] = {&c->ctg, &c->dist, &c->std_dev, &c->flags, &c->line_root, &c->line_start};
   for (DevBuf *b : bs)
     if (!b->owned) *b = DevBuf();
-  ENSURE(c->root, R * 4);
   ENSURE(c->ctg, R * 4);
   ENSURE(c->dist, R * 4);
   ENSURE(c->std_dev, R * 4);
@@ -893,10 +916,6 @@ int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line
   if (R) {
     CK(cudaMemcpyAsync(c->line_root.p, line_root, L * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->line_start.p, line_start, (L + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    k_expand_roots<<<(uint32_t) ((L + 255) / 256), 256, 0, c->stream>>>((uint32_t) L, c->line_root.as<uint32_t>(),
-                                                                        c->line_start.as<uint32_t>(),
-                                                                        c->root.as<uint32_t>());
-    c->stats.kernel_launches++;
     CK(cudaMemcpyAsync(c->ctg.p, ctg, R * 4, cudaMemcpyHostToDevice, c->stream));
     // first needed by k2_partition: the line starts and the classification run under this copy
     if (copy_stream_follows_main(c) != 0) return -1;
@@ -907,7 +926,36 @@ int gtsb_set_record_lines_host(gtsb_context *c, uint64_t L, const uint32_t *line
     c->records_pending = true;
   }
   c->R = R;
+  c->n_lines = L;
   c->have_records = true;
+  c->have_lines = R != 0;
+  c->have_root_column = false;
+  c->have_num_pairs = false;
+  c->stats.nof_records = R;
+  return 0;
+}
+
+int gtsb_set_record_lines_device(gtsb_context *c, uint64_t L, const uint32_t *line_root, const uint32_t *line_start,
+                                 uint64_t R, const uint32_t *ctg, const int32_t *dist, const float *std_dev,
+                                 const uint8_t *flags) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (R >= 0xFFFFFFF0ull || L > R) return fail(c, "gtsb_set_record_lines_device: bad sizes");
+  if (c->records_pending) {                  // a late copy may still write the buffers adopt() frees
+    CK(cudaStreamSynchronize(c->copy_stream));
+    c->records_pending = false;
+  }
+  adopt(c->line_root, line_root);
+  adopt(c->line_start, line_start);
+  adopt(c->ctg, ctg);
+  adopt(c->dist, dist);
+  adopt(c->std_dev, std_dev);
+  adopt(c->flags, flags);
+  c->R = R;
+  c->n_lines = L;
+  c->have_records = true;
+  c->have_lines = R != 0;
+  c->have_root_column = false;
   c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;
@@ -928,6 +976,8 @@ int gtsb_set_records_device(gtsb_context *c, uint64_t R, const uint32_t *root, c
   adopt(c->flags, flags);
   c->R = R;
   c->have_records = true;
+  c->have_root_column = true;
+  c->have_lines = false;
   c->have_num_pairs = false;
   c->stats.nof_records = R;
   return 0;

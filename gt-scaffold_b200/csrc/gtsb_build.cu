@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(256) k_emit_csr(
     d = row_ptr[v + 1] - r0;
   }
   const bool big = d > BIG_ROW;
-  if (big) atomicMax(&counters[CNT_MAX_DEG], d);
+  {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, d);     // largest row of the graph (stats, hub scratch)
+    if (lane_id() == 0 && wmax) atomicMax(&counters[CNT_MAX_DEG], wmax);
+  }
   warp_append(big, v, big_rows, &counters[CNT_BIG_ROWS]);
   if (!big) {
     for (uint32_t k = 0; k < d; k++) {

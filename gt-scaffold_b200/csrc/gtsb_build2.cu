@@ -330,6 +330,17 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
     if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
   // creator rank in record order = k - k0[first line]: one block scan per 256 records
+  // Partitioned graph: the chunk's entries are first grouped by destination rank in shared memory
+  // and then stored by consecutive threads, so that what crosses NVLink are runs of whole entries
+  // (16-byte stores scattered over 8 peers moved ~300 GB/s per GPU; runs coalesce into full packets).
+  __shared__ uint4 s_sent[SEG_THREADS];
+  __shared__ uint32_t s_sdest[SEG_THREADS], s_cc[MAX_RANKS], s_co[MAX_RANKS + 1], s_cb[MAX_RANKS];
+  __shared__ uint8_t s_sbin[SEG_THREADS];
+  const bool remote = a.peer_ent != nullptr;
+  if (remote) {
+    for (uint32_t j = threadIdx.x; j < (uint32_t) a.nranks; j += blockDim.x) s_cc[j] = 0;
+    __syncthreads();
+  }
   uint32_t carry = a.k_base + a.k0[g.p0];
   for (uint32_t base = 0; base < g.n; base += blockDim.x) {
     const uint32_t r = base + threadIdx.x;
@@ -337,37 +348,67 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     uint32_t total;
     const uint32_t k = carry + block_excl_scan(creator ? 1u : 0u, &total);   // syncs: bin bases visible
     carry += total;
-    if (!creator) continue;
-    const uint32_t j = s_line[r], pc = s_pc[r];
-    // final flags of edge root->c: strict running maximum over the line's records
-    float best = s_std[r];
-    uint32_t bf = s_fl[r];
-    if (s_rf[r] & RF_DUP) {
-      const uint32_t rb = s_ls[j + 1] - g.rec0;
-      for (uint32_t t = r + 1; t < rb; t++)
-        if (s_pc[t] == pc && best < s_std[t]) {
-          best = s_std[t];
-          bf = s_fl[t];
-        }
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t pc = 0, b = 0;
+    if (creator) {
+      const uint32_t j = s_line[r];
+      pc = s_pc[r];
+      // final flags of edge root->c: strict running maximum over the line's records
+      float best = s_std[r];
+      uint32_t bf = s_fl[r];
+      if (s_rf[r] & RF_DUP) {
+        const uint32_t rb = s_ls[j + 1] - g.rec0;
+        for (uint32_t t = r + 1; t < rb; t++)
+          if (s_pc[t] == pc && best < s_std[t]) {
+            best = s_std[t];
+            bf = s_fl[t];
+          }
+      }
+      const uint32_t sf = s_fl[r];
+      e.x = k;
+      e.y = (a.pos_base + g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
+            ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u) |
+            ((s_rf[r] & RF_LT) ? 0u : M_LT);
+      e.z = (uint32_t) a.dist[g.rec0 + r];
+      e.w = __float_as_uint(s_std[r]);
+      b = bin_of(pc);
     }
-    const uint32_t sf = s_fl[r];
-    uint4 e;
-    e.x = k;
-    e.y = (a.pos_base + g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
-          ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u) |
-          ((s_rf[r] & RF_LT) ? 0u : M_LT);
-    e.z = (uint32_t) a.dist[g.rec0 + r];
-    e.w = __float_as_uint(s_std[r]);
-    const uint32_t b = bin_of(pc);
-    const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
-    if (a.peer_ent == nullptr) {
-      a.tmp_ent[at] = e;
-      a.tmp_dest[at] = pc;
-    } else {                                        // the receiving rank's memory
-      const long long to = (long long) at + a.peer_shift[b];
-      a.peer_ent[b][to] = e;
-      a.peer_dest[b][to] = pc;
+    if (!remote) {
+      if (creator) {
+        const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
+        a.tmp_ent[at] = e;
+        a.tmp_dest[at] = pc;
+      }
+      continue;
     }
+    const uint32_t lr = creator ? atomicAdd(&s_cc[b], 1u) : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (int o = 0; o < a.nranks; o++) {
+        s_co[o] = run;
+        run += s_cc[o];
+        s_cb[o] = s_bin[NB_COARSE + o] + s_bin[2 * NB_COARSE + o];     // this block's share of rank o, so far
+        s_bin[2 * NB_COARSE + o] += s_cc[o];
+      }
+      s_co[a.nranks] = run;
+    }
+    __syncthreads();
+    if (creator) {
+      const uint32_t idx = s_co[b] + lr;
+      s_sent[idx] = e;
+      s_sdest[idx] = pc;
+      s_sbin[idx] = (uint8_t) b;
+    }
+    __syncthreads();
+    if (threadIdx.x < s_co[a.nranks]) {
+      const uint32_t o = s_sbin[threadIdx.x];
+      const long long to = (long long) s_cb[o] + (threadIdx.x - s_co[o]) + a.peer_shift[o];
+      a.peer_ent[o][to] = s_sent[threadIdx.x];                          // the receiving rank's memory
+      a.peer_dest[o][to] = s_sdest[threadIdx.x];
+    }
+    if (threadIdx.x < (uint32_t) a.nranks) s_cc[threadIdx.x] = 0;
+    __syncthreads();
   }
 }
 
@@ -592,6 +633,27 @@ __global__ void __launch_bounds__(256) k2_count_mail(Build2Args a, uint32_t n) {
   }
 }
 
+// lines handed in as (root, first record): thread per line
+__global__ void __launch_bounds__(256) k3_lines(Build2Args a) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > a.n_lines) return;
+  if (l == a.n_lines) {
+    if (l <= a.V) a.ls[l] = (uint32_t) a.R;
+    a.tile_off[0] = a.n_lines;                     // where k2_lineless_assign reads the line count
+    return;
+  }
+  const uint32_t r = a.line_root[l], b = a.line_start[l], e = a.line_start[l + 1];
+  if (r >= a.Vg) {
+    atomicOr(&a.counters[CNT_ERROR], 1u);
+  } else if (l < a.V && b < e && e <= a.R) {
+    a.ls[l] = b;
+    a.vid[l] = r;
+    if (atomicExch(&a.pos[r], a.pos_base + l) != UNSET) raise(a.counters, FB_MULTIRUN);
+  } else {
+    raise(a.counters, FB_MULTIRUN);              // more lines than vertices, or an empty line
+  }
+}
+
 // ------------------------------------------------------------------ export to plain CSR
 
 __global__ void __launch_bounds__(256) k2_export_deg(uint32_t V, const uint32_t *__restrict__ pos,
@@ -645,6 +707,20 @@ static void build2_attrs() {
   cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
   cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
   attr_done = true;
+}
+
+int launch_b3_lines(const Build2Args &a, cudaStream_t s) {
+  {
+    KernelTimer t_("k3_lines", s);
+    k3_lines<<<(a.n_lines + 256) / 256, 256, 0, s>>>(a);
+  }
+  KernelTimer t_("k2_lineless(2 kernels+scan)", s);
+  const uint32_t vb = (a.V + 256) / 256;
+  k2_lineless_flags<<<vb, 256, 0, s>>>(a.V, a.pos, a.lineless_flag);
+  exclusive_scan<uint8_t>(a.lineless_flag, a.V, a.lineless_rank, a.scan_scratch, s);
+  k2_lineless_assign<<<vb, 256, 0, s>>>(a.V, a.R, a.tile_off, a.lineless_flag, a.lineless_rank, a.pos, a.vid, a.ls,
+                                        a.counters);
+  return 1 + 2 + 3;
 }
 
 int launch_b2_head_counts(const Build2Args &a, cudaStream_t s) {

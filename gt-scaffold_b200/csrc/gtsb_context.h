@@ -45,6 +45,9 @@ struct gtsb_context {
 
   uint64_t V = 0, R = 0, E = 0;
   bool have_vertices = false, have_records = false, have_graph = false;
+  bool have_lines = false;      // records were handed in as lines (line_root / line_start)
+  bool have_root_column = false;   // the per-record root column is current
+  uint64_t n_lines = 0;
   bool line_layout = false;     // rows in .de line order (rs/re/vid/pos) instead of plain CSR
   bool csr_exported = false;    // plain CSR copy of a line-layout graph is current
 
@@ -98,7 +101,7 @@ struct gtsb_context {
   uint64_t Vloc = 0;                // rows held by this rank (== V when world == 1)
 
   // L2 residency of the table a flat pass gathers from (access-policy window on the stream)
-  int l2_mode = 1;                  // GTSB_L2_PIN: 0 off, 1 on
+  int l2_mode = 0;                  // GTSB_L2_PIN: 0 off, 1 on
   size_t l2_persist_max = 0, l2_window_max = 0;
   bool l2_pinned = false;
 
@@ -121,6 +124,7 @@ int ensure_rows(gtsb_context *c, uint64_t R);
 int ensure_filter_buffers(gtsb_context *c, uint64_t Vg, uint64_t E, gtsb::FilterArgs &a);
 int await_vertices(gtsb_context *c);      // the main stream waits for late copies (no host sync)
 int await_records(gtsb_context *c);
+int ensure_root_column(gtsb_context *c);
 // keep [p, p + bytes) L2-resident for the kernels launched next on the stream (the slot columns a
 // flat pass streams are evict-first; the table it gathers from per slot should survive them)
 void l2_pin(gtsb_context *c, const void *p, size_t bytes);

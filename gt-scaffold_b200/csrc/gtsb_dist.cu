@@ -43,6 +43,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;   // optional (NCCL >= 2.18)
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -66,6 +67,7 @@ const char *load_nccl() {
   SYM(GetUniqueId, "ncclGetUniqueId")
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
+  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(h, "ncclCommSplit"));
   SYM(GetErrorString, "ncclGetErrorString")
   SYM(Broadcast, "ncclBroadcast")
   SYM(AllReduce, "ncclAllReduce")
@@ -81,7 +83,12 @@ const char *load_nccl() {
 
 struct DistState {
   ncclComm_t comm = nullptr;
-  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage, peer_tab, handles;
+  // exchanges that do not depend on the rows (contig ids by position, packed neighbour facts)
+  // run on a side stream with their own communicator, under the build
+  ncclComm_t comm2 = nullptr;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage, stage2, peer_tab, handles;
   uint32_t *h_small = nullptr;     // pinned, world * SMALL_N words
   // every rank's receive buffers, opened through CUDA IPC (peer memory over NVLink)
   void *peer_ptr[MAX_RANKS][2] = {};
@@ -114,26 +121,55 @@ int small_allgather(gtsb_context *c, const uint32_t *mine, int n, std::vector<ui
 // The slices differ in length, so they travel through a staging buffer of
 // equal-sized slots with ONE ncclAllGather (grouped per-rank broadcasts measured
 // ~4x slower on 8 GPUs) and are copied to their places afterwards.
-int allgatherv(gtsb_context *c, const char *what, void *buf, size_t es, const std::vector<uint64_t> &lo) {
+int allgatherv(gtsb_context *c, const char *what, void *buf, size_t es, const std::vector<uint64_t> &lo,
+               bool on_side = false) {
   DistState *D = static_cast<DistState *>(c->dstate);
-  KernelTimer t_(what, c->stream);
+  cudaStream_t st = on_side ? D->side : c->stream;
+  ncclComm_t comm = on_side ? D->comm2 : D->comm;
+  DevBuf &stage_buf = on_side ? D->stage2 : D->stage;
+  KernelTimer t_(what, st);
   const int N = c->world, me = c->rank;
   uint64_t slot = 0;
   for (int r = 0; r < N; r++) slot = lo[r + 1] - lo[r] > slot ? lo[r + 1] - lo[r] : slot;
   if (slot == 0) return 0;
   const size_t slot_bytes = ((size_t) slot * es + 15) & ~(size_t) 15;
-  ENSURE(D->stage, slot_bytes * N);
-  char *stage = D->stage.as<char>();
+  ENSURE(stage_buf, slot_bytes * N);
+  char *stage = stage_buf.as<char>();
   char *base = static_cast<char *>(buf);
   const size_t mine = (size_t) (lo[me + 1] - lo[me]) * es;
-  if (mine) CK(cudaMemcpyAsync(stage + slot_bytes * me, base + (size_t) lo[me] * es, mine, cudaMemcpyDeviceToDevice, c->stream));
-  NK(g_nccl.AllGather(stage + slot_bytes * me, stage, slot_bytes, ncclUint8, D->comm, c->stream));
+  if (mine) CK(cudaMemcpyAsync(stage + slot_bytes * me, base + (size_t) lo[me] * es, mine, cudaMemcpyDeviceToDevice, st));
+  NK(g_nccl.AllGather(stage + slot_bytes * me, stage, slot_bytes, ncclUint8, comm, st));
   for (int r = 0; r < N; r++) {
     const size_t bytes = (size_t) (lo[r + 1] - lo[r]) * es;
     if (r == me || bytes == 0) continue;
-    CK(cudaMemcpyAsync(base + (size_t) lo[r] * es, stage + slot_bytes * r, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(base + (size_t) lo[r] * es, stage + slot_bytes * r, bytes, cudaMemcpyDeviceToDevice, st));
   }
   return 0;
+}
+
+// Buffers whose size is a function of exchanged (rank-uniform) numbers grow on every rank in the
+// same step.  ensure_u notes that an allocation is attempted; the caller then ends the block
+// with a status exchange, so that a rank that runs out of memory stops ALL ranks there instead
+// of leaving them in the next collective.  Steps that allocate nothing exchange nothing.
+int ensure_u(gtsb_context *c, DevBuf &b, size_t bytes, bool &grew) {
+  if (bytes == 0) bytes = 16;
+  if (b.owned && b.cap >= bytes && b.p != nullptr) return 0;
+  grew = true;
+  return ensure(c, b, bytes);
+}
+#define ENSURE_U(buf, bytes)                                   \
+  do {                                                         \
+    if (ensure_u(c, buf, (bytes), grew) != 0) return -1;       \
+  } while (0)
+
+// test hook: GTSB_FAIL_AT="<rank>:<place>" makes that rank report an allocation failure at that place
+int injected_failure(gtsb_context *c, const char *place) {
+  const char *e = getenv("GTSB_FAIL_AT");
+  if (e == nullptr) return 0;
+  char want[64];
+  snprintf(want, sizeof want, "%d:%s", c->rank, place);
+  if (strcmp(e, want) != 0) return 0;
+  return fail(c, "injected failure at '%s' on rank %d (GTSB_FAIL_AT)", place, c->rank);
 }
 
 // Every rank contributes n words and its own status; any rank in trouble stops
@@ -265,12 +301,17 @@ namespace gtsbi {
 void dist_release(gtsb_context *c) {
   DistState *D = static_cast<DistState *>(c->dstate);
   if (D == nullptr) return;
+  if (D->side != nullptr) cudaStreamSynchronize(D->side);
+  if (D->comm2 != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(D->comm2);
   if (D->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(D->comm);
+  if (D->side != nullptr) cudaStreamDestroy(D->side);
+  for (cudaEvent_t e : {D->ev_fork, D->ev_join})
+    if (e != nullptr) cudaEventDestroy(e);
   for (int r = 0; r < c->world; r++)
     for (int k = 0; k < 2; k++)
       if (r != c->rank && D->peer_ptr[r][k] != nullptr) cudaIpcCloseMemHandle(D->peer_ptr[r][k]);
   for (DevBuf *b : {&D->small, &D->bounds, &D->rank_cnt, &D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage,
-                    &D->peer_tab, &D->handles})
+                    &D->stage2, &D->peer_tab, &D->handles})
     if (b->owned && b->p != nullptr) cudaFree(b->p);
   if (D->h_small != nullptr) cudaFreeHost(D->h_small);
   delete D;
@@ -308,7 +349,53 @@ struct Plan {                     // what the ranks agreed on while building
   uint32_t L = 0;                 // lines of this rank
   uint64_t L_total = 0;
   uint32_t own_lo = 0, Vloc = 0;
+  uint64_t E_max = 0;             // most slots held by one rank
+  uint32_t big_rows_max = 0, deg_max = 0;   // most rows > BIG_ROW on one rank, longest row anywhere
+  float cn_cutoff = 0.f, astat_cutoff = 0.f;
+  int use_cn = 0;
+  bool facts_on_side = false;     // vinfo was computed and gathered on the side stream
 };
+
+// contig ids by position and the packed per-neighbour facts of the pairs pass: both depend on
+// the positions only, not on the rows, so they are computed and gathered on the side stream
+// (own communicator) while the main stream classifies, mails and resolves
+int dist_side_facts(gtsb_context *c, DistState *D, Plan &P) {
+  const uint64_t Vg = c->V;
+  bool grew = false;
+  int rc = [&]() -> int {
+    if (injected_failure(c, "facts") != 0) { grew = true; return -1; }
+    ENSURE_U(c->vinfo, (Vg + 1) * sizeof(uint2));
+    ENSURE_U(c->rep_pred, Vg + 1);
+    uint64_t slot = 0;
+    for (int r = 0; r < c->world; r++) slot = P.lo[r + 1] - P.lo[r] > slot ? P.lo[r + 1] - P.lo[r] : slot;
+    ENSURE_U(D->side != nullptr ? D->stage2 : D->stage, (((size_t) slot * 8 + 15) & ~(size_t) 15) * c->world);
+    return 0;
+  }();
+  if (grew && agree(c, rc, "neighbour facts") != 0) return -1;
+  cudaStream_t st = c->stream;
+  const bool side = D->side != nullptr;
+  if (side) {
+    st = D->side;
+    CK(cudaEventRecord(D->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(st, D->ev_fork, 0));
+    if (c->vertices_pending) CK(cudaStreamWaitEvent(st, c->ev_vertices, 0));
+  } else if (await_vertices(c) != 0) {
+    return -1;
+  }
+  if (allgatherv(c, "nccl_allgather_vid", c->vid.p, 4, P.lo, side) != 0) return -1;
+  FilterArgs fa{};
+  c->line_layout = true;
+  fa.g = graph_args(c);
+  fa.rep_pred = c->rep_pred.as<uint8_t>();
+  fa.vinfo = c->vinfo.as<uint2>();
+  fa.fused_repeats = 1;
+  launch_vertex_facts(fa, 1, P.cn_cutoff, P.astat_cutoff, P.use_cn, st);
+  c->stats.kernel_launches += 1;
+  if (allgatherv(c, "nccl_allgather_vinfo", c->vinfo.p, sizeof(uint2), P.lo, side) != 0) return -1;
+  if (side) CK(cudaEventRecord(D->ev_join, st));
+  P.facts_on_side = side;
+  return 0;
+}
 
 // lines, positions, contig ids by position
 int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int setup_rc) {
@@ -365,7 +452,6 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int se
     k_dist_fill<<<(P.Vloc - L + 1 + 255) / 256, 256, 0, s>>>(a.ls, L, P.Vloc + 1, (uint32_t) R);
     c->stats.kernel_launches += 7;
   }
-  if (allgatherv(c, "nccl_allgather_vid", c->vid.p, 4, P.lo) != 0) return -1;
   a.V = P.Vloc;
   return 0;
 }
@@ -404,6 +490,8 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
     ENSURE(D->bounds, (MAX_RANKS + 2) * 4);
     ENSURE(D->rank_cnt, (MAX_RANKS + 2) * 4);
+    ENSURE(c->corrections, (size_t) (R / 8 + 4096) * sizeof(uint4));
+    if (injected_failure(c, "setup") != 0) return -1;
     CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
     CK(cudaMemsetAsync(c->pos.p, 0xFF, (Vg + 1) * 4, s));
     CK(cudaMemsetAsync(c->vstate.p, 0, Vg ? Vg : 1, s));
@@ -413,6 +501,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     CK(cudaMemsetAsync(D->rank_cnt.p, 0, (MAX_RANKS + 2) * 4, s));
     return 0;
   }();
+  if (rc == 0 && ensure_root_column(c) != 0) rc = -1;
   const int setup_rc = rc;
   Trace tr(s);
   tr.mark(me, "setup");
@@ -451,6 +540,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   rc = dist_positions(c, D, a, P, setup_rc);      // exchanges the setup status with the line counts
   if (rc != 0) return -1;
   tr.mark(me, "positions");
+  if (dist_side_facts(c, D, P) != 0) return -1;
 
   // ---- classify, creator ranks, mail per destination rank
   c->stats.kernel_launches += launch_b2_classify(a, s);
@@ -462,23 +552,21 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     if (c->h_counters[CNT_ERROR] & 2u) return fail(c, "gtsb_pipeline: self link (root == ctg) is not supported");
     if (c->h_counters[CNT_FALLBACK])
       return fail(c, "gtsb_pipeline: input outside what the rank-partitioned build accepts (reason mask %u: "
-                     "1 = a contig heads several lines, 2 = line longer than %u records, 4 = oversized segment)",
-                  c->h_counters[CNT_FALLBACK], MAX_LINE_RECS);
+                     "1 = a contig heads several lines, 2 = line longer than %u records, 4 = oversized segment, "
+                     "8 = a link listed only on the later line); a single device rebuilds such input with its "
+                     "general path, the partitioned build has none", c->h_counters[CNT_FALLBACK], MAX_LINE_RECS);
     CK(cudaMemcpyAsync(&mine[1], a.rank_cnt, N * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&mine[0], a.k0 + P.Vloc, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 0;
   }();
-  // besides the counts every rank tells how much mail its receive buffers hold now, so that all
-  // ranks know who is about to reallocate them (the peers then have to reopen them)
-  const uint64_t rx_cap = D->peers_open ? D->rx_dest.cap / 4 : 0;
-  mine[N + 1] = (uint32_t) (rx_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : rx_cap);
-  if (exchange(c, rc, "classify", mine, N + 2, all) != 0) return -1;
-  const int W = N + 2;
-  uint64_t k_base = 0, n_creators = 0;
+  if (exchange(c, rc, "classify", mine, N + 1, all) != 0) return -1;
+  const int W = N + 1;
+  uint64_t k_base = 0, n_creators = 0, creators_max = 0;
   for (int r = 0; r < N; r++) {
     if (r < me) k_base += all[(size_t) r * W];
     n_creators += all[(size_t) r * W];
+    creators_max = all[(size_t) r * W] > creators_max ? all[(size_t) r * W] : creators_max;
   }
   if (2 * n_creators >= 0xFFFFFFF0ull) return fail(c, "too many edges for 32-bit edge ids");
   a.k_base = (uint32_t) k_base;
@@ -488,39 +576,43 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     r_off[r + 1] = r_off[r] + all[(size_t) r * W + 1 + me];      // what r sends to me
   }
   const uint64_t M = r_off[N];                                         // mail for my rows
-  bool reopen = false;
   std::vector<long long> shift(N, 0);
+  uint64_t M_max = 0;                                                  // every size below is a function of
+  P.E_max = 0;                                                         // numbers all ranks hold: uniform growth
   for (int r = 0; r < N; r++) {
     uint64_t Mr = 0, before_me = 0;                                    // r's mail; the part from ranks before me
     for (int h = 0; h < N; h++) {
       if (h < me) before_me += all[(size_t) h * W + 1 + r];
       Mr += all[(size_t) h * W + 1 + r];
     }
-    reopen |= Mr + 1 > (uint64_t) all[(size_t) r * W + N + 1];
+    M_max = Mr > M_max ? Mr : M_max;
+    P.E_max = Mr + all[(size_t) r * W] > P.E_max ? Mr + all[(size_t) r * W] : P.E_max;
     shift[r] = (long long) before_me - (long long) s_off[r];
   }
   tr.mark(me, "classify+exchange");
 
   // ---- receive buffers, then the messages: k2_partition stores every rank's mail straight into
   // that rank's buffers (peer memory over NVLink) while it computes the next ones
+  bool grew = false, rx_grew = false;
   rc = [&]() -> int {
+    if (injected_failure(c, "receive") != 0) { grew = true; return -1; }
     // 1/8 headroom: the buffers, and with them the peers' mappings, survive small changes
-    if (D->rx_dest.cap / 4 < M + 1 || !D->peers_open) {
-      ENSURE(D->rx_ent, (M + M / 8 + 16) * sizeof(uint4));
-      ENSURE(D->rx_dest, (M + M / 8 + 16) * 4);
+    if (ensure_u(c, D->rx_ent, (M_max + M_max / 8 + 16) * sizeof(uint4), rx_grew) != 0) { grew = true; return -1; }
+    if (ensure_u(c, D->rx_dest, (M_max + M_max / 8 + 16) * 4, rx_grew) != 0) { grew = true; return -1; }
+    grew |= rx_grew;
+    ENSURE_U(c->bucket, (M_max + 1) * sizeof(uint4));
+    ENSURE_U(c->bucket_line, M_max + 16);
+    const uint64_t max_rows = (M_max + creators_max + 1) / 2 + 1;      // slots = mail + own creators
+    if (c->srcp.cap < 2 * max_rows * 4 + 256 || c->estate.cap < 2 * max_rows) {
+      grew = true;
+      if (ensure_rows(c, max_rows) != 0) return -1;
     }
-    ENSURE(c->bucket, (M + 1) * sizeof(uint4));
-    ENSURE(c->bucket_line, M + 16);
-    const uint64_t max_rows = (M + mine[0] + 1) / 2 + 1;               // slots = mail + own creators
-    if (ensure_rows(c, max_rows) != 0) return -1;
-    const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
-    ENSURE(c->corrections, (size_t) corr_cap * sizeof(uint4));
-    a.corrections_cap = corr_cap;
-    ENSURE(D->peer_tab, MAX_RANKS * 24);
+    ENSURE_U(D->peer_tab, MAX_RANKS * 24);
     return 0;
   }();
-  if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
-  if (reopen && open_peer_buffers(c) != 0) return -1;
+  if (grew && agree(c, rc, "receive buffers") != 0) return -1;
+  a.corrections_cap = (uint32_t) (c->corrections.cap / sizeof(uint4));
+  if ((rx_grew || !D->peers_open) && open_peer_buffers(c) != 0) return -1;
   {
     char tab[MAX_RANKS * 24];
     void **pe = reinterpret_cast<void **>(tab), **pd = pe + MAX_RANKS;
@@ -567,7 +659,9 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     if (c->h_counters[CNT_ERROR] & 8u) return fail(c, "gtsb_pipeline: mail for a row of another rank (internal)");
     if (c->h_counters[CNT_FALLBACK])
       return fail(c, "gtsb_pipeline: input outside what the rank-partitioned build accepts (reason mask %u: "
-                     "4 = oversized segment, 8 = a link listed only on the later line)", c->h_counters[CNT_FALLBACK]);
+                     "1 = a contig heads several lines, 2 = line longer than %u records, 4 = oversized segment, "
+                     "8 = a link listed only on the later line); a single device rebuilds such input with its "
+                     "general path, the partitioned build has none", c->h_counters[CNT_FALLBACK], MAX_LINE_RECS);
     return 0;
   }();
   c->E = P.Vloc ? c->h_counters[CNT_EDGES] : 0;
@@ -578,24 +672,40 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   // ---- reverse-flag corrections may belong to rows of other ranks
   const uint32_t my_corr = c->h_counters[CNT_CORRECTIONS] < a.corrections_cap ? c->h_counters[CNT_CORRECTIONS]
                                                                                 : a.corrections_cap;
-  if (exchange(c, rc, "rows", &my_corr, 1, all) != 0) return -1;
+  const uint32_t rows_mine[3] = {my_corr, c->n_big_rows, c->max_deg};
+  if (exchange(c, rc, "rows", rows_mine, 3, all) != 0) return -1;
   std::vector<uint64_t> c_off(N + 1, 0);
-  for (int r = 0; r < N; r++) c_off[r + 1] = c_off[r] + all[r];
+  P.big_rows_max = P.deg_max = 0;
+  for (int r = 0; r < N; r++) {
+    c_off[r + 1] = c_off[r] + all[(size_t) r * 3];
+    P.big_rows_max = all[(size_t) r * 3 + 1] > P.big_rows_max ? all[(size_t) r * 3 + 1] : P.big_rows_max;
+    P.deg_max = all[(size_t) r * 3 + 2] > P.deg_max ? all[(size_t) r * 3 + 2] : P.deg_max;
+  }
   if (c_off[N]) {
+    bool grew = false;
     rc = [&]() -> int {
-      ENSURE(D->corr_all, c_off[N] * sizeof(uint4));
-      if (my_corr)
-        CK(cudaMemcpyAsync(D->corr_all.as<uint4>() + c_off[me], a.corrections, (size_t) my_corr * sizeof(uint4),
-                           cudaMemcpyDeviceToDevice, s));
+      if (injected_failure(c, "corrections") != 0) { grew = true; return -1; }
+      ENSURE_U(D->corr_all, c_off[N] * sizeof(uint4));
       return 0;
     }();
-    if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
+    if (grew && agree(c, rc, "corrections") != 0) return -1;
+    if (my_corr)
+      CK(cudaMemcpyAsync(D->corr_all.as<uint4>() + c_off[me], a.corrections, (size_t) my_corr * sizeof(uint4),
+                         cudaMemcpyDeviceToDevice, s));
     if (allgatherv(c, "nccl_allgather_corrections", D->corr_all.p, sizeof(uint4), c_off) != 0) return -1;
     c->stats.kernel_launches += launch_b2_apply_corrections(a, D->corr_all.as<uint4>(), (uint32_t) c_off[N], s);
   }
 
   // ---- windows over my rows
-  if (ensure_windows(c, P.Vloc, c->E + 1) != 0) return -1;
+  {
+    // window tables: sized by the largest share of rows / slots any rank holds (uniform growth)
+    uint64_t rows_max = 0;
+    for (int r = 0; r < N; r++) rows_max = P.lo[r + 1] - P.lo[r] > rows_max ? P.lo[r + 1] - P.lo[r] : rows_max;
+    const bool grew = c->wcount.cap < ((rows_max + 63) / 64 + 2) * 4 || c->win_start.cap < ((rows_max < P.E_max + 1 ? rows_max : P.E_max + 1) + 2) * 4;
+    rc = injected_failure(c, "windows") != 0 ? -1 : ensure_windows(c, rows_max, P.E_max + 1);
+    if (grew && agree(c, rc, "windows") != 0) return -1;
+    if (!grew && rc != 0) return -1;
+  }
   c->line_layout = true;
   c->csr_exported = false;
   c->have_graph = true;
@@ -624,9 +734,24 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   uint32_t *cnt = c->counters.as<uint32_t>();
   std::vector<uint32_t> all;
   FilterArgs a{};
+  // sized by what the fullest rank holds, so that every rank's buffers grow in the same step
+  const bool grew = c->proposals.cap < (P.E_max + 1) * sizeof(uint2) || c->poly_cur.cap < (Vg + 1) * 4 ||
+                    c->vres.cap < (Vg + 1) * 4 ||
+                    (P.big_rows_max != 0 &&
+                     c->big_scratch.cap < (size_t) (P.big_rows_max < (uint32_t) c->sm_count * 2 ? P.big_rows_max
+                                                                                               : (uint32_t) c->sm_count * 2) *
+                                              P.deg_max * BIG_SCRATCH_STRIDE);
   int rc = [&]() -> int {
+    if (injected_failure(c, "filter") != 0) return -1;
     if (await_vertices(c) != 0) return -1;
-    if (ensure_filter_buffers(c, Vg, c->E, a) != 0) return -1;
+    const uint32_t nb = c->n_big_rows, md = c->max_deg;
+    c->n_big_rows = P.big_rows_max;                      // scratch for the largest hub population of any rank
+    c->max_deg = P.deg_max;
+    const int e = ensure_filter_buffers(c, Vg, P.E_max, a);
+    c->n_big_rows = nb;
+    c->max_deg = md;
+    if (e != 0) return -1;
+    if (ensure_filter_buffers(c, Vg, P.E_max, a) != 0) return -1;      // arguments for this rank's rows
     CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, (CNT_NUM - CNT_PROPOSALS) * 4, s));
     CK(cudaMemsetAsync(c->poly_cur.p, 0xFF, (Vg + 1) * 4, s));
     CK(cudaMemsetAsync(c->poly_new.p, 0xFF, (Vg + 1) * 4, s));
@@ -635,17 +760,17 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
     CK(cudaMemsetAsync(c->fstat.p, 0x0C, Vg + 1, s));
     return 0;
   }();
-  if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
+  if (grew && agree(c, rc, "filter buffers") != 0) return -1;
+  if (!grew && rc != 0) return -1;            // no allocation was due: not a memory problem, and not rank-local
   a.ambig = c->ambig;
   a.cncutoff = cncutoff;
   a.ocutoff = ocutoff;
   a.fused_repeats = 1;
 
-  // phase 1
-  launch_vertex_facts(a, 1, cn_cutoff, astat_cutoff, use_cn, s);
-  if (allgatherv(c, "nccl_allgather_vinfo", c->vinfo.p, sizeof(uint2), P.lo) != 0) return -1;
+  // phase 1: the neighbour facts were computed and gathered under the build (dist_side_facts)
+  if (P.facts_on_side) CK(cudaStreamWaitEvent(s, D->ev_join, 0));
   launch_pairs(a, s);
-  c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
+  c->stats.kernel_launches += 1 + (c->n_big_rows ? 1 : 0);
   rc = [&]() -> int {
     if (read_counters(c) != 0) return -1;
     if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
@@ -662,14 +787,16 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   c->stats.proposals = nprop;
   c->stats.poly_sweeps = 0;
   if (nprop) {
+    bool pgrew = false;
     rc = [&]() -> int {
-      ENSURE(D->prop_all, (size_t) nprop * sizeof(uint2));
-      if (my_prop)
-        CK(cudaMemcpyAsync(D->prop_all.as<uint2>() + p_off[me], a.proposals, (size_t) my_prop * sizeof(uint2),
-                           cudaMemcpyDeviceToDevice, s));
+      if (injected_failure(c, "proposals") != 0) { pgrew = true; return -1; }
+      if (ensure_u(c, D->prop_all, (size_t) nprop * sizeof(uint2), pgrew) != 0) return -1;
       return 0;
     }();
-    if (rc != 0) return -1;            // out of memory on this rank: nothing to agree on
+    if (pgrew && agree(c, rc, "proposal list") != 0) return -1;
+    if (my_prop)
+      CK(cudaMemcpyAsync(D->prop_all.as<uint2>() + p_off[me], a.proposals, (size_t) my_prop * sizeof(uint2),
+                         cudaMemcpyDeviceToDevice, s));
     if (allgatherv(c, "nccl_allgather_proposals", D->prop_all.p, sizeof(uint2), p_off) != 0) return -1;
     // every rank holds every proposal: the polyTime fix-point runs redundantly,
     // identically, without any exchange
@@ -719,7 +846,11 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
       if (pending == 0) break;
       if (c->stats.fire_rounds > Vg + 2) return fail(c, "gtsb_filter: fire rounds did not converge");
       cap = (cap + 3u) & ~3u;
-      ENSURE(D->stage, (size_t) cap * 4 * N);
+      {
+        bool sgrew = false;
+        const int e = injected_failure(c, "fire") != 0 ? (sgrew = true, -1) : ensure_u(c, D->stage, (size_t) cap * 4 * N, sgrew);
+        if (sgrew && agree(c, e, "fire round staging") != 0) return -1;
+      }
       uint32_t *stage = D->stage.as<uint32_t>();
       for (int k = 0; k < FIRE_ROUNDS_PER_SYNC; k++) {
         CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
@@ -762,6 +893,9 @@ int dist_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
   if (!c->have_vertices || !c->have_records) rc = fail(c, "gtsb_pipeline: vertices and records must be set first");
   if (rc == 0 && get_ambig(c, pcutoff) != 0) rc = -1;
   Plan P;
+  P.cn_cutoff = cn_cutoff;
+  P.astat_cutoff = astat_cutoff;
+  P.use_cn = use_cn;
   {
     KernelTimer t_("PHASE_build", c->stream);
     if (dist_build(c, D, P, rc) != 0) return -1;
@@ -810,6 +944,14 @@ int gtsb_dist_init(gtsb_context *c, int rank, int world, const void *id128) {
   NK(g_nccl.CommInitRank(&D->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
+  if (g_nccl.CommSplit != nullptr && getenv("GTSB_NO_SIDE_STREAM") == nullptr) {
+    if (g_nccl.CommSplit(D->comm, 0, rank, &D->comm2, nullptr) != ncclSuccess) D->comm2 = nullptr;
+    if (D->comm2 != nullptr) {
+      CK(cudaStreamCreateWithFlags(&D->side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&D->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&D->ev_join, cudaEventDisableTiming));
+    }
+  }
   ENSURE(D->small, (size_t) MAX_RANKS * SMALL_N * 4);
   CK(cudaMallocHost(&D->h_small, (size_t) MAX_RANKS * SMALL_N * 4));
   return 0;

@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(256) k4_fill_srcp(GraphArgs g, uint32_t *__res
       g.flags[r0 + k] = (uint8_t) ((g.flags[r0 + k] & 0x0Fu) | (g.dst[r0 + k] < p ? F_LT : 0u));
     }
   if (big_rows != nullptr) {
-    if (big) atomicMax(&g.counters[CNT_MAX_DEG], d);
+    const uint32_t wmax = __reduce_max_sync(FULL, d);
+    if (lane_id() == 0 && wmax) atomicMax(&g.counters[CNT_MAX_DEG], wmax);
     warp_append(big, p, big_rows, &g.counters[CNT_BIG_ROWS]);
   }
   unsigned todo = __ballot_sync(FULL, big);
@@ -589,10 +590,14 @@ __global__ void __launch_bounds__(256) k4_dirty(FilterArgs a, uint32_t n) {
   if (i >= n) return;
   const uint2 pr = a.proposals[i];
   if (a.poly_cur[pr.y] != id_at(g, pr.x)) return;             // not the winning proposer
-  a.dirty[pr.y] = 1;
+  const uint32_t t = a.poly_cur[pr.y];                        // when the target turned polymorphic
   const uint32_t rl = pr.y - g.row_base;                      // the target's row, if this device holds it
   if (rl >= g.V) return;
-  for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) a.dirty[g.dst[s]] = 1;
+  // U(v -> target) fails only for rows v whose turn comes at or after t (polyTime(w) <= v)
+  for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) {
+    const uint32_t v = g.dst[s];
+    if (t <= id_at(g, v)) a.dirty[v] = 1;
+  }
 }
 
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s) {
@@ -624,8 +629,11 @@ __global__ void __launch_bounds__(256) k4_fire_init(FilterArgs a, uint32_t *__re
   if (pl < g.V) {
     const uint32_t d = g.row_ptr[pl + 1] - g.row_ptr[pl];
     if (d <= BIG_ROW) {
-      const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < id_at(g, p));
-      redo = active && a.ocutoff >= 0 && d >= 2 && a.dirty[p] != 0;
+      const uint32_t v_id = id_at(g, p);
+      const bool active = !(a.vinfo[p].y & VI_MARKED) && !(a.poly_cur[p] < v_id);
+      // a row next to a contig that turned polymorphic before the row's turn (k4_dirty) loses
+      // edges: its static answer can only go from "some pair overlaps" to "none does"
+      redo = active && a.ocutoff >= 0 && d >= 2 && a.dirty[p] != 0 && a.gbits[p] != 0;
       if (!redo) {
         const uint32_t gb = !active ? 0u : (a.ocutoff < 0 ? 3u : (uint32_t) a.gbits[p]);   // 0 > ocutoff: :301-324
         a.gbits[p] = (uint8_t) gb;

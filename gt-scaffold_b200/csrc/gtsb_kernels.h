@@ -95,7 +95,11 @@ struct Build2Args {
   int32_t *edist;
   float *estd;
   uint8_t *eflags;
+  // lines handed in as such (gtsb_set_record_lines_*): k3_lines instead of the head passes
+  const uint32_t *line_root, *line_start;
+  uint32_t n_lines;
 };
+int launch_b3_lines(const Build2Args &a, cudaStream_t s);          // line_root/line_start -> ls, vid, pos
 int launch_build2_lines(const Build2Args &a, cudaStream_t s);
 int launch_build2_classify(const Build2Args &a, cudaStream_t s);   // needs line starts + ctg only
 int launch_build2_rows(const Build2Args &a, cudaStream_t s);       // needs every record column

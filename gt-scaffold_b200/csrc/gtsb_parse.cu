@@ -244,6 +244,8 @@ int gtsb_parse_de_host(gtsb_context *c, const char *text, uint64_t n, uint64_t *
   }
   c->R = R;
   c->have_records = true;
+  c->have_root_column = true;
+  c->have_lines = false;
   c->have_num_pairs = true;
   c->stats.nof_records = R;
   *nof_records = R;
@@ -317,6 +319,7 @@ int gtsb_get_records(gtsb_context *c, uint32_t *root, uint32_t *ctg, int32_t *di
   if (num_pairs != nullptr && !c->have_num_pairs)
     return fail(c, "gtsb_get_records: pair counts exist for records parsed on the device only");
   if (await_records(c) != 0) return -1;
+  if (root != nullptr && gtsbi::ensure_root_column(c) != 0) return -1;
   const uint64_t R = c->R;
   cudaStream_t s = c->stream;
   if (R) {

@@ -89,6 +89,11 @@ int gtsb_set_records_device(gtsb_context *ctx, uint64_t nof_records, const uint3
 int gtsb_set_record_lines_host(gtsb_context *ctx, uint64_t nof_lines, const uint32_t *line_root,
                                const uint32_t *line_start, uint64_t nof_records, const uint32_t *ctg,
                                const int32_t *dist, const float *std_dev, const uint8_t *flags);
+/* the same with device pointers that must stay valid (what gtsb_parse_de_host leaves behind,
+   or a caller that tokenises on the GPU itself) */
+int gtsb_set_record_lines_device(gtsb_context *ctx, uint64_t nof_lines, const uint32_t *line_root,
+                                 const uint32_t *line_start, uint64_t nof_records, const uint32_t *ctg,
+                                 const int32_t *dist, const float *std_dev, const uint8_t *flags);
 /* an already-built graph (host CSR, flags incl. GTSB_RSENSE/RSAME, states);
    used by the GtScaffolderGraph binding of mark_repeats / filter */
 int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_edges,

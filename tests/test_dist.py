@@ -87,6 +87,21 @@ def test_partitioned_pipeline_matches_the_oracle():
     assert out.count("-> OK") >= 7 and "MISMATCH" not in out, out[-3000:]
 
 
+@pytest.mark.gpu
+def test_a_failing_rank_stops_all_ranks():
+    """an allocation failure on one rank must not leave its peers in a collective."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519",
+                        os.path.join(HERE, "dist_fail_check.py")], cwd=ROOT, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=900)
+    out = r.stdout.decode()
+    assert r.returncode == 0, out[-3000:]
+    assert out.count("-> OK") >= 16 and "BAD" not in out, out[-3000:]
+
+
 def test_chunk_fractions_and_lines_of(pkg):
     for world in (1, 2, 5, 8):
         fr = pkg.api.chunk_fractions(world)

@@ -321,10 +321,58 @@ def test_full_size_c3_vs_reference(pkg, synth):
     assert st["nof_vertices"] == 10_000_000 and st["line_ordered_build"] == 1
 
 
-def test_full_size_c4_hubs_vs_reference(pkg, synth):
+def _full_size_vs_golden_digest(pkg, synth, name):
+    """A named config at full size against tests/golden/full_size_<name>.json: sha256 of every
+    result array of the compiled, unmodified reference, made in the build container by
+    tests/golden/make_full_size_digest.py (the reference needs ~13 min for config 4).  The inputs
+    are regenerated here by the same seeded numpy generator and checked by hash first."""
+    import hashlib
+    import json
+    sys_path = os.path.join(HERE, "golden")
+    gold = json.load(open(os.path.join(sys_path, "full_size_%s.json" % name)))
+    inp = synth.generate(name, **gold["kwargs"])
+    for k, h in gold["input_sha256"].items():
+        assert hashlib.sha256(np.ascontiguousarray(getattr(inp, k)).tobytes()).hexdigest() == h, \
+            f"generator drifted: input {k} is not the one the golden digest was made from"
+    g = pkg.ScaffoldGraphB200()
+    g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+    line_root, line_start = pkg.api.lines_of(inp.root)
+    g.set_record_lines(line_root, line_start, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+    g.pipeline(*[DEFAULT[k] for k in ("cn_cut", "a_cut", "use_cn", "pc", "cnc", "oc")])
+    got, st = g.result(), g.stats()
+    g.close()
+    dt = dict(src=np.uint32, dst=np.uint32, dist=np.int64, std_dev=np.float32, flags=np.uint8,
+              row_ptr=np.uint64, adj_eid=np.uint32, vstate=np.uint8, estate=np.uint8)
+    assert len(got["src"]) == gold["E"]
+    assert np.bincount(got["estate"], minlength=8).tolist() == gold["states"]["estate"]
+    assert np.bincount(got["vstate"], minlength=8).tolist() == gold["states"]["vstate"]
+    for k in KEYS:
+        a = np.ascontiguousarray(got[k]).astype(dt[k], copy=False)
+        assert a.shape[0] == gold["digest"][k]["n"], k
+        assert hashlib.sha256(a.tobytes()).hexdigest() == gold["digest"][k]["sha256"], \
+            f"{name} at full size: {k} differs from the reference's result"
+    return st, gold
+
+
+def test_full_size_c4_hubs_vs_reference_digest(pkg, synth):
     """BASELINE.json config 4 as named: 5*10^6 contigs, power-law degrees with hubs of up to 10^4
     edges (the reference's O(d^2) paths: find_edge in parser.c:359, the pair loops of
-    algorithms.c:283-320, mark_edge's twin scan :61-73)."""
+    algorithms.c:283-320, mark_edge's twin scan :61-73 -- 88 s + 72 s + 544 s on one core)."""
+    st, gold = _full_size_vs_golden_digest(pkg, synth, "c4_repeat_hubs")
+    assert st["nof_vertices"] == 5_000_000 and st["max_degree"] == gold["max_degree"] >= 10_000
+
+
+def test_full_size_c3_vs_reference_digest(pkg, synth):
+    """Config 3 once more, through the host-buffer entry points and the numpy generator, against
+    the digest (the direct comparison above uses the torch generator and device buffers)."""
+    st, _ = _full_size_vs_golden_digest(pkg, synth, "c3_human")
+    assert st["line_ordered_build"] == 1
+
+
+@pytest.mark.skipif(os.environ.get("GTSB_FULL_REFERENCE") != "1",
+                    reason="~13 min of reference CPU time on the box; set GTSB_FULL_REFERENCE=1 "
+                           "(the digest test above pins the same result)")
+def test_full_size_c4_hubs_vs_reference(pkg, synth):
     st = _full_size_vs_reference(pkg, synth, "c4_repeat_hubs", max_deg=10_000)
     assert st["nof_vertices"] == 5_000_000 and st["max_degree"] > 5_000
 

@@ -23,8 +23,20 @@ if __name__ == "__main__":
     stream = torch.cuda.current_stream()
     g = pkg.ScaffoldGraphB200(device=0, stream=stream.cuda_stream)
     g.set_vertices_device(Vn, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
-    g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
-                         t["std_dev"].data_ptr(), t["flags"].data_ptr())
+    lines = kw.pop("lines", 1) if False else int(os.environ.get("PROBE_LINES", "1"))
+    if lines:
+        # what a .de tokeniser has: one (root, first record) per line instead of a root per record
+        root = t["root"]
+        brk = torch.nonzero(root[1:] != root[:-1]).flatten() + 1
+        line_start = torch.cat([torch.zeros(1, dtype=brk.dtype, device=brk.device), brk,
+                                torch.tensor([Rn], dtype=brk.dtype, device=brk.device)]).to(torch.int32)
+        line_root = root[line_start[:-1].long()].contiguous()
+        g.set_record_lines_device(int(line_root.shape[0]), line_root.data_ptr(), line_start.data_ptr(), Rn,
+                                  t["ctg"].data_ptr(), t["dist"].data_ptr(), t["std_dev"].data_ptr(),
+                                  t["flags"].data_ptr())
+    else:
+        g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
+                             t["std_dev"].data_ptr(), t["flags"].data_ptr())
     for _ in range(3):
         g.pipeline()
     torch.cuda.synchronize()
