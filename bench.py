@@ -163,7 +163,9 @@ def parity_check(pkg, torch, dist, rank, world, local, uid, args, ref_result):
     g = pkg.ScaffoldGraphB200(device=local)
     mine = inp
     if world > 1:
-        g.dist_init(rank, world, uid)
+        box = [pkg.api.dist_unique_id() if rank == 0 else None]      # a communicator of its own
+        dist.broadcast_object_list(box, src=0)
+        g.dist_init(rank, world, box[0])
         mine = pkg.api.shard_lines(inp, world, rank)
     g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
     g.set_records(mine.root, mine.ctg, mine.dist, mine.std_dev, mine.flags)

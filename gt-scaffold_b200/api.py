@@ -34,7 +34,8 @@ EXPORTS = [
     "gtsb_device_pointers", "gtsb_get_stats", "gtsb_synchronize", "gtsb_ambig_thresholds",
     "gtsb_set_profile", "gtsb_get_profile", "gtsb_force_general_build",
     "gtsb_dist_unique_id", "gtsb_dist_init", "gtsb_get_edges",
-    "gtsb_set_record_lines_host", "gtsb_set_record_lines_device", "gtsb_get_edge_states",
+    "gtsb_set_record_lines_host", "gtsb_set_record_lines_device", "gtsb_update_vertices_host",
+    "gtsb_set_states_host", "gtsb_get_edge_states",
     "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
     "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host",
 ]
@@ -100,6 +101,8 @@ def load_library():
     L.gtsb_set_record_lines_host.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
     L.gtsb_set_record_lines_device.argtypes = [vp, u64, vp, vp, u64, vp, vp, vp, vp]
     L.gtsb_get_edge_states.argtypes = [vp, vp]
+    L.gtsb_update_vertices_host.argtypes = [vp, u64, vp, vp, vp]
+    L.gtsb_set_states_host.argtypes = [vp, vp, vp]
     L.gtsb_set_vertex_names_host.argtypes = [vp, u64, C.c_char_p, vp]
     L.gtsb_parse_de_host.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.gtsb_get_records.argtypes = [vp] * 7
@@ -303,6 +306,17 @@ class ScaffoldGraphB200:
     def set_record_lines_device(self, L, line_root_ptr, line_start_ptr, R, ctg_ptr, dist_ptr, std_ptr, flags_ptr):
         self._ck(self.L.gtsb_set_record_lines_device(self.h, int(L), line_root_ptr, line_start_ptr, int(R), ctg_ptr,
                                                      dist_ptr, std_ptr, flags_ptr))
+
+    def update_vertices(self, seq_len, astat, copy_num):
+        """New per-vertex attributes for the resident graph (states and rows stay)."""
+        a = [np.ascontiguousarray(seq_len, np.uint32), np.ascontiguousarray(astat, np.float32),
+             np.ascontiguousarray(copy_num, np.float32)]
+        self._ck(self.L.gtsb_update_vertices_host(self.h, a[0].shape[0], *[_ptr(x) for x in a]))
+
+    def set_states(self, vstate=None, estate_by_eid=None):
+        v = None if vstate is None else np.ascontiguousarray(vstate, np.uint8)
+        e = None if estate_by_eid is None else np.ascontiguousarray(estate_by_eid, np.uint8)
+        self._ck(self.L.gtsb_set_states_host(self.h, _ptr(v), _ptr(e)))
 
     def set_graph(self, row_ptr, dst, dist, std_dev, flags, seq_len, astat, copy_num, vstate, estate):
         a = [np.ascontiguousarray(row_ptr, np.uint32), np.ascontiguousarray(dst, np.uint32),

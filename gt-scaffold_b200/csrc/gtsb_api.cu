@@ -115,6 +115,14 @@ __global__ void __launch_bounds__(256) k_states_by_eid(uint64_t E, const uint32_
   if (s < E) out[eid[s]] = estate[s];
 }
 
+// estate by eid -> estate by slot
+__global__ void __launch_bounds__(256) k_states_from_eid(uint64_t E, const uint32_t *__restrict__ eid,
+                                                          const uint8_t *__restrict__ in,
+                                                          uint8_t *__restrict__ estate) {
+  const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < E) estate[s] = in[eid[s]];
+}
+
 __global__ void k_pack_vattr(uint32_t V, const uint32_t *__restrict__ seq_len,
                              const float *__restrict__ copy_num, VAttr *__restrict__ out) {
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,6 +394,12 @@ int do_build_lines(gtsb_context *c) {
   a.edist = c->edist.as<int32_t>();
   a.estd = c->estd.as<float>();
   a.eflags = c->eflags.as<uint8_t>();
+  if (c->want_win) {
+    ENSURE(c->win_rec, 2 * R * 4);
+    ENSURE(c->bwin, (R + 1) * 4);              // creating record of every pair
+    a.win_rec = c->win_rec.as<uint32_t>();
+    a.creator_rec = c->bwin.as<uint32_t>();
+  }
 
   if (ensure_windows(c, V, 2 * R) != 0) return -1;
   if (c->have_lines) {                          // lines handed in as such: no need to find them in a root column
@@ -435,7 +449,7 @@ int do_build(gtsb_context *c) {
   if (2 * R >= 0xFFFFFFF0ull) return fail(c, "too many records");
   cudaStream_t s = c->stream;
   c->fallback_reason = 0;
-  if (!c->want_win && !c->force_general && R > 0 && V > 0) {
+  if (!c->force_general && R > 0 && V > 0) {
     const int rc = do_build_lines(c);
     if (rc <= 0) return rc;
   }
@@ -715,6 +729,11 @@ int export_csr(gtsb_context *c) {
   x.dist_o = c->x_dist.as<int32_t>();
   x.std_o = c->x_std.as<float>();
   x.flags_o = c->x_flags.as<uint8_t>();
+  if (c->want_win && c->win_rec.p != nullptr) {
+    ENSURE(c->x_win, (E + 1) * 4);
+    x.win = c->win_rec.as<uint32_t>();
+    x.win_o = c->x_win.as<uint32_t>();
+  }
   x.estate_o = c->x_estate.as<uint8_t>();
   c->stats.kernel_launches += launch_export_csr(x, c->x_deg.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), c->stream);
   CK(cudaGetLastError());
@@ -796,7 +815,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
                     &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line, &c->line_root, &c->line_start,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,
-                    &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg,
+                    &c->x_dist, &c->x_std, &c->x_flags, &c->x_eid, &c->x_estate, &c->x_deg, &c->x_win,
                     &c->p_names, &c->p_name_off, &c->p_slots, &c->p_flags, &c->p_text, &c->p_chunk_cnt,
                     &c->p_chunk_off, &c->p_line_end, &c->p_line_cnt, &c->p_line_off, &c->num_pairs,
                     &c->p_last, &c->p_astat, &c->p_copy_num, &c->f_state, &c->f_sense, &c->f_src, &c->f_dst,
@@ -866,6 +885,52 @@ int gtsb_set_vertices_device(gtsb_context *c, uint64_t V, const uint32_t *seq_le
   adopt(c->copy_num_in, copy_num);
   adopt(c->astat, astat);
   return vertices_common(c, V, c->stream);
+}
+
+int gtsb_update_vertices_host(gtsb_context *c, uint64_t V, const uint32_t *seq_len, const float *astat,
+                              const float *copy_num) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (!c->have_graph || !c->have_vertices || V != c->V)
+    return fail(c, "gtsb_update_vertices_host: no resident graph with %llu vertices", (unsigned long long) V);
+  if (c->world > 1) return fail(c, "gtsb_update_vertices_host: single-device graphs only");
+  if (await_vertices(c) != 0) return -1;
+  if (!c->seq_len_in.owned || !c->copy_num_in.owned || !c->astat.owned)
+    return fail(c, "gtsb_update_vertices_host: the vertex attributes are caller-owned device buffers");
+  cudaStream_t s = c->stream;
+  if (V) {
+    CK(cudaMemcpyAsync(c->seq_len_in.p, seq_len, V * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->copy_num_in.p, copy_num, V * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->astat.p, astat, V * 4, cudaMemcpyHostToDevice, s));
+    k_pack_vattr<<<(uint32_t) ((V + 255) / 256), 256, 0, s>>>((uint32_t) V, c->seq_len_in.as<uint32_t>(),
+                                                              c->copy_num_in.as<float>(), c->vattr.as<VAttr>());
+    c->stats.kernel_launches++;
+  }
+  CK(cudaStreamSynchronize(s));                  // the host buffers may go away on return
+  return 0;
+}
+
+int gtsb_set_states_host(gtsb_context *c, const uint8_t *vstate, const uint8_t *estate_by_eid) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (!c->have_graph) return fail(c, "gtsb_set_states_host: no graph");
+  if (c->world > 1) return fail(c, "gtsb_set_states_host: single-device graphs only");
+  if (c->eid.p == nullptr || c->R == 0) return fail(c, "gtsb_set_states_host: this graph has no edge ids (not built here)");
+  if (await_vertices(c) != 0) return -1;
+  cudaStream_t s = c->stream;
+  const uint64_t V = c->V, E = c->E;
+  if (vstate != nullptr && V) CK(cudaMemcpyAsync(c->vstate.p, vstate, V, cudaMemcpyHostToDevice, s));
+  if (estate_by_eid != nullptr && E) {
+    ENSURE(c->x_estate, E + 1);
+    c->csr_exported = false;                     // the export buffer is reused
+    CK(cudaMemcpyAsync(c->x_estate.p, estate_by_eid, E, cudaMemcpyHostToDevice, s));
+    k_states_from_eid<<<(uint32_t) ((E + 255) / 256), 256, 0, s>>>(E, c->eid.as<uint32_t>(), c->x_estate.as<uint8_t>(),
+                                                                   c->estate.as<uint8_t>());
+    c->stats.kernel_launches++;
+  }
+  CK(cudaStreamSynchronize(s));
+  c->csr_exported = false;
+  return 0;
 }
 
 int gtsb_set_records_host(gtsb_context *c, uint64_t R, const uint32_t *root, const uint32_t *ctg,
@@ -1102,7 +1167,7 @@ int gtsb_get_csr(gtsb_context *c, uint32_t *row_ptr, uint32_t *dst, int32_t *dis
     }
     if (win_rec) {
       if (!c->want_win || c->win_rec.p == nullptr) return fail(c, "gtsb_get_csr: win_rec was not requested before gtsb_build");
-      CK(cudaMemcpyAsync(win_rec, c->win_rec.p, E * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(win_rec, ll ? c->x_win.p : c->win_rec.p, E * 4, cudaMemcpyDeviceToHost, s));
     }
     if (estate) CK(cudaMemcpyAsync(estate, ll ? c->x_estate.p : c->estate.p, E, cudaMemcpyDeviceToHost, s));
   }

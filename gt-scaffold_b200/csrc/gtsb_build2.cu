@@ -560,6 +560,10 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     a.estd[slot] = best;
     a.eflags[slot] = (uint8_t) (bf | (tw ? F_RSENSE : 0u) | (sm ? F_RSAME : 0u) | ((rf & RF_LT) ? F_LT : 0u));
     a.eid[slot] = 2u * (a.k_base + s_k0[j] + q);
+    if (a.win_rec != nullptr) {                    // which record's attributes the edge carries (num_pairs)
+      a.win_rec[slot] = g.rec0 + bi;
+      a.creator_rec[a.k_base + s_k0[j] + q] = g.rec0 + t;     // the record that seeds the twin edge
+    }
   }
   __syncthreads();
   // twin-created slots, ordered by the creator's k
@@ -577,6 +581,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     int32_t bdist = (int32_t) m.z;
     uint32_t bf = seedf;
     const uint32_t t0 = s_match[e];
+    bool won = false;
+    uint32_t bwin = 0;
     if (t0 != NO_MATCH) {                          // the line's own records of u, in file order
       const uint32_t rb = (s_rf[t0] & RF_DUP) ? s_ls[j + 1] - g.rec0 : t0 + 1u;
       uint32_t bi = NO_MATCH;
@@ -588,6 +594,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
       if (bi != NO_MATCH) {
         bdist = a.dist[g.rec0 + bi];
         bf = s_fl[bi] & (F_SENSE | F_SAME);
+        won = true;
+        bwin = bi;
       }
     }
     const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
@@ -599,6 +607,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     a.eflags[slot] = (uint8_t) (bf | ((m.y & M_FWD_SENSE) ? F_RSENSE : 0u) | ((m.y & M_FWD_SAME) ? F_RSAME : 0u) |
                                 ((m.y & M_LT) ? F_LT : 0u));
     a.eid[slot] = 2u * m.x + 1u;
+    if (a.win_rec != nullptr)                      // seed: the creator's record, looked up by k2_win_seeds
+      a.win_rec[slot] = won ? g.rec0 + bwin : (WIN_SEEDED | m.x);
     if (bf != seedf) {
       // the creator assumed its twin keeps the seed's flags: tell it otherwise
       const uint32_t at = atomicAdd(&a.counters[CNT_CORRECTIONS], 1u);
@@ -622,6 +632,18 @@ __global__ void __launch_bounds__(128) k2_corrections(Build2Args a, const uint4 
       if (a.dst[s] == c.y)
         a.eflags[s] = (uint8_t) ((a.eflags[s] & (F_SENSE | F_SAME | F_LT)) | ((c.z & F_SENSE) ? F_RSENSE : 0u) |
                                  ((c.z & F_SAME) ? F_RSAME : 0u));
+  }
+}
+
+// win_rec of twin-created slots that kept the creator's seed: k -> the creating record
+__global__ void __launch_bounds__(256) k2_win_seeds(uint32_t E, uint32_t *__restrict__ win_rec,
+                                                     const uint32_t *__restrict__ creator_rec,
+                                                     const uint32_t *__restrict__ counters) {
+  if (counters[CNT_FALLBACK] | counters[CNT_ERROR]) return;
+  const uint32_t n = min(E, counters[CNT_EDGES]);
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint32_t w = win_rec[s];
+    if (w & WIN_SEEDED) win_rec[s] = WIN_SEEDED | creator_rec[w & ~WIN_SEEDED];
   }
 }
 
@@ -670,6 +692,7 @@ __device__ __forceinline__ void export_slot(const ExportArgs &x, uint32_t to, ui
   x.flags_o[to] = x.flags[from] & 0x0Fu;
   x.eid_o[to] = x.eid[from];
   x.estate_o[to] = x.estate[from];
+  if (x.win_o != nullptr) x.win_o[to] = x.win[from];
 }
 
 __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
@@ -813,8 +836,15 @@ int launch_build2_classify(const Build2Args &a, cudaStream_t s) {
 int launch_build2_rows(const Build2Args &a, cudaStream_t s) {
   int n = launch_b2_partition(a, s);
   n += launch_b2_deliver_resolve(a, s);
-  KernelTimer t_("k2_corrections", s);
-  k2_corrections<<<64, 128, 0, s>>>(a, a.corrections, a.counters + CNT_CORRECTIONS, 0u);
+  {
+    KernelTimer t_("k2_corrections", s);
+    k2_corrections<<<64, 128, 0, s>>>(a, a.corrections, a.counters + CNT_CORRECTIONS, 0u);
+  }
+  if (a.win_rec != nullptr) {
+    KernelTimer t_("k2_win_seeds", s);
+    k2_win_seeds<<<a.sm_count * 8, 256, 0, s>>>((uint32_t) (2 * a.R), a.win_rec, a.creator_rec, a.counters);
+    n++;
+  }
   return n + 1;
 }
 

@@ -61,7 +61,7 @@ struct gtsb_context {
   uint32_t n_windows = 0;
   DevBuf ls, tile_cnt, tile_off, rf, pc, cnt_in, bptr2, cursor2, nown, k0, tmp_ent, tmp_dest,
       tmp_cursor, bucket, bucket_line, corrections, lineless_flag, lineless_rank;
-  DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg;   // plain-CSR export
+  DevBuf x_row_ptr, x_dst, x_dist, x_std, x_flags, x_eid, x_estate, x_deg, x_win;   // plain-CSR export
   uint32_t fallback_reason = 0;
   int force_general = 0;
   // build work

@@ -96,6 +96,7 @@ struct DistState {
   bool peers_open = false;
 };
 constexpr int SMALL_N = MAX_RANKS + 8;
+void dist_reset_buffers(gtsb_context *c);
 
 #define NK(call)                                                                               \
   do {                                                                                         \
@@ -103,6 +104,33 @@ constexpr int SMALL_N = MAX_RANKS + 8;
     if (r_ != ncclSuccess)                                                                     \
       return fail(c, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
   } while (0)
+
+// after a failed step (collective: every rank calls it from the same exchange)
+void dist_reset_buffers(gtsb_context *c) {
+  DistState *D = static_cast<DistState *>(c->dstate);
+  cudaStreamSynchronize(c->stream);
+  if (D->side != nullptr) cudaStreamSynchronize(D->side);
+  for (int r = 0; r < c->world; r++)
+    for (int k = 0; k < 2; k++) {
+      if (r != c->rank && D->peer_ptr[r][k] != nullptr) cudaIpcCloseMemHandle(D->peer_ptr[r][k]);
+      D->peer_ptr[r][k] = nullptr;
+    }
+  D->peers_open = false;
+  // nobody frees a receive buffer a peer still has mapped
+  if (g_nccl.AllReduce(D->small.p, D->small.p, 1, ncclUint32, ncclSum, D->comm, c->stream) == ncclSuccess)
+    cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage, &D->stage2, &D->peer_tab,
+                    &c->vinfo, &c->bucket, &c->bucket_line, &c->srcp, &c->dst, &c->edist, &c->estd,
+                    &c->eflags, &c->eid, &c->estate, &c->wcount, &c->woff, &c->win_start, &c->proposals,
+                    &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat, &c->work_a, &c->work_b, &c->vres, &c->dirty,
+                    &c->big_scratch};
+  for (DevBuf *b : bufs) {
+    if (b->owned && b->p != nullptr) cudaFree(b->p);
+    *b = DevBuf();
+  }
+  cudaGetLastError();
+  c->have_graph = false;
+}
 
 // every rank contributes n (<= SMALL_N) words; host gets the world x n matrix
 int small_allgather(gtsb_context *c, const uint32_t *mine, int n, std::vector<uint32_t> &out) {
@@ -116,6 +144,9 @@ int small_allgather(gtsb_context *c, const uint32_t *mine, int n, std::vector<ui
   out.assign(D->h_small, D->h_small + (size_t) c->world * n);
   return 0;
 }
+
+int ensure_u(gtsb_context *c, DevBuf &b, size_t bytes, bool &grew);
+int agree(gtsb_context *c, int local_rc, const char *where);
 
 // in-place allgather of slices [lo[r], lo[r+1]) of an array of `es`-byte elements.
 // The slices differ in length, so they travel through a staging buffer of
@@ -133,7 +164,11 @@ int allgatherv(gtsb_context *c, const char *what, void *buf, size_t es, const st
   for (int r = 0; r < N; r++) slot = lo[r + 1] - lo[r] > slot ? lo[r + 1] - lo[r] : slot;
   if (slot == 0) return 0;
   const size_t slot_bytes = ((size_t) slot * es + 15) & ~(size_t) 15;
-  ENSURE(stage_buf, slot_bytes * N);
+  {
+    bool grew = false;                          // slot sizes are rank-uniform: every rank grows here or none
+    const int e = ensure_u(c, stage_buf, slot_bytes * N, grew);
+    if (grew && agree(c, e, what) != 0) return -1;
+  }
   char *stage = stage_buf.as<char>();
   char *base = static_cast<char *>(buf);
   const size_t mine = (size_t) (lo[me + 1] - lo[me]) * es;
@@ -162,13 +197,16 @@ int ensure_u(gtsb_context *c, DevBuf &b, size_t bytes, bool &grew) {
     if (ensure_u(c, buf, (bytes), grew) != 0) return -1;       \
   } while (0)
 
-// test hook: GTSB_FAIL_AT="<rank>:<place>" makes that rank report an allocation failure at that place
-int injected_failure(gtsb_context *c, const char *place) {
+// test hook: GTSB_FAIL_AT="<rank>:<place>" makes that rank report an allocation failure at that
+// place; EVERY rank treats the place as a step that grows buffers (grew = true), as a real
+// growth step is rank-uniform
+int injected_failure(gtsb_context *c, const char *place, bool &grew) {
   const char *e = getenv("GTSB_FAIL_AT");
   if (e == nullptr) return 0;
-  char want[64];
-  snprintf(want, sizeof want, "%d:%s", c->rank, place);
-  if (strcmp(e, want) != 0) return 0;
+  const char *colon = strchr(e, ':');
+  if (colon == nullptr || strcmp(colon + 1, place) != 0) return 0;
+  grew = true;
+  if (atoi(e) != c->rank) return 0;
   return fail(c, "injected failure at '%s' on rank %d (GTSB_FAIL_AT)", place, c->rank);
 }
 
@@ -188,7 +226,15 @@ int exchange(gtsb_context *c, int local_rc, const char *where, const uint32_t *m
     if (all[(size_t) r * (n + 1)] && bad < 0) bad = r;
     for (int i = 0; i < n; i++) out[(size_t) r * n + i] = all[(size_t) r * (n + 1) + 1 + i];
   }
-  if (bad >= 0) return local_rc == 0 ? fail(c, "%s: rank %d failed (see its message)", where, bad) : -1;
+  if (bad >= 0) {
+    // Every rank is here.  The rank that failed did not grow the buffers its peers may just have
+    // grown, and rank-uniform capacities are what lets a step decide locally whether an agreement
+    // is due: give all of them back, so that the next call starts from equal (empty) buffers.
+    const std::string msg = c->err;
+    dist_reset_buffers(c);
+    c->err = msg;
+    return local_rc == 0 ? fail(c, "%s: rank %d failed (see its message)", where, bad) : -1;
+  }
   return 0;
 }
 
@@ -363,9 +409,8 @@ int dist_side_facts(gtsb_context *c, DistState *D, Plan &P) {
   const uint64_t Vg = c->V;
   bool grew = false;
   int rc = [&]() -> int {
-    if (injected_failure(c, "facts") != 0) { grew = true; return -1; }
+    if (injected_failure(c, "facts", grew) != 0) return -1;
     ENSURE_U(c->vinfo, (Vg + 1) * sizeof(uint2));
-    ENSURE_U(c->rep_pred, Vg + 1);
     uint64_t slot = 0;
     for (int r = 0; r < c->world; r++) slot = P.lo[r + 1] - P.lo[r] > slot ? P.lo[r + 1] - P.lo[r] : slot;
     ENSURE_U(D->side != nullptr ? D->stage2 : D->stage, (((size_t) slot * 8 + 15) & ~(size_t) 15) * c->world);
@@ -491,7 +536,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     ENSURE(D->bounds, (MAX_RANKS + 2) * 4);
     ENSURE(D->rank_cnt, (MAX_RANKS + 2) * 4);
     ENSURE(c->corrections, (size_t) (R / 8 + 4096) * sizeof(uint4));
-    if (injected_failure(c, "setup") != 0) return -1;
+    { bool unused = false; if (injected_failure(c, "setup", unused) != 0) return -1; }
     CK(cudaMemsetAsync(c->counters.p, 0, CNT_NUM * 4, s));
     CK(cudaMemsetAsync(c->pos.p, 0xFF, (Vg + 1) * 4, s));
     CK(cudaMemsetAsync(c->vstate.p, 0, Vg ? Vg : 1, s));
@@ -595,7 +640,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   // that rank's buffers (peer memory over NVLink) while it computes the next ones
   bool grew = false, rx_grew = false;
   rc = [&]() -> int {
-    if (injected_failure(c, "receive") != 0) { grew = true; return -1; }
+    if (injected_failure(c, "receive", grew) != 0) return -1;
     // 1/8 headroom: the buffers, and with them the peers' mappings, survive small changes
     if (ensure_u(c, D->rx_ent, (M_max + M_max / 8 + 16) * sizeof(uint4), rx_grew) != 0) { grew = true; return -1; }
     if (ensure_u(c, D->rx_dest, (M_max + M_max / 8 + 16) * 4, rx_grew) != 0) { grew = true; return -1; }
@@ -684,7 +729,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   if (c_off[N]) {
     bool grew = false;
     rc = [&]() -> int {
-      if (injected_failure(c, "corrections") != 0) { grew = true; return -1; }
+      if (injected_failure(c, "corrections", grew) != 0) return -1;
       ENSURE_U(D->corr_all, c_off[N] * sizeof(uint4));
       return 0;
     }();
@@ -701,8 +746,8 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     // window tables: sized by the largest share of rows / slots any rank holds (uniform growth)
     uint64_t rows_max = 0;
     for (int r = 0; r < N; r++) rows_max = P.lo[r + 1] - P.lo[r] > rows_max ? P.lo[r + 1] - P.lo[r] : rows_max;
-    const bool grew = c->wcount.cap < ((rows_max + 63) / 64 + 2) * 4 || c->win_start.cap < ((rows_max < P.E_max + 1 ? rows_max : P.E_max + 1) + 2) * 4;
-    rc = injected_failure(c, "windows") != 0 ? -1 : ensure_windows(c, rows_max, P.E_max + 1);
+    bool grew = c->wcount.cap < ((rows_max + 63) / 64 + 2) * 4 || c->win_start.cap < ((rows_max < P.E_max + 1 ? rows_max : P.E_max + 1) + 2) * 4;
+    rc = injected_failure(c, "windows", grew) != 0 ? -1 : ensure_windows(c, rows_max, P.E_max + 1);
     if (grew && agree(c, rc, "windows") != 0) return -1;
     if (!grew && rc != 0) return -1;
   }
@@ -735,14 +780,14 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   std::vector<uint32_t> all;
   FilterArgs a{};
   // sized by what the fullest rank holds, so that every rank's buffers grow in the same step
-  const bool grew = c->proposals.cap < (P.E_max + 1) * sizeof(uint2) || c->poly_cur.cap < (Vg + 1) * 4 ||
+  bool grew = c->proposals.cap < (P.E_max + 1) * sizeof(uint2) || c->poly_cur.cap < (Vg + 1) * 4 ||
                     c->vres.cap < (Vg + 1) * 4 ||
                     (P.big_rows_max != 0 &&
                      c->big_scratch.cap < (size_t) (P.big_rows_max < (uint32_t) c->sm_count * 2 ? P.big_rows_max
                                                                                                : (uint32_t) c->sm_count * 2) *
                                               P.deg_max * BIG_SCRATCH_STRIDE);
   int rc = [&]() -> int {
-    if (injected_failure(c, "filter") != 0) return -1;
+    if (injected_failure(c, "filter", grew) != 0) return -1;
     if (await_vertices(c) != 0) return -1;
     const uint32_t nb = c->n_big_rows, md = c->max_deg;
     c->n_big_rows = P.big_rows_max;                      // scratch for the largest hub population of any rank
@@ -789,7 +834,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   if (nprop) {
     bool pgrew = false;
     rc = [&]() -> int {
-      if (injected_failure(c, "proposals") != 0) { pgrew = true; return -1; }
+      if (injected_failure(c, "proposals", pgrew) != 0) return -1;
       if (ensure_u(c, D->prop_all, (size_t) nprop * sizeof(uint2), pgrew) != 0) return -1;
       return 0;
     }();
@@ -848,7 +893,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
       cap = (cap + 3u) & ~3u;
       {
         bool sgrew = false;
-        const int e = injected_failure(c, "fire") != 0 ? (sgrew = true, -1) : ensure_u(c, D->stage, (size_t) cap * 4 * N, sgrew);
+        const int e = injected_failure(c, "fire", sgrew) != 0 ? -1 : ensure_u(c, D->stage, (size_t) cap * 4 * N, sgrew);
         if (sgrew && agree(c, e, "fire round staging") != 0) return -1;
       }
       uint32_t *stage = D->stage.as<uint32_t>();

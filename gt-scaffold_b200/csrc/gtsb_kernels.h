@@ -95,6 +95,7 @@ struct Build2Args {
   int32_t *edist;
   float *estd;
   uint8_t *eflags;
+  uint32_t *win_rec, *creator_rec;          // optional (gtsb_want_win_rec): winning record per slot / creating record per pair
   // lines handed in as such (gtsb_set_record_lines_*): k3_lines instead of the head passes
   const uint32_t *line_root, *line_start;
   uint32_t n_lines;
@@ -119,6 +120,8 @@ struct ExportArgs {        // line layout -> plain CSR in vertex order
   const float *std_dev;
   const uint8_t *flags, *estate;
   uint32_t *row_ptr, *dst_o, *eid_o;
+  const uint32_t *win;                      // optional
+  uint32_t *win_o;
   int32_t *dist_o;
   float *std_o;
   uint8_t *flags_o, *estate_o;

@@ -72,7 +72,11 @@ int gtsb_want_win_rec(gtsb_context *ctx, int on);
 int gtsb_force_general_build(gtsb_context *ctx, int on);
 
 /* ---- inputs.  *_host variants copy from host memory (H2D on the context's
-   stream); *_device variants adopt device pointers that must stay valid. */
+   stream or on its copy stream, asynchronously): the host buffers must stay valid and
+   unmodified until the next gtsb_build / gtsb_pipeline / gtsb_synchronize /
+   gtsb_get_* call has returned (pageable memory is staged before the call returns;
+   PINNED memory is read by the DMA engine later).  *_device variants adopt device
+   pointers that must stay valid. */
 int gtsb_set_vertices_host(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
                            const float *astat, const float *copy_num);
 int gtsb_set_vertices_device(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
@@ -101,6 +105,17 @@ int gtsb_set_graph_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t nof_e
                         const float *std_dev, const uint8_t *flags, const uint32_t *seq_len,
                         const float *astat, const float *copy_num, const uint8_t *vstate,
                         const uint8_t *estate);
+
+/* ---- the resident graph between the three calls of the reference's driver (test.c:130-146):
+   gtsb_build leaves the graph on the device; mark_repeats and filter then need only what the host
+   may have changed in between.  gtsb_update_vertices_host refreshes the per-vertex attributes
+   (the .astat values gt_scaffolder_graph_mark_repeats reads, algorithms.c:140-141) and keeps
+   the graph and its states; gtsb_set_states_host overwrites the states (vstate[V]; edge states
+   in graph->edges[] order) when host code marked something itself.  Single-device graphs built
+   by gtsb_build. */
+int gtsb_update_vertices_host(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
+                              const float *astat, const float *copy_num);
+int gtsb_set_states_host(gtsb_context *ctx, const uint8_t *vstate, const uint8_t *estate_by_eid);
 
 /* ---- .de text on the device: the record loop of gt_scaffolder_parser_read_distances
    (gt_scaffolder_parser.c:323-388) -- 1024-byte fgets pieces, last character dropped,

@@ -51,8 +51,13 @@
 
 static gtsb_context *b200_ctx = NULL;
 
+static void b200_report(void);
+static void mirror_drop(void);
+
 static void b200_release(void)
 {
+  b200_report();
+  mirror_drop();
   gtsb_destroy(b200_ctx);
   b200_ctx = NULL;
 }
@@ -75,6 +80,84 @@ static void b200_die(const char *where)
   fprintf(stderr, "gt_scaffolder (B200): %s: %s\n", where,
           b200_ctx != NULL ? gtsb_error(b200_ctx) : "no CUDA device (there is no CPU fallback)");
   exit(EXIT_FAILURE);
+}
+
+/* ------------------------------------------------------------------ device mirror */
+
+/* GtScaffolderGraph has no spare field (graph.h:73-80), so the device-resident copy that
+   gt_scaffolder_graph_new_from_file leaves behind is kept in a side registry keyed by the
+   graph pointer (SURVEY.md 8(b) "ownership"): mark_repeats and filter then run on it and
+   only fetch states.  Before every use the host graph is compared with what the device
+   holds -- counts, array addresses, a fingerprint of every edge's endpoints and attributes,
+   and every state against a host shadow of the device's states; states the host changed in
+   between are sent over (1 B per item), anything else re-uploads the graph. */
+static struct {
+  const GtScaffolderGraph *graph;
+  const GtScaffolderGraphVertex *vertices;
+  const GtScaffolderGraphEdge *edges;
+  GtUword V, E;
+  uint64_t fingerprint;
+  uint8_t *vstate, *estate;               /* what the device holds (estate in graph->edges[] order) */
+  bool valid;
+} b200_mirror;
+static unsigned long b200_graph_uploads = 0, b200_state_uploads = 0, b200_mirror_hits = 0;
+
+static void mirror_drop(void)
+{
+  gt_free(b200_mirror.vstate);
+  gt_free(b200_mirror.estate);
+  memset(&b200_mirror, 0, sizeof b200_mirror);
+}
+
+static uint64_t mix64(uint64_t h, uint64_t x)
+{
+  h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
+}
+
+/* endpoints and attributes of every edge, adjacency sizes: what the device graph was built from */
+static uint64_t graph_fingerprint(const GtScaffolderGraph *graph)
+{
+  uint64_t h = 0;
+  GtUword i;
+  for (i = 0; i < graph->nof_edges; i++) {
+    const GtScaffolderGraphEdge *e = graph->edges + i;
+    uint32_t sd;
+    memcpy(&sd, &e->std_dev, sizeof sd);
+    h = mix64(h, (uint64_t) (e->start - graph->vertices));
+    h = mix64(h, (uint64_t) (e->end - graph->vertices));
+    h = mix64(h, (uint64_t) e->dist);
+    h = mix64(h, ((uint64_t) sd << 2) | (e->sense ? 2u : 0u) | (e->same ? 1u : 0u));
+  }
+  for (i = 0; i < graph->nof_vertices; i++)
+    h = mix64(h, graph->vertices[i].nof_edges);
+  return h;
+}
+
+static void mirror_remember(const GtScaffolderGraph *graph)
+{
+  GtUword i;
+  mirror_drop();
+  b200_mirror.graph = graph;
+  b200_mirror.vertices = graph->vertices;
+  b200_mirror.edges = graph->edges;
+  b200_mirror.V = graph->nof_vertices;
+  b200_mirror.E = graph->nof_edges;
+  b200_mirror.fingerprint = graph_fingerprint(graph);
+  b200_mirror.vstate = gt_malloc(graph->nof_vertices + 1);
+  b200_mirror.estate = gt_malloc(graph->nof_edges + 1);
+  for (i = 0; i < graph->nof_vertices; i++)
+    b200_mirror.vstate[i] = (uint8_t) graph->vertices[i].state;
+  for (i = 0; i < graph->nof_edges; i++)
+    b200_mirror.estate[i] = (uint8_t) graph->edges[i].state;
+  b200_mirror.valid = true;
+}
+
+static void b200_report(void)
+{
+  if (getenv("GTSB_VERBOSE") != NULL)
+    fprintf(stderr, "gt_scaffolder (B200): graph uploads %lu, calls on the resident graph %lu, "
+                    "state uploads %lu\n", b200_graph_uploads, b200_mirror_hits, b200_state_uploads);
 }
 
 /* ------------------------------------------------------------------ records */
@@ -469,6 +552,10 @@ int gt_scaffolder_graph_new_from_file(GtScaffolderGraph **graph_par,
   if (had_err != 0) {
     gt_scaffolder_graph_delete(graph);
     graph = NULL;
+    mirror_drop();
+  } else {
+    b200_graph_uploads++;                   /* the records: the one transfer of the graph */
+    mirror_remember(graph);
   }
   *graph_par = graph;
   return had_err;
@@ -586,6 +673,67 @@ static int graph_fetch_states(gtsb_context *c, GtScaffolderGraph *graph, B200Fla
   return 0;
 }
 
+/* Is the device-resident graph still this host graph?  If so bring its vertex attributes and
+   (where the host changed them) its states up to date and return 1; 0: not resident, the
+   caller uploads; -1: device error. */
+static int mirror_sync(gtsb_context *c, const GtScaffolderGraph *graph)
+{
+  B200Vertices vert;
+  uint8_t *vs, *es;
+  GtUword i;
+  bool dirty = false;
+  int rc = 1;
+  if (!b200_mirror.valid || getenv("GTSB_NO_MIRROR") != NULL)
+    return 0;
+  if (b200_mirror.graph != graph || b200_mirror.vertices != graph->vertices ||
+      b200_mirror.edges != graph->edges || b200_mirror.V != graph->nof_vertices ||
+      b200_mirror.E != graph->nof_edges || gtsb_nof_edges(c) != graph->nof_edges ||
+      b200_mirror.fingerprint != graph_fingerprint(graph)) {
+    mirror_drop();
+    return 0;
+  }
+  memset(&vert, 0, sizeof vert);
+  if (vertices_flatten(graph, &vert, NULL) != 0) {
+    vertices_free(&vert);
+    mirror_drop();
+    return 0;
+  }
+  vs = vert.vstate;
+  es = gt_malloc(graph->nof_edges + 1);
+  for (i = 0; i < graph->nof_vertices; i++)
+    dirty |= vs[i] != b200_mirror.vstate[i];
+  for (i = 0; i < graph->nof_edges; i++) {
+    es[i] = (uint8_t) graph->edges[i].state;
+    dirty |= es[i] != b200_mirror.estate[i];
+  }
+  if (gtsb_update_vertices_host(c, graph->nof_vertices, vert.seq_len, vert.astat, vert.copy_num) != 0)
+    rc = -1;
+  if (rc == 1 && dirty) {
+    b200_state_uploads++;
+    if (gtsb_set_states_host(c, vs, es) != 0)
+      rc = -1;
+  }
+  if (rc == 1)
+    b200_mirror_hits++;
+  gt_free(es);
+  vertices_free(&vert);
+  return rc;
+}
+
+/* states of the resident graph -> host graph and shadow */
+static int mirror_fetch_states(gtsb_context *c, GtScaffolderGraph *graph)
+{
+  GtUword i;
+  if (gtsb_get_vertex_states(c, b200_mirror.vstate) != 0 ||
+      gtsb_get_edge_states(c, b200_mirror.estate) != 0)
+    return -1;
+  for (i = 0; i < graph->nof_vertices; i++)
+    graph->vertices[i].state = (GraphItemState) b200_mirror.vstate[i];
+  for (i = 0; i < graph->nof_edges; i++)
+    graph->edges[i].state = (GraphItemState) b200_mirror.estate[i];
+  return 0;
+}
+
 /* ------------------------------------------------------------------ mark_repeats */
 
 int gt_scaffolder_graph_mark_repeats(const char *filename,
@@ -646,6 +794,19 @@ int gt_scaffolder_graph_mark_repeats(const char *filename,
       gt_error_set(err, "no CUDA device available (the B200 path has no CPU fallback)");
       return -1;
     }
+    const int resident = mirror_sync(c, graph);
+    if (resident == 1) {
+      if (gtsb_mark_repeats(c, copy_num_cutoff, astat_cutoff, have_file ? 1 : 0) != 0 ||
+          mirror_fetch_states(c, graph) != 0) {
+        gt_error_set(err, "%s", gtsb_error(c));
+        had_err = -1;
+      }
+      return had_err;
+    }
+    if (resident < 0) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      return -1;
+    }
     if (graph_flatten(graph, &f, "mark_repeats") != 0) {
       gt_error_set(err, "graph cannot be represented on the device");
       had_err = -1;
@@ -655,6 +816,7 @@ int gt_scaffolder_graph_mark_repeats(const char *filename,
       gt_error_set(err, "%s", gtsb_error(c));
       had_err = -1;
     }
+    b200_graph_uploads++;
     flat_free(&f);
   }
   return had_err;
@@ -669,13 +831,23 @@ void gt_scaffolder_graph_filter(GtScaffolderGraph *graph,
 {
   B200Flat f;
   gtsb_context *c = b200_context();
+  int resident;
   if (c == NULL)
     b200_die("gt_scaffolder_graph_filter");
+  resident = mirror_sync(c, graph);
+  if (resident < 0)
+    b200_die("gt_scaffolder_graph_filter");
+  if (resident == 1) {
+    if (gtsb_filter(c, pcutoff, cncutoff, (int64_t) ocutoff) != 0 || mirror_fetch_states(c, graph) != 0)
+      b200_die("gt_scaffolder_graph_filter");
+    return;
+  }
   if (graph_flatten(graph, &f, "filter") != 0)
     exit(EXIT_FAILURE);
   if (graph_upload(c, &f) != 0 || gtsb_filter(c, pcutoff, cncutoff, (int64_t) ocutoff) != 0 ||
       graph_fetch_states(c, graph, &f) != 0)
     b200_die("gt_scaffolder_graph_filter");
+  b200_graph_uploads++;
   flat_free(&f);
 }
 

@@ -96,7 +96,7 @@ def test_a_failing_rank_stops_all_ranks():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29519",
                         os.path.join(HERE, "dist_fail_check.py")], cwd=ROOT, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, timeout=900)
+                       stderr=subprocess.STDOUT, timeout=400)
     out = r.stdout.decode()
     assert r.returncode == 0, out[-3000:]
     assert out.count("-> OK") >= 16 and "BAD" not in out, out[-3000:]

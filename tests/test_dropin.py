@@ -92,6 +92,9 @@ def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth):
         r = _run(exe, ["scaffold", fa, de, astat, "false"], d, tok)
         assert r.returncode == 0, (name, r.stderr.decode()[-500:])
         if name != "ref":
+            # the graph crosses the bus ONCE (the records, in new_from_file); mark_repeats and
+            # filter run on the device-resident copy and only fetch states
+            assert b"graph uploads 1, calls on the resident graph 2" in r.stderr, (name, r.stderr.decode()[-500:])
             where = b"host" if (tok == "host" or irregular) else b"device"
             assert b"lib.de tokenised on the " + where in r.stderr, (name, r.stderr.decode()[-500:])
             if tok == "host":
@@ -107,3 +110,28 @@ def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth):
     changed = a != b
     if case != "tiny0":
         assert changed, "the filter stage did nothing on this input: the case pins nothing"
+
+
+@pytest.mark.gpu
+@needs_bin
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_binding_without_the_device_mirror(tmp_path, synth):
+    """GTSB_NO_MIRROR=1: every call flattens and uploads the host graph again (what a caller gets
+    that builds or edits the graph itself); same files."""
+    inp = synth.generate("c2_bacterial", V=1500, seed=5, mirror_diff_frac=0.2)
+    data = tmp_path / "in"
+    data.mkdir()
+    fa, de, astat = O.write_text_inputs(inp, str(data))
+    outs = {}
+    for name, exe, extra in (("ref", O.REF_TESTX, {}), ("b200", B200_TESTX, {"GTSB_NO_MIRROR": "1"})):
+        d = tmp_path / name
+        d.mkdir()
+        env = dict(os.environ, GTSB_VERBOSE="1", **extra)
+        r = subprocess.run([exe, "scaffold", fa, de, astat, "false"], cwd=d, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()[-500:]
+        if name == "b200":
+            assert b"graph uploads 3, calls on the resident graph 0" in r.stderr, r.stderr.decode()[-500:]
+        outs[name] = d
+    for f in OUTPUTS:
+        assert (outs["ref"] / f).read_bytes() == (outs["b200"] / f).read_bytes(), f

@@ -169,6 +169,25 @@ def test_win_rec_points_at_the_winning_record(pkg, synth):
     assert np.array_equal(seeded, rec_root != e["src"])
 
 
+def test_win_rec_on_the_line_ordered_build(pkg, synth):
+    """The same on .de-shaped input, which stays on the line-ordered build (the drop-in binding
+    needs the winning record of every edge for GtScaffolderGraphEdge.num_pairs)."""
+    for seed in range(6):
+        inp = synth.generate("c2_bacterial", V=300 + 500 * seed, seed=500 + seed, mean_pairs=2.0 + seed % 3,
+                             mirror_diff_frac=0.4, dup_same_line_frac=0.3, one_sided_frac=0.2, one_sided_up=True)
+        g = pkg.ScaffoldGraphB200.new_from_records(inp, want_win_rec=True)
+        assert g.stats()["line_ordered_build"] == 1
+        c = g.csr(win_rec=True)
+        ref = O.PortGraph(inp)
+        e = ref.edges()
+        order = np.argsort(c["eid"])
+        win = c["win_rec"][order]
+        assert np.array_equal((win & 0x7FFFFFFF).astype(np.int64), e["win_rec"]), seed
+        seeded = (win >> 31).astype(bool)
+        assert np.array_equal(seeded, inp.root[(win & 0x7FFFFFFF)] != e["src"]), seed
+        g.close()
+
+
 def test_filter_on_uploaded_graph_with_arbitrary_states(pkg, synth):
     """gtsb_set_graph_host path (what the GtScaffolderGraph binding uses)."""
     rng = np.random.default_rng(11)
