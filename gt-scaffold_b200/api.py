@@ -37,7 +37,7 @@ EXPORTS = [
     "gtsb_set_record_lines_host", "gtsb_set_record_lines_device", "gtsb_update_vertices_host",
     "gtsb_set_states_host", "gtsb_get_edge_states",
     "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
-    "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host",
+    "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host", "gtsb_scaf_lines_host",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
     L.gtsb_parse_astat_host.argtypes = [vp, C.c_char_p, u64, vp, vp, C.POINTER(C.c_uint32)]
     L.gtsb_dot_vertex_lines_host.argtypes = [vp, i32, u64, u64, vp, C.c_char_p, u64, C.POINTER(u64)]
     L.gtsb_dot_edge_lines_host.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp, C.c_char_p, u64, C.POINTER(u64)]
+    L.gtsb_scaf_lines_host.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_char_p, u64, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -275,6 +276,17 @@ class ScaffoldGraphB200:
         n = C.c_uint64(0)
         self._ck(self.L.gtsb_dot_edge_lines_host(self.h, int(scaffold_only), len(a[0]), *[_ptr(x) for x in a],
                                                  out, cap, C.byref(n)))
+        return out.raw[:n.value]
+
+    def scaf_lines(self, rec_root, rec_edge_off, edge_end, edge_dist, edge_std_dev, edge_flags, cap: int):
+        """The `.scaf` text of gt_scaffolder_graph_write_scaffold (algorithms.c:1000-1042) for records
+        given as flat arrays; vertex ids index the names set."""
+        a = [np.ascontiguousarray(rec_root, np.uint32), np.ascontiguousarray(rec_edge_off, np.uint64),
+             np.ascontiguousarray(edge_end, np.uint32), np.ascontiguousarray(edge_dist, np.int64),
+             np.ascontiguousarray(edge_std_dev, np.float32), np.ascontiguousarray(edge_flags, np.uint8)]
+        out = C.create_string_buffer(cap + 16)
+        n = C.c_uint64(0)
+        self._ck(self.L.gtsb_scaf_lines_host(self.h, len(a[0]), *[_ptr(x) for x in a], out, cap, C.byref(n)))
         return out.raw[:n.value]
 
     def records(self, num_pairs: bool = True):

@@ -328,7 +328,7 @@ int do_build_lines(gtsb_context *c) {
   ENSURE(c->cursor2, ngrp * 4);
   ENSURE(c->tmp_ent, R * sizeof(uint4));
   ENSURE(c->tmp_dest, R * 4);
-  ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
+  ENSURE(c->tmp_cursor, (NB_COARSE2 + 2) * 4);
   ENSURE(c->bucket, R * sizeof(uint4));
   ENSURE(c->bucket_line, R + 16);
   const uint32_t corr_cap = (uint32_t) (R / 8 + 4096);
@@ -353,8 +353,13 @@ int do_build_lines(gtsb_context *c) {
   a.V = (uint32_t) V;
   a.Vg = (uint32_t) V;
   a.sm_count = c->sm_count;
+  {
+    const char *e = getenv("GTSB_MAIL");               // 0: the per-entry scatter passes (dev switch)
+    a.mail_sorted = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  a.nb_coarse = a.mail_sorted ? NB_COARSE2 : NB_COARSE;
   uint32_t shift = 0;
-  while (((V ? V - 1 : 0) >> shift) >= (uint64_t) NB_COARSE) shift++;
+  while (((V ? V - 1 : 0) >> shift) >= (uint64_t) a.nb_coarse) shift++;
   a.coarse_shift = shift;
   a.corrections_cap = corr_cap;
   a.root = c->root.as<uint32_t>();
@@ -661,21 +666,37 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   }
   // phase 2: fire candidates (static answer, recomputed next to polymorphic
   // vertices), then the order-respecting fire fixpoint
-  CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
-  launch_fire_init(a, s);
+  static const int coop = [] {
+    const char *e = getenv("GTSB_FIRE");                 // 1: one launch per fire round (dev switch)
+    return (e != nullptr && atoi(e) == 1) ? 0 : 1;
+  }();
+  // the worklist that fire_init_big and the dense round fill: its length lives in ring[0] when
+  // the cooperative rounds kernel follows (the counters were cleared above)
+  uint32_t *n_dense = coop ? cnt + CNT_RING0 : cnt + CNT_WORK_B;
+  CK(cudaMemsetAsync(n_dense, 0, 4, s));
+  launch_fire_init(a, n_dense, s);
   c->stats.kernel_launches += (V ? 2 : 0) + (V && c->n_big_rows ? 1 : 0);
   c->stats.fire_rounds = 0;
+  c->fire_ring_pending = false;
   uint32_t *win = a.work_b, *wout = a.work_a;
   int in_idx = CNT_WORK_B, out_idx = CNT_WORK_A;
   uint32_t n_in = 0;
+  bool rounds_done = false;
   if (ocutoff >= 0 && V) {
-    launch_fire_dense(a, a.work_b, cnt + CNT_WORK_B, s);
+    launch_fire_dense(a, a.work_b, n_dense, s);
     c->stats.kernel_launches += E ? 1 : 0;
     c->stats.fire_rounds++;
-    if (read_counters(c) != 0) return -1;
-    n_in = c->h_counters[CNT_WORK_B];
+    if (coop && launch_fire_rounds_all(a, cnt + CNT_RING0, (uint32_t) (V + 2), s) == 0) {
+      c->stats.kernel_launches += 1;
+      rounds_done = true;                              // the round count is read with the final counters
+      c->fire_ring_pending = true;
+    } else {
+      if (coop) CK(cudaMemcpyAsync(cnt + CNT_WORK_B, cnt + CNT_RING0, 4, cudaMemcpyDeviceToDevice, s));
+      if (read_counters(c) != 0) return -1;
+      n_in = c->h_counters[CNT_WORK_B];
+    }
   }
-  while (n_in) {
+  while (n_in && !rounds_done) {
     // worklists only shrink: n_in bounds the next rounds' lists, so a few rounds are queued per sync
     for (int k = 0; k < FIRE_ROUNDS_PER_SYNC; k++) {
       CK(cudaMemsetAsync(cnt + out_idx, 0, 4, s));
@@ -1212,6 +1233,12 @@ int gtsb_device_pointers(gtsb_context *c, const uint32_t **row_ptr, const uint32
 
 int gtsb_get_stats(gtsb_context *c, gtsb_stats *st) {
   if (c == nullptr || st == nullptr) return -1;
+  if (c->fire_ring_pending) {                        // rounds run by the cooperative fire kernel
+    c->fire_ring_pending = false;
+    if (read_counters(c) != 0) return -1;
+    c->stats.fire_rounds += c->h_counters[CNT_RING_ROUNDS];
+    if (c->h_counters[CNT_RING_ROUNDS] >= c->V + 2 && c->V) return fail(c, "gtsb_filter: fire rounds did not converge");
+  }
   c->stats.nof_vertices = c->V;
   c->stats.line_ordered_build = c->line_layout ? 1u : 0u;
   c->stats.fallback_reason = c->fallback_reason;

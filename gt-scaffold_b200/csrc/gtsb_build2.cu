@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_classify(Build2Args a) {
   __shared__ uint32_t s_bounds[MAX_RANKS + 1], s_rcnt[MAX_RANKS];
   // 256-bit Bloom filter per line over its neighbours: a line whose records all hit distinct
   // bits has no repeated neighbour, and the quadratic duplicate scan is skipped for it
+  // (512 bits measured slower: 1.00 vs 0.82 ms at C3, the extra shared memory costs residency)
   __shared__ uint32_t s_bloom[SEG_LINES][8];
   __shared__ uint8_t s_maydup[SEG_LINES];
   Seg g;
@@ -286,7 +287,7 @@ __global__ void k2_init_cursors(Build2Args a) {
     }
     return;
   }
-  if (b > NB_COARSE) return;
+  if (b > a.nb_coarse) return;
   const uint64_t p = (uint64_t) b << a.coarse_shift;
   a.tmp_cursor[b] = a.bptr[p < a.V ? p : a.V];
 }
@@ -413,9 +414,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
 }
 
 // every group's cursor starts at the offset of its mailbox region
-__global__ void __launch_bounds__(256) k2_init_group_cursors(Build2Args a) {
+__global__ void __launch_bounds__(256) k2_init_group_cursors(Build2Args a, int group_shift) {
   const uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t p = (uint64_t) grp << GROUP_SHIFT;
+  const uint64_t p = (uint64_t) grp << group_shift;
   if (p < a.V) a.cursor[grp] = a.bptr[p];
 }
 
@@ -450,6 +451,214 @@ __global__ void __launch_bounds__(256) k2_deliver(Build2Args a) {
         a.bucket[at[k]] = ent[k];
         a.bucket_line[at[k]] = (uint8_t) (pc[k] & (SEG_LINES - 1));
       }
+  }
+}
+
+// ------------------------------------------------------------------ mail, tile-sorted (single device)
+//
+// The two passes above move every entry with one 16-byte store of its own (and k2_deliver one
+// returning atomic per entry): 1.2e8 scattered L2 transactions for 4e7 entries, which is what
+// bounds them (profiles/r01_microbench_scatter.txt: 16-byte scatters run at 30-50 G/s whatever the
+// window).  The tile-sorted variants counting-sort a tile of entries by bin in shared memory, take
+// ONE cursor atomic per (tile, non-empty bin) and store the sorted tile with consecutive threads,
+// so that entries of a bin leave as runs: pass A bins by NB_COARSE2 position ranges, pass B by
+// resolve segment (RSEG_LINES positions) inside the few coarse bins a tile touches.
+
+constexpr int P2_THREADS = 512;
+constexpr uint32_t P2_ENT_CAP = 2432;        // entries staged per flush of pass A (>= SEG_REC_CAP)
+static_assert(P2_ENT_CAP >= SEG_REC_CAP, "one segment's creators must fit the staging buffer");
+constexpr int P2_SEGS = 12;                  // 128-line segments per block of pass A
+constexpr int D2_THREADS = 512;
+constexpr uint32_t D2_TILE = 3072;           // entries per block of pass B
+constexpr uint32_t D2_BINS = 2048;           // resolve segments a tile of pass B may span
+constexpr int RSEG_SHIFT = 6;
+static_assert((1 << RSEG_SHIFT) == RSEG_LINES, "RSEG_SHIFT");
+
+// Counting sort of n staged items by key (< nbins) and reservation of their output ranges:
+// s_perm[t] = item at sorted place t, s_off[b] = first sorted place of bin b (s_off[nbins] = n),
+// s_gbase[b] = what the bin's global cursor held before this tile's share was added.
+// All threads of the block call it; nbins <= 4 * blockDim.x.
+__device__ __forceinline__ void tile_sort(uint32_t n, uint32_t nbins, const uint16_t *s_key, uint16_t *s_rank,
+                                          uint16_t *s_perm, uint32_t *s_off, uint32_t *s_gbase,
+                                          uint32_t *cursors) {
+  for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x) s_off[b] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_rank[i] = (uint16_t) atomicAdd(&s_off[s_key[i]], 1u);
+  __syncthreads();
+  uint32_t v[4], sum = 0;
+  const uint32_t base = threadIdx.x * 4u;
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    v[k] = base + k < nbins ? s_off[base + k] : 0u;
+    sum += v[k];
+  }
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++)
+    if (v[k]) s_gbase[base + k] = atomicAdd(&cursors[base + k], v[k]);
+  uint32_t total;
+  uint32_t ex = block_excl_scan(sum, &total);           // syncs: every count is read before any offset is written
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    if (base + k < nbins) s_off[base + k] = ex;
+    ex += v[k];
+  }
+  if (threadIdx.x == 0) s_off[nbins] = total;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_perm[s_off[s_key[i]] + s_rank[i]] = (uint16_t) i;
+  __syncthreads();
+}
+
+// pass A: the creators of P2_SEGS consecutive segments build their mailbox entries into a staging
+// buffer; a buffer that cannot take the next segment's creators is sorted by coarse bin and
+// written in runs.  No block-wide scan: a warp takes 32 consecutive records, a creator's rank k is
+// k0[line] + (creators of its line before it) -- a ballot inside the warp, a short loop over the
+// flag bytes for the part of the first line that lies before the warp's records -- and the warp
+// reserves its buffer places with one shared-memory atomic.
+__global__ void __launch_bounds__(P2_THREADS) k2_partition2(Build2Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (block_abort(a.counters)) return;
+  uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
+  uint32_t *s_dest = reinterpret_cast<uint32_t *>(s_ent + P2_ENT_CAP);
+  uint32_t *s_off = s_dest + P2_ENT_CAP;                    // [NB_COARSE2 + 4]
+  uint32_t *s_gbase = s_off + NB_COARSE2 + 4;
+  uint32_t *s_ls = s_gbase + NB_COARSE2;                    // [SEG_LINES + 4]
+  uint32_t *s_k0 = s_ls + SEG_LINES + 4;                    // [SEG_LINES + 4]
+  uint16_t *s_key = reinterpret_cast<uint16_t *>(s_k0 + SEG_LINES + 4);
+  uint16_t *s_rank = s_key + P2_ENT_CAP;
+  uint16_t *s_perm = s_rank + P2_ENT_CAP;
+  uint8_t *s_rf = reinterpret_cast<uint8_t *>(s_perm + P2_ENT_CAP);
+  uint8_t *s_line = s_rf + SEG_REC_CAP;
+  __shared__ uint32_t s_nent;
+  const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
+  const uint32_t seg0 = blockIdx.x * P2_SEGS, seg1 = min(nseg, seg0 + P2_SEGS);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_nent = 0;
+  auto flush = [&]() {                                      // called by every thread, after a barrier
+    const uint32_t n = s_nent;
+    tile_sort(n, a.nb_coarse, s_key, s_rank, s_perm, s_off, s_gbase, a.tmp_cursor);
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+      const uint32_t i = s_perm[t], b = s_key[i];
+      const uint32_t at = s_gbase[b] + (t - s_off[b]);
+      a.tmp_ent[at] = s_ent[i];
+      a.tmp_dest[at] = s_dest[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_nent = 0;
+  };
+  for (uint32_t sg = seg0; sg < seg1; sg++) {
+    Seg g;
+    __syncthreads();                                        // the previous segment is done with the staging
+    if (!seg_open(a, sg, g, s_ls)) return;
+    for (uint32_t j = threadIdx.x; j <= g.nlines; j += blockDim.x) s_k0[j] = a.k0[g.p0 + j];
+    __syncthreads();
+    if (s_nent + (s_k0[g.nlines] - s_k0[0]) > P2_ENT_CAP) flush();      // block-uniform
+    seg_lines(a, g, s_ls, s_line);
+    for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x) s_rf[r] = a.rf[g.rec0 + r];
+    __syncthreads();
+    for (uint32_t w0 = warp * 32u; w0 < g.n; w0 += nwarps * 32u) {
+      const uint32_t r = w0 + lane;
+      const uint32_t rf = r < g.n ? s_rf[r] : 0u;
+      const bool creator = (rf & RF_CREATOR) == RF_CREATOR;
+      const uint32_t cm = __ballot_sync(0xffffffffu, creator);
+      if (cm == 0u) continue;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_nent, (uint32_t) __popc(cm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!creator) continue;
+      const uint32_t below = (1u << lane) - 1u;
+      const uint32_t idx = base + __popc(cm & below);
+      const uint32_t j = s_line[r];
+      const uint32_t t0 = s_ls[j] - g.rec0, t1 = s_ls[j + 1] - g.rec0;   // the line's records
+      uint32_t before;
+      if (t0 >= w0) {
+        before = __popc(cm & below & ~((1u << (t0 - w0)) - 1u));
+      } else {
+        before = __popc(cm & below);
+        for (uint32_t t = t0; t < w0; t++) before += (s_rf[t] & RF_CREATOR) == RF_CREATOR ? 1u : 0u;
+      }
+      const uint64_t gr = (uint64_t) g.rec0 + r;
+      const uint32_t pc = a.pc[gr];
+      const float sd = a.std_dev[gr];
+      const uint32_t sf = a.flags[gr];
+      // final flags of edge root->c: strict running maximum over the line's records
+      float best = sd;
+      uint32_t bf = sf;
+      if (rf & RF_DUP)
+        for (uint32_t t = r + 1; t < t1; t++) {
+          const float st = a.std_dev[g.rec0 + t];
+          if (a.pc[g.rec0 + t] == pc && best < st) {
+            best = st;
+            bf = a.flags[g.rec0 + t];
+          }
+        }
+      uint4 e;
+      e.x = a.k_base + s_k0[j] + before;
+      e.y = (a.pos_base + g.p0 + j) | ((sf & F_SENSE) ? M_SEED_SENSE : 0u) | ((sf & F_SAME) ? M_SEED_SAME : 0u) |
+            ((bf & F_SENSE) ? M_FWD_SENSE : 0u) | ((bf & F_SAME) ? M_FWD_SAME : 0u) | ((rf & RF_LT) ? 0u : M_LT);
+      e.z = (uint32_t) a.dist[gr];
+      e.w = __float_as_uint(sd);
+      s_ent[idx] = e;
+      s_dest[idx] = pc;
+      s_key[idx] = (uint16_t) (pc >> a.coarse_shift);
+    }
+  }
+  __syncthreads();
+  flush();
+}
+
+// pass B: a tile of coarsely sorted entries, sorted by destination segment and written in runs
+// into the segments' mailbox regions (k2_resolve sorts a segment's mail by line)
+__global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (block_abort(a.counters)) return;
+  uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
+  uint32_t *s_dest = reinterpret_cast<uint32_t *>(s_ent + D2_TILE);
+  uint32_t *s_off = s_dest + D2_TILE;                       // [D2_BINS + 4]
+  uint32_t *s_gbase = s_off + D2_BINS + 4;
+  uint16_t *s_key = reinterpret_cast<uint16_t *>(s_gbase + D2_BINS);
+  uint16_t *s_rank = s_key + D2_TILE;
+  uint16_t *s_perm = s_rank + D2_TILE;
+  __shared__ uint32_t s_lo, s_hi;
+  const uint32_t n = a.bptr[a.V];
+  const uint64_t tile0 = (uint64_t) blockIdx.x * D2_TILE;
+  if (tile0 >= n) return;
+  const uint32_t cnt = (uint32_t) min((uint64_t) D2_TILE, n - tile0);
+  if (threadIdx.x == 0) {
+    s_lo = UNSET;
+    s_hi = 0;
+  }
+  __syncthreads();
+  uint32_t lo = UNSET, hi = 0;
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const uint32_t d = a.mail_dest[tile0 + i] - a.pos_base;
+    s_dest[i] = d;
+    s_ent[i] = a.mail_ent[tile0 + i];
+    lo = min(lo, d >> RSEG_SHIFT);
+    hi = max(hi, d >> RSEG_SHIFT);
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane_id() == 0) {
+    atomicMin(&s_lo, lo);
+    atomicMax(&s_hi, hi);
+  }
+  __syncthreads();
+  const uint32_t f_lo = s_lo, nf = s_hi - s_lo + 1u;
+  if (nf > D2_BINS) {                                       // entries from all over (unsorted input): one by one
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint32_t at = atomicAdd(&a.cursor[s_dest[i] >> RSEG_SHIFT], 1u);
+      a.bucket[at] = s_ent[i];
+      a.bucket_line[at] = (uint8_t) (s_dest[i] & (SEG_LINES - 1));
+    }
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_key[i] = (uint16_t) ((s_dest[i] >> RSEG_SHIFT) - f_lo);
+  tile_sort(cnt, nf, s_key, s_rank, s_perm, s_off, s_gbase, a.cursor + f_lo);
+  for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+    const uint32_t i = s_perm[t], b = s_key[i];
+    const uint32_t at = s_gbase[b] + (t - s_off[b]);
+    a.bucket[at] = s_ent[i];
+    a.bucket_line[at] = (uint8_t) (s_dest[i] & (SEG_LINES - 1));
   }
 }
 
@@ -721,6 +930,10 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
 
 size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
 size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
+size_t build2_smem_partition2() {
+  return P2_ENT_CAP * (16 + 4 + 6) + (2 * NB_COARSE2 + 4) * 4 + 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 2 + 16;
+}
+size_t build2_smem_deliver2() { return D2_TILE * (16 + 4 + 6) + (2 * D2_BINS + 4) * 4 + 16; }
 size_t build2_smem_resolve() { return RSEG_ENT_CAP * 19 + 4 * (RSEG_LINES + 4) * 4 + RSEG_REC_CAP * 11 + 16; }
 
 static void build2_attrs() {
@@ -729,6 +942,8 @@ static void build2_attrs() {
   cudaFuncSetAttribute(k2_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_classify());
   cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
   cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
+  cudaFuncSetAttribute(k2_partition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition2());
+  cudaFuncSetAttribute(k2_deliver2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_deliver2());
   attr_done = true;
 }
 
@@ -790,8 +1005,11 @@ int launch_b2_partition(const Build2Args &a, cudaStream_t s) {
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
   if (nseg == 0) return 0;
   KernelTimer t_("k2_partition", s);
-  k2_init_cursors<<<1, 128, 0, s>>>(a);
-  k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
+  k2_init_cursors<<<(a.nb_coarse + 128) / 128, 128, 0, s>>>(a);
+  if (a.mail_sorted && a.nranks == 0)
+    k2_partition2<<<(nseg + P2_SEGS - 1) / P2_SEGS, P2_THREADS, build2_smem_partition2(), s>>>(a);
+  else
+    k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
   return 2;
 }
 
@@ -808,9 +1026,17 @@ int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
   if (nseg == 0) return 0;
   {
     KernelTimer t_("k2_deliver", s);
-    const uint32_t ngrp = (a.V >> GROUP_SHIFT) + 1;
-    k2_init_group_cursors<<<(ngrp + 255) / 256, 256, 0, s>>>(a);
-    k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
+    if (a.mail_sorted && a.nranks == 0) {
+      const uint32_t nsg = (a.V >> RSEG_SHIFT) + 1;
+      k2_init_group_cursors<<<(nsg + 255) / 256, 256, 0, s>>>(a, RSEG_SHIFT);
+      // the grid covers every record (an upper bound of the mail the device knows only after the scan)
+      const uint64_t tiles = (a.R + D2_TILE - 1) / D2_TILE;
+      k2_deliver2<<<(uint32_t) (tiles ? tiles : 1), D2_THREADS, build2_smem_deliver2(), s>>>(a);
+    } else {
+      const uint32_t ngrp = (a.V >> GROUP_SHIFT) + 1;
+      k2_init_group_cursors<<<(ngrp + 255) / 256, 256, 0, s>>>(a, GROUP_SHIFT);
+      k2_deliver<<<a.sm_count * 8, 256, 0, s>>>(a);
+    }
   }
   KernelTimer t_("k2_resolve", s);
   k2_resolve<<<(a.V + RSEG_LINES - 1) / RSEG_LINES, SEG_THREADS, build2_smem_resolve(), s>>>(a);

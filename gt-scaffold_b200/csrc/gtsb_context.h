@@ -50,6 +50,7 @@ struct gtsb_context {
   uint64_t n_lines = 0;
   bool line_layout = false;     // rows in .de line order (rs/re/vid/pos) instead of plain CSR
   bool csr_exported = false;    // plain CSR copy of a line-layout graph is current
+  bool fire_ring_pending = false;   // the round count of k_fire_rounds_all is still on the device
 
   // inputs
   DevBuf vattr, astat, seq_len_in, copy_num_in;
@@ -74,6 +75,7 @@ struct gtsb_context {
   DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,
       p_line_cnt, p_line_off, num_pairs, p_last, p_astat, p_copy_num;
   DevBuf f_state, f_sense, f_src, f_dst, f_dist, f_len, f_off, f_out;     // .dot lines (gtsb_format.cu)
+  DevBuf s_root, s_recoff, s_end, s_dist, s_std, s_flags, s_len_r, s_off_r;   // .scaf records (gtsb_format.cu)
   uint64_t names_V = 0, names_mask = 0;
   bool have_names = false, names_dup = false, have_num_pairs = false;
 

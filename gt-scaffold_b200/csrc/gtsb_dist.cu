@@ -866,7 +866,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
 
   // phase 2
   CK(cudaMemsetAsync(cnt + CNT_WORK_B, 0, 4, s));
-  launch_fire_init(a, s);
+  launch_fire_init(a, cnt + CNT_WORK_B, s);
   c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
   if (allgatherv(c, "nccl_allgather_fstat", c->fstat.p, 1, P.lo) != 0) return -1;
   c->stats.fire_rounds = 0;

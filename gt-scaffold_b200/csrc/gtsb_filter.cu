@@ -42,6 +42,8 @@
 //   vinfo[p] = {copy_num, seq_len | marked-on-entry << 31}          (pairs pass)
 //   vres[p]  = polyTime (27 bits) | F[p,antisense] | F[p,sense] | repeat-pred
 //                                                                   (final pass)
+#include <stdlib.h>
+#include <cooperative_groups.h>
 #include "gtsb_common.cuh"
 #include "gtsb_scan.cuh"
 #include "gtsb_kernels.h"
@@ -469,6 +471,97 @@ __global__ void __launch_bounds__(32 * WARPS, 8) k4_pairs(FilterArgs a) {
     });
 }
 
+// The same pass with far fewer pair evaluations.  All that phase 2 needs from a (row, direction)
+// is whether SOME pair of unmarked edges overlaps by more than ocutoff, and most groups have such a
+// pair among neighbouring slots.  Step A: every unmarked slot is tested against the NEXT unmarked
+// slot of its group -- one pair per lane, partner by shuffle, no dealing.  Step B deals out only
+// what is left: the other pairs of the groups that have not fired yet, and (for the polymorphic
+// test, algorithms.c:232-238) the pairs with a member of low copy number -- a pair can propose only
+// if cn1 + cn2 < cncutoff, so one of the two lies below cncutoff / 2 (taken with a margin that
+// covers the rounding of the float sum; the exact test decides).
+// (Walking ALL pairs per slot, lane i stepping through its partners, measured slower than dealing
+// them: 1.86 vs 1.59 ms at C3.)
+template <int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) k4_pairs3(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  const uint32_t lane = lane_id();
+  const float half = __fmul_rn(a.cncutoff, 0.5f);
+  const float low_bound = half + fabsf(half) * 1e-6f + 1e-30f;
+  for_each_window<1>(g,
+    [&](uint32_t start, uint32_t n) {
+      PairsState t;
+      t.start = start;
+      t.n = n;
+      const bool valid = lane < n;
+      const uint32_t s = start + lane;
+      t.sp = valid ? __ldcs(g.srcp + s) : NONE;
+      t.dst = valid ? __ldcs(g.dst + s) : 0u;
+      t.fl = valid ? __ldcs(g.flags + s) : 0u;
+      t.me.dist = valid ? __ldcs(g.dist + s) : 0;
+      t.me.std_dev = valid ? __ldcs(g.std_dev + s) : 0.f;
+      t.es = (valid && !a.fused_repeats) ? __ldcs(g.estate + s) : (uint8_t) 0;
+      return t;
+    },
+    [&](PairsState &t) {
+      const bool valid = lane < t.n;
+      t.own_y = valid ? a.vinfo[t.sp & S_POS].y : VI_MARKED;
+      t.vi = valid ? a.vinfo[t.dst] : make_uint2(0u, 0u);
+    },
+    [&](PairsState &t) {
+      const Window W = open_window(t.start, t.n, t.sp);
+      const bool act = W.valid && !(t.own_y & VI_MARKED) && (W.ve - W.vb) >= 2u;
+      if (!__any_sync(FULL, act)) return;
+      SlotFacts me = t.me;
+      me.cn = __uint_as_float(t.vi.x);
+      me.len = t.vi.y & ~VI_MARKED;
+      const bool wm = (t.vi.y & VI_MARKED) != 0;
+      const bool ok = act && (a.fused_repeats ? !wm : !edge_state_marked(t.es)) && a.ocutoff >= 0;
+      const bool sense = (t.fl & F_SENSE) != 0;
+      const bool low = act && !(me.cn > low_bound);
+      const uint32_t A = __ballot_sync(FULL, act), S = __ballot_sync(FULL, act && sense);
+      const uint32_t OK = __ballot_sync(FULL, ok), LOW = __ballot_sync(FULL, low);
+      const uint32_t higher = lane == 31u ? 0u : FULL << (lane + 1u);
+      const uint32_t grp = act ? (W.rowmask & (sense ? S : (A & ~S))) : 0u;     // my row and direction
+      // step A: the next unmarked slot of the group
+      const uint32_t cand = ok ? (grp & OK & higher) : 0u;
+      const uint32_t nxt = cand ? (uint32_t) __ffs(cand) - 1u : lane;
+      const int32_t d2 = __shfl_sync(FULL, me.dist, nxt);
+      const uint32_t l2 = __shfl_sync(FULL, me.len, nxt);
+      uint32_t fire_mask = __ballot_sync(FULL, cand != 0u && interval_overlap(me.dist, me.len, d2, l2) > a.ocutoff);
+      const bool fired = (fire_mask & grp) != 0u;
+      // step B: what is left
+      uint32_t P = 0;
+      if (act) {
+        uint32_t rest = LOW;
+        if (low) rest = FULL;
+        else if (ok && !fired) rest |= OK & ~(cand ? 1u << nxt : 0u);
+        P = grp & higher & rest;
+      }
+      uint32_t prop_mask = 0;
+      if (__any_sync(FULL, P != 0u)) {
+        for_each_pair(P, [&](bool live, uint32_t i, uint32_t j) {
+          const SlotFacts e1 = shfl_facts(me, i), e2 = shfl_facts(me, j);   // e1 = earlier adjacency slot
+          uint32_t hit = 0, fire = 0;
+          if (live) {
+            // check_mark_polymorphic, algorithms.c:232-238
+            if (__fadd_rn(e1.cn, e2.cn) < a.cncutoff &&
+                ambiguous_order(e1.dist, e1.std_dev, e2.dist, e2.std_dev, a.ambig))
+              hit = 1u << (e1.cn < e2.cn ? i : j);
+            if (((OK >> i) & (OK >> j) & 1u) && interval_overlap(e1.dist, e1.len, e2.dist, e2.len) > a.ocutoff)
+              fire = 1u << i;
+          }
+          prop_mask |= __reduce_or_sync(FULL, hit);
+          fire_mask |= __reduce_or_sync(FULL, fire);
+        });
+      }
+      // proposals (target must be unmarked, algorithms.c:242)
+      warp_append2(act && ((prop_mask >> lane) & 1u) && !wm, make_uint2(W.row, t.dst), a.proposals,
+                   a.proposals_cap, &g.counters[CNT_PROPOSALS], &g.counters[CNT_OVERFLOW]);
+      const uint32_t g1 = fire_mask & W.rowmask & S, g0 = fire_mask & W.rowmask & ~S;
+      if (W.head && act && (g0 | g1)) a.gbits[W.row] = (uint8_t) ((g0 ? 1u : 0u) | (g1 ? 2u : 0u));
+    });
+}
+
 // block per big row; per-block scratch: copy_num[max_deg] f32, low[max_deg] u32, mark[max_deg] u8.
 // A pair can only propose if cn1 + cn2 < cncutoff, so one of the two has cn < cncutoff / 2:
 // only the pairs with at least one such "low" slot are evaluated (|low| x d instead of d^2 / 2).
@@ -535,7 +628,20 @@ void launch_pairs(const FilterArgs &a, cudaStream_t s) {
   if (a.g.E == 0) return;
   {
     KernelTimer t_("k4_pairs", s);
-    k4_pairs<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
+    static const int pruned = [] {
+      const char *e = getenv("GTSB_PAIRS");              // 1: every pair dealt to the lanes (dev switch)
+      return (e != nullptr && atoi(e) == 1) ? 0 : 1;
+    }();
+    static const int occ6 = [] {
+      const char *e = getenv("GTSB_PAIRS_OCC");          // 6: 40 registers, 6 blocks per SM (dev switch)
+      return (e != nullptr && atoi(e) == 6) ? 1 : 0;
+    }();
+    if (pruned && occ6)
+      k4_pairs3<6><<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
+    else if (pruned)
+      k4_pairs3<8><<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
+    else
+      k4_pairs<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_pairs_big", s);
@@ -772,7 +878,7 @@ __global__ void __launch_bounds__(512) k4_fire_init_big(FilterArgs a, uint32_t *
   }
 }
 
-void launch_fire_init(const FilterArgs &a, cudaStream_t s) {
+void launch_fire_init(const FilterArgs &a, uint32_t *n_work_b, cudaStream_t s) {
   if (a.g.V == 0) return;
   {
     KernelTimer t_("k4_fire_init(2 kernels)", s);
@@ -781,7 +887,7 @@ void launch_fire_init(const FilterArgs &a, cudaStream_t s) {
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_fire_init_big", s);
-    k4_fire_init_big<<<a.big_blocks, 512, 0, s>>>(a, a.work_b, &a.g.counters[CNT_WORK_B]);
+    k4_fire_init_big<<<a.big_blocks, 512, 0, s>>>(a, a.work_b, n_work_b);
   }
 }
 
@@ -908,6 +1014,67 @@ void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, const uint3
   if (n_max == 0) return;
   KernelTimer t_("k_fire_round", s);
   k_fire_round<<<(n_max + 127) / 128, 128, 0, s>>>(a, work_in, n_in_dev, work_out, n_out);
+}
+
+// All later rounds in ONE cooperative launch (single device): the worklists ping-pong between
+// work_a and work_b, the three counters rotate (round r reads ring[r % 3], appends to
+// ring[(r + 1) % 3] and clears ring[(r + 2) % 3], which nobody touches during round r), and a
+// grid-wide barrier separates the rounds -- no host round trips, no launches sized for the first
+// round's list.  ring[3] receives the number of rounds run; ring[0] holds the length of work_b
+// on entry.
+__global__ void __launch_bounds__(256) k_fire_rounds_all(FilterArgs a, uint32_t *__restrict__ ring,
+                                                          uint32_t max_rounds) {
+  const GraphArgs &g = a.g;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const volatile uint8_t *fstat = a.fstat;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  uint32_t *win = a.work_b, *wout = a.work_a;
+  uint32_t r = 0;
+  for (;; r++) {
+    const uint32_t n_in = *reinterpret_cast<volatile uint32_t *>(&ring[r % 3u]);
+    if (n_in == 0u || r >= max_rounds) break;
+    uint32_t *n_out = &ring[(r + 1u) % 3u];
+    if (tid == 0) ring[(r + 2u) % 3u] = 0u;
+    for (uint32_t base = 0; base < n_in; base += nthreads) {       // warp-uniform trip count
+      const uint32_t idx = base + tid;
+      bool again = false;
+      uint32_t p = 0;
+      if (idx < n_in) {
+        p = win[idx];
+        uint8_t st = fstat[p];
+        const uint32_t und = (~(uint32_t) st >> 2) & 3u;
+        uint32_t res = 0;
+        const uint32_t rl = p - g.row_base;
+        for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) res |= fire_probe(g, fstat, s, und);
+        st = fire_decide(st, und, res);
+        a.fstat[p] = st;
+        again = (st & FS_DECIDED_ALL) != FS_DECIDED_ALL;
+      }
+      warp_append(again, p, wout, n_out);
+    }
+    grid.sync();
+    uint32_t *t = win; win = wout; wout = t;
+  }
+  if (tid == 0) ring[3] = r;
+}
+
+// returns 0, or -1 when the cooperative launch is not possible (the caller then runs the rounds one by one)
+int launch_fire_rounds_all(const FilterArgs &a, uint32_t *ring, uint32_t max_rounds, cudaStream_t s) {
+  static int blocks_per_sm = -1;
+  if (blocks_per_sm < 0) {
+    int coop = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    int n = 0;
+    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fire_rounds_all, 256, 0);
+    blocks_per_sm = n;
+  }
+  if (blocks_per_sm <= 0) return -1;
+  KernelTimer t_("k_fire_round", s);
+  FilterArgs aa = a;
+  void *args[] = {(void *) &aa, (void *) &ring, (void *) &max_rounds};
+  const dim3 grid((unsigned) (a.g.sm_count * blocks_per_sm)), block(256);
+  return cudaLaunchCooperativeKernel((const void *) k_fire_rounds_all, grid, block, args, 0, s) == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------ final states

@@ -36,6 +36,7 @@ enum {
   CNT_EDGES,              // slots written by the line-ordered build
   CNT_CORRECTIONS,        // reverse-flag corrections posted by k2_resolve
   CNT_WINDOWS,            // windows cut by k4_pack_windows
+  CNT_RING0, CNT_RING1, CNT_RING2, CNT_RING_ROUNDS,   // worklist lengths / round count of k_fire_rounds_all
   CNT_NUM
 };
 
@@ -54,6 +55,7 @@ constexpr int RSEG_LINES = 64;            // k2_resolve works on half segments (
 constexpr uint32_t RSEG_REC_CAP = 1024, RSEG_ENT_CAP = 768;
 constexpr uint32_t MAX_LINE_RECS = 64;         // longest line the per-thread scans accept
 constexpr int NB_COARSE = 64;             // coarse bins of the mailbox partition
+constexpr int NB_COARSE2 = 512;           // ... of its tile-sorted variant (single device)
 constexpr int GROUP_SHIFT = 3;            // mail is delivered to groups of 8 positions
 
 constexpr int MAX_RANKS = 64;
@@ -75,6 +77,8 @@ struct Build2Args {
   const long long *peer_shift;
   int sm_count;
   uint32_t coarse_shift, corrections_cap;
+  uint32_t nb_coarse;                       // coarse bins in use: NB_COARSE, or NB_COARSE2 with mail_sorted
+  int mail_sorted;                          // single device: tile-sorted mail passes (k2_partition2 / k2_deliver2)
   const uint32_t *root, *ctg;
   const int32_t *dist;
   const float *std_dev;
@@ -215,12 +219,15 @@ void launch_repeat_edges(const GraphArgs &g, const uint8_t *rep_pred, cudaStream
 void launch_pairs(const FilterArgs &a, cudaStream_t s);
 void launch_poly_sweep(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s);
-void launch_fire_init(const FilterArgs &a, cudaStream_t s);
+// undecided big rows are appended to work_b, whose length counter is n_work_b
+void launch_fire_init(const FilterArgs &a, uint32_t *n_work_b, cudaStream_t s);
 void launch_fire_dense(const FilterArgs &a, uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
 // one round over the listed rows; the list length is read on the device (n_in_dev), the grid
 // covers n_max >= it, so that several rounds can be queued between two host synchronisations
 void launch_fire_round(const FilterArgs &a, const uint32_t *work_in, const uint32_t *n_in_dev, uint32_t n_max,
                        uint32_t *work_out, uint32_t *n_out, cudaStream_t s);
+// every later round in one cooperative launch; ring = 4 words {len(work_b), 0, 0, rounds run}; -1: not available
+int launch_fire_rounds_all(const FilterArgs &a, uint32_t *ring, uint32_t max_rounds, cudaStream_t s);
 constexpr int FIRE_ROUNDS_PER_SYNC = 4;
 constexpr int POLY_SWEEPS_PER_SYNC = 4;
 void launch_vres(const FilterArgs &a, cudaStream_t s);          // final per-vertex facts (+ POLYMORPHIC vertex marks)

@@ -165,6 +165,20 @@ int gtsb_dot_edge_lines_host(gtsb_context *ctx, int scaffold_only, uint64_t coun
                              const uint32_t *dst, const int32_t *dist, const uint8_t *estate,
                              const uint8_t *sense, char *out, uint64_t cap, uint64_t *bytes);
 
+/* ---- `.scaf` text: what gt_scaffolder_graph_write_scaffold prints (gt_scaffolder_algorithms.c:
+   1000-1042), one line per scaffold record -- the root's header, then per edge
+   "\t<end header>,<dist %ld>,<std_dev %f>,<sense %d>,<same %d>," -- with the "%f" produced by
+   integer arithmetic on the float's bits (correctly rounded, as glibc's printf).  Records as
+   flat arrays: rec_root[i] = vertex id of the root, its edges are [rec_edge_off[i],
+   rec_edge_off[i+1]) of the edge arrays (edge_end = vertex id of edge->end, edge_flags bit 0 =
+   sense, bit 1 = same).  Vertex ids index the names set (gtsb_set_vertex_names_host).  At most
+   2^25 records and 2^25 edges per call; 80 + header bytes per edge and 1 + header bytes per
+   record always suffice for out. */
+int gtsb_scaf_lines_host(gtsb_context *ctx, uint64_t nof_records, const uint32_t *rec_root,
+                         const uint64_t *rec_edge_off, const uint32_t *edge_end, const int64_t *edge_dist,
+                         const float *edge_std_dev, const uint8_t *edge_flags, char *out, uint64_t cap,
+                         uint64_t *bytes);
+
 /* ---- the hot path */
 int gtsb_build(gtsb_context *ctx);
 int gtsb_mark_repeats(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff,

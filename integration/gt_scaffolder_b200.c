@@ -952,3 +952,128 @@ int gt_scaffolder_graph_print(const GtScaffolderGraph *g, const char *filename, 
   gt_free(dist);
   return had_err != 0 ? -1 : 0;
 }
+
+/* ------------------------------------------------------------------ .scaf */
+
+static int cmp_vertex_ptr(const void *a, const void *b)
+{
+  const GtScaffolderGraphVertex *x = *(GtScaffolderGraphVertex *const *) a,
+                                *y = *(GtScaffolderGraphVertex *const *) b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+static uint32_t local_vertex_id(GtScaffolderGraphVertex *const *set, GtUword n, const GtScaffolderGraphVertex *v)
+{
+  GtUword lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const GtUword mid = lo + (hi - lo) / 2;
+    if (set[mid] <= v) lo = mid; else hi = mid;
+  }
+  return (uint32_t) lo;
+}
+
+/* gt_scaffolder_graph_write_scaffold (algorithms.c:1000-1042): same file, the text formatted
+   on the device (gtsb_scaf_lines_host).  The records name their vertices by pointer; the
+   vertices that occur are numbered here (sorted by address) and their headers handed to the
+   device as the names set of this call. */
+int gt_scaffolder_graph_write_scaffold(GtArray *records, const char *file_name, GtError *err)
+{
+  gtsb_context *c;
+  FILE *fp;
+  GtUword n, m = 0, i, j, k, nv = 0;
+  GtScaffolderGraphVertex **set = NULL;
+  uint64_t *name_off = NULL, *rec_edge_off = NULL, names_bytes = 0, cap = 0, bytes = 0;
+  char *names = NULL, *out = NULL;
+  uint32_t *rec_root = NULL, *edge_end = NULL;
+  int64_t *edge_dist = NULL;
+  float *edge_std = NULL;
+  uint8_t *edge_flags = NULL;
+  int had_err = 0;
+
+  gt_assert(records != NULL);
+  c = b200_context();
+  if (c == NULL) {
+    gt_error_set(err, "no CUDA device available (the B200 path has no CPU fallback)");
+    return -1;
+  }
+  fp = fopen(file_name, "w");
+  if (fp == NULL) {
+    gt_error_set(err, "can not create file %s", file_name);
+    return -1;
+  }
+  n = gt_array_size(records);
+  for (i = 0; i < n; i++) {
+    const GtScaffolderGraphRecord *rec = *(GtScaffolderGraphRecord **) gt_array_get(records, i);
+    m += gt_array_size(rec->edges);
+  }
+  /* the vertices that occur, by address */
+  set = gt_malloc((n + m + 1) * sizeof (*set));
+  for (i = 0, k = 0; i < n; i++) {
+    const GtScaffolderGraphRecord *rec = *(GtScaffolderGraphRecord **) gt_array_get(records, i);
+    set[k++] = rec->root;
+    for (j = 0; j < gt_array_size(rec->edges); j++)
+      set[k++] = (*(GtScaffolderGraphEdge **) gt_array_get(rec->edges, j))->end;
+  }
+  qsort(set, k, sizeof (*set), cmp_vertex_ptr);
+  for (i = 0; i < k; i++)
+    if (nv == 0 || set[nv - 1] != set[i])
+      set[nv++] = set[i];
+  name_off = gt_malloc((nv + 1) * sizeof (*name_off));
+  for (i = 0; i < nv; i++) {
+    name_off[i] = names_bytes;
+    names_bytes += gt_str_length(set[i]->header_seq);
+  }
+  name_off[nv] = names_bytes;
+  names = gt_malloc(names_bytes + 1);
+  for (i = 0; i < nv; i++)
+    memcpy(names + name_off[i], gt_str_get(set[i]->header_seq), name_off[i + 1] - name_off[i]);
+  /* flat records */
+  rec_root = gt_malloc((n + 1) * sizeof (*rec_root));
+  rec_edge_off = gt_malloc((n + 1) * sizeof (*rec_edge_off));
+  edge_end = gt_malloc((m + 1) * sizeof (*edge_end));
+  edge_dist = gt_malloc((m + 1) * sizeof (*edge_dist));
+  edge_std = gt_malloc((m + 1) * sizeof (*edge_std));
+  edge_flags = gt_malloc(m + 1);
+  for (i = 0, k = 0; i < n; i++) {
+    const GtScaffolderGraphRecord *rec = *(GtScaffolderGraphRecord **) gt_array_get(records, i);
+    rec_root[i] = local_vertex_id(set, nv, rec->root);
+    rec_edge_off[i] = k;
+    cap += gt_str_length(rec->root->header_seq) + 1;
+    for (j = 0; j < gt_array_size(rec->edges); j++, k++) {
+      const GtScaffolderGraphEdge *e = *(GtScaffolderGraphEdge **) gt_array_get(rec->edges, j);
+      edge_end[k] = local_vertex_id(set, nv, e->end);
+      edge_dist[k] = (int64_t) e->dist;
+      edge_std[k] = e->std_dev;
+      edge_flags[k] = (uint8_t) ((e->sense ? 1 : 0) | (e->same ? 2 : 0));
+      cap += gt_str_length(e->end->header_seq) + 80;
+    }
+  }
+  rec_edge_off[n] = k;
+  out = gt_malloc(cap + 16);
+  if (n > 0) {
+    if (gtsb_set_vertex_names_host(c, nv, names, name_off) != 0 ||
+        gtsb_scaf_lines_host(c, n, rec_root, rec_edge_off, edge_end, edge_dist, edge_std, edge_flags, out, cap,
+                             &bytes) != 0) {
+      gt_error_set(err, "%s", gtsb_error(c));
+      had_err = -1;
+    } else if (fwrite(out, 1, bytes, fp) != bytes) {
+      gt_error_set(err, "cannot write to file '%s'", file_name);
+      had_err = -1;
+    }
+  }
+  if (fclose(fp) != 0 && had_err == 0) {
+    gt_error_set(err, "cannot write to file '%s'", file_name);
+    had_err = -1;
+  }
+  gt_free(set);
+  gt_free(name_off);
+  gt_free(names);
+  gt_free(rec_root);
+  gt_free(rec_edge_off);
+  gt_free(edge_end);
+  gt_free(edge_dist);
+  gt_free(edge_std);
+  gt_free(edge_flags);
+  gt_free(out);
+  return had_err;
+}

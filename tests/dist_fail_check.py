@@ -58,7 +58,10 @@ def main():
             dist.all_gather_object(agains, again)
             if rank == 0:
                 all_failed = all(o.startswith("error") for o in outs)
-                good = all_failed and all(a == "ok" for a in agains)
+                # "corrections" is only a growth step when the input has reverse-flag corrections
+                # (rare); when the place is not reached every rank must return ok together
+                not_reached = place == "corrections" and all(o == "returned ok" for o in outs)
+                good = (all_failed or not_reached) and all(a == "ok" for a in agains)
                 print(f"[dist_fail] place={place} failing rank={bad_rank}: every rank returned an error: {all_failed}; "
                       f"next call: {agains} -> {'OK' if good else 'BAD ' + str(outs)}", flush=True)
                 ok &= good

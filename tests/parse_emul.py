@@ -104,3 +104,36 @@ def dot_edge_lines(src, dst, dist, estate, sense, scaffold_only=False):
     rc = lib().emul_dot_edge_lines(C.c_int(int(scaffold_only)), C.c_uint64(len(a[0])), *[_vp(x) for x in a],
                                    out, C.c_uint64(cap), C.byref(n))
     return None if rc else out.raw[:n.value]
+
+
+def f6(bits: int) -> bytes:
+    """printf("%f") of the float with these bits, by the integer routine of gtsb_format_core.h"""
+    out = C.create_string_buffer(64)
+    n = lib().emul_f6(C.c_uint32(bits), out)
+    assert n != 0xFFFFFFFF, "f6_len and put_f6 disagree"
+    return out.raw[:n]
+
+
+def scaf_arrays(records):
+    """records = [(root id, [(end id, dist, std_dev f32, sense, same), ...]), ...] -> the flat arrays of
+    gtsb_scaf_lines_host"""
+    root = np.array([r for r, _ in records], np.uint32)
+    off = np.zeros(len(records) + 1, np.uint64)
+    off[1:] = np.cumsum([len(e) for _, e in records])
+    edges = [x for _, e in records for x in e]
+    end = np.array([x[0] for x in edges], np.uint32)
+    dist = np.array([x[1] for x in edges], np.int64)
+    std = np.array([x[2] for x in edges], np.float32)
+    flags = np.array([(1 if x[3] else 0) | (2 if x[4] else 0) for x in edges], np.uint8)
+    return root, off, end, dist, std, flags
+
+
+def scaf_lines(names, records):
+    blob, off = pack_names(names)
+    root, reo, end, dist, std, flags = scaf_arrays(records)
+    cap = len(blob) * 0 + sum(len(names[r]) + 1 for r in root) + sum(len(names[w]) + 80 for w in end) + 16
+    out = C.create_string_buffer(cap)
+    n = C.c_uint64(0)
+    rc = lib().emul_scaf_lines(C.c_uint64(len(root)), _vp(root), _vp(reo), _vp(end), _vp(dist), _vp(std.view(np.uint32)),
+                               _vp(flags), blob, _vp(off), C.c_uint64(len(names)), out, C.c_uint64(cap), C.byref(n))
+    return None if rc else out.raw[:n.value]
