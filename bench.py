@@ -42,17 +42,17 @@ def kernel_bytes(name, V, R, E, M):
     n = name.split("(")[0]
     table = {
         "k3_lines": 8 * V + 12 * V, "k2_heads": 2 * 4 * R + 12 * V, "k2_lineless": 9 * V,
-        "k3_classify": (4 + 4) * R + (1 + 4) * R,                 # ctg + position gather in, rf + pc out
-        "k3_partition": 14 * R + 20 * M,                          # pc, std_dev, dist, flags, rf in; mail out
-        "k3_fine_hist": 4 * M, "k3_deliver": 20 * M + 17 * M,
-        "k3_resolve": 14 * R + 17 * M + 21 * E + 4 * V,           # records + mail in, slot columns + row_ptr out
+        "k2_classify": (4 + 4) * R + (1 + 4) * R,                 # ctg + position gather in, rf + pc out
+        "k2_partition": 14 * R + 20 * M,                          # pc, std_dev, dist, flags, rf in; mail out
+        "k2_deliver": 20 * M + 17 * M,                            # coarse bins in; mailbox regions out
+        "k2_resolve": 14 * R + 17 * M + 21 * E + 4 * V,           # records + mail in, slot columns + row_ptr out
         "k4_pack_windows": 2 * 4 * V + 4 * (E // 26),
         "k4_vertex_facts": 16 * V + 9 * V,                        # vid, seq_len, copy_num, astat in; vinfo + pred out
-        "k5_pairs": (13 + 8) * E + 4 * V + 8 * V + V,             # slot columns + vinfo gather; row_ptr, own vinfo, gbits
+        "k4_pairs": (13 + 8) * E + 8 * V + V,                     # slot columns + vinfo gather; own vinfo, gbits
         "k4_fire_init": 4 * V + 8 * V + 4 * V + 2 * V + 2 * V,
-        "k4_fire_dense": (9 + 1) * E + 2 * V, "k5_fire_dense": (5 + 1) * E + 4 * V + 2 * V,
+        "k4_fire_dense": (9 + 1) * E + 2 * V,
         "k4_vres": 4 * V + V + 4 * V,
-        "k4_finalize": (9 + 4) * E + E, "k5_finalize": (5 + 4) * E + E + 4 * V + 4 * V,
+        "k4_finalize": (9 + 4) * E + E,
     }
     return table.get(n)
 
@@ -372,14 +372,23 @@ def run_b200_arm(args, pkg):
     line_start_h = torch.from_numpy(line_start_np.view(np.int32)).pin_memory()
     n_lines = int(line_root_h.shape[0])
 
+    v_first = Vn * rank // world
+    v_count = Vn * (rank + 1) // world - v_first
+
     def e2e_step():
         # records first: the vertex attributes are needed last (by the filter) and their copy,
         # like that of dist/std_dev/flags, runs on the context's copy stream under the first kernels
         g2._ck(g2.L.gtsb_set_record_lines_host(g2.h, n_lines, line_root_h.data_ptr(), line_start_h.data_ptr(), Rn,
                                                host["ctg"].data_ptr(), host["dist"].data_ptr(),
                                                host["std_dev"].data_ptr(), host["flags"].data_ptr()))
-        g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
-                                           host["copy_num"].data_ptr()))
+        if world == 1:
+            g2._ck(g2.L.gtsb_set_vertices_host(g2.h, Vn, host["seq_len"].data_ptr(), host["astat"].data_ptr(),
+                                               host["copy_num"].data_ptr()))
+        else:
+            # every rank uploads its share of the contig attributes; the pipeline gathers the rest over NVLink
+            g2._ck(g2.L.gtsb_set_vertices_slice_host(g2.h, Vn, v_first, v_count, host["seq_len"].data_ptr() + 4 * v_first,
+                                                     host["astat"].data_ptr() + 4 * v_first,
+                                                     host["copy_num"].data_ptr() + 4 * v_first))
         g2.V = Vn
         g2.pipeline(P["copy_num_cutoff"], P["astat_cutoff"], P["use_copy_num"], P["pcutoff"],
                     P["cncutoff"], P["ocutoff"])
@@ -403,7 +412,7 @@ def run_b200_arm(args, pkg):
     ev3.record(stream)
     barrier()
     e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3) / e2e_steps
-    h2d = Vn * 12 + Rn * 13 + n_lines * 8 + 4
+    h2d = v_count * 12 + Rn * 13 + n_lines * 8 + 4
     d2h = Vn + E * (1 if world == 1 else 5)
     if world == 1:
         g2.close()

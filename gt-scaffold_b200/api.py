@@ -37,7 +37,7 @@ EXPORTS = [
     "gtsb_set_record_lines_host", "gtsb_set_record_lines_device", "gtsb_update_vertices_host",
     "gtsb_set_states_host", "gtsb_get_edge_states",
     "gtsb_set_vertex_names_host", "gtsb_parse_de_host", "gtsb_get_records", "gtsb_parse_astat_host",
-    "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host", "gtsb_scaf_lines_host",
+    "gtsb_dot_vertex_lines_host", "gtsb_dot_edge_lines_host", "gtsb_scaf_lines_host", "gtsb_result_digest", "gtsb_components", "gtsb_set_vertices_slice_host",
 ]
 
 
@@ -110,6 +110,9 @@ def load_library():
     L.gtsb_dot_vertex_lines_host.argtypes = [vp, i32, u64, u64, vp, C.c_char_p, u64, C.POINTER(u64)]
     L.gtsb_dot_edge_lines_host.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp, C.c_char_p, u64, C.POINTER(u64)]
     L.gtsb_scaf_lines_host.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_char_p, u64, C.POINTER(u64)]
+    L.gtsb_result_digest.argtypes = [vp, C.POINTER(u64 * 3)]
+    L.gtsb_components.argtypes = [vp, vp, vp]
+    L.gtsb_set_vertices_slice_host.argtypes = [vp, u64, u64, u64, vp, vp, vp]
     _lib = L
     return L
 
@@ -397,6 +400,19 @@ class ScaffoldGraphB200:
                                                              ("eid", "src", "dst", "dist", "std_dev", "flags", "estate")]))
         return o
 
+    def components(self):
+        """(label[V], terminal[V]) of the current graph and states, see gtsb_components."""
+        lab, term = np.zeros(self.V, np.uint32), np.zeros(self.V, np.uint8)
+        self._ck(self.L.gtsb_components(self.h, _ptr(lab), _ptr(term)))
+        return lab, term
+
+    def digest(self):
+        """(edges on this device, edge digest, vertex digest): order-independent 64-bit sums, see
+        gtsb_result_digest; result_digest() below is the same arithmetic in numpy."""
+        out = (C.c_uint64 * 3)()
+        self._ck(self.L.gtsb_result_digest(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def csr(self, eid=True, win_rec=False):
         E, V = self.E, self.V
         o = dict(row_ptr=np.zeros(V + 1, np.uint32), dst=np.zeros(E, np.uint32),
@@ -461,3 +477,27 @@ class ScaffoldGraphB200:
             self.close()
         except Exception:
             pass
+
+
+def _mix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def result_digest(edges, vstate):
+    """The digests of gtsb_result_digest from fetched arrays (edges: dict with eid, src, dst, dist,
+    std_dev, flags, estate)."""
+    with np.errstate(over="ignore"):
+        u = lambda a: np.asarray(a).astype(np.uint64)
+        x = _mix64(u(edges["eid"]))
+        x = _mix64(x ^ u(edges["src"]))
+        x = _mix64(x ^ u(edges["dst"]))
+        x = _mix64(x ^ u(np.asarray(edges["dist"], np.int32).view(np.uint32)))
+        x = _mix64(x ^ u(np.asarray(edges["std_dev"], np.float32).view(np.uint32)))
+        x = _mix64(x ^ (u(np.asarray(edges["flags"]) & 15) | (u(edges["estate"]) << np.uint64(8))))
+        e = int(x.sum(dtype=np.uint64)) if len(x) else 0
+        vs = np.asarray(vstate)
+        v = _mix64(_mix64(np.arange(len(vs), dtype=np.uint64)) ^ u(vs))
+        return len(x), e, (int(v.sum(dtype=np.uint64)) if len(v) else 0)

@@ -204,6 +204,7 @@ int vertices_common(gtsb_context *c, uint64_t V, cudaStream_t on) {
   }
   c->have_vertices = true;
   c->have_graph = false;
+  c->vertices_sliced = false;
   return 0;
 }
 
@@ -354,10 +355,15 @@ int do_build_lines(gtsb_context *c) {
   a.Vg = (uint32_t) V;
   a.sm_count = c->sm_count;
   {
-    const char *e = getenv("GTSB_MAIL");               // 0: the per-entry scatter passes (dev switch)
-    a.mail_sorted = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    // dev switch.  0: the per-entry scatter passes; 3: per-entry pass A into NB_COARSE2 bins, tile-sorted pass B
+    const char *e = getenv("GTSB_MAIL");
+    a.mail_sorted = e != nullptr ? atoi(e) : 1;
   }
   a.nb_coarse = a.mail_sorted ? NB_COARSE2 : NB_COARSE;
+  if (a.mail_sorted && getenv("GTSB_NB") != nullptr) {   // dev switch: fewer coarse bins (64 .. NB_COARSE2)
+    const int nb = atoi(getenv("GTSB_NB"));
+    if (nb >= 64 && nb <= NB_COARSE2) a.nb_coarse = (uint32_t) nb;
+  }
   uint32_t shift = 0;
   while (((V ? V - 1 : 0) >> shift) >= (uint64_t) a.nb_coarse) shift++;
   a.coarse_shift = shift;
@@ -576,8 +582,14 @@ int do_mark_repeats(gtsb_context *c, float cn_cutoff, float astat_cutoff, int us
 }
 
 // work arrays of the filter: per-vertex ones for Vg vertices, proposals for E slots
+uint64_t proposal_capacity(uint64_t E) { return E / 4 + 65536 < E + 1 ? E / 4 + 65536 : E + 1; }
+
 int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a) {
-  ENSURE(c->proposals, (E + 1) * sizeof(uint2));
+  // proposals are rare (a pair needs two low copy numbers and an ambiguous order); room for E / 4,
+  // the single-device filter reruns the pairs pass with room for all E when that overflows
+  const uint64_t prop_cap = proposal_capacity(E) > c->proposals.cap / sizeof(uint2) ? proposal_capacity(E)
+                                                                                    : c->proposals.cap / sizeof(uint2);
+  ENSURE(c->proposals, prop_cap * sizeof(uint2));
   ENSURE(c->poly_cur, (V + 1) * 4);
   ENSURE(c->poly_new, (V + 1) * 4);
   ENSURE(c->gbits, V + 1);
@@ -586,6 +598,7 @@ int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a
   ENSURE(c->work_b, (V + 1) * 4);
   ENSURE(c->vinfo, (V + 1) * sizeof(uint2));
   ENSURE(c->vres, (V + 1) * 4);
+  ENSURE(c->vsum, V + 1);
   ENSURE(c->dirty, V + 1);
   a.big_blocks = (uint32_t) c->sm_count * 2;
   if (c->n_big_rows) {
@@ -594,7 +607,7 @@ int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a
   }
   a.g = graph_args(c);
   a.proposals = c->proposals.as<uint2>();
-  a.proposals_cap = (uint32_t) E;
+  a.proposals_cap = (uint32_t) (prop_cap > E + 1 ? E + 1 : prop_cap);
   a.poly_cur = c->poly_cur.as<uint32_t>();
   a.poly_new = c->poly_new.as<uint32_t>();
   a.gbits = c->gbits.as<uint8_t>();
@@ -606,6 +619,7 @@ int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a
   a.big_scratch = c->big_scratch.as<uint8_t>();
   a.vinfo = c->vinfo.as<uint2>();
   a.vres = c->vres.as<uint32_t>();
+  a.vsum = c->vsum.as<uint8_t>();
   return 0;
 }
 
@@ -644,6 +658,18 @@ int do_filter(gtsb_context *c, float pcutoff, float cncutoff, int64_t ocutoff, b
   c->stats.kernel_launches += (V ? 1 : 0) + (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
   if (read_counters(c) != 0) return -1;
   if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
+  if (c->h_counters[CNT_OVERFLOW] && a.proposals_cap < E + 1) {
+    // more proposals than the list was sized for: once more with room for every slot
+    ENSURE(c->proposals, (E + 1) * sizeof(uint2));
+    a.proposals = c->proposals.as<uint2>();
+    a.proposals_cap = (uint32_t) (E + 1);
+    CK(cudaMemsetAsync(cnt + CNT_PROPOSALS, 0, 4, s));
+    CK(cudaMemsetAsync(cnt + CNT_OVERFLOW, 0, 4, s));
+    CK(cudaMemsetAsync(c->gbits.p, 0, V + 1, s));
+    launch_pairs(a, s);
+    c->stats.kernel_launches += (E ? 1 : 0) + (E && c->n_big_rows ? 1 : 0);
+    if (read_counters(c) != 0) return -1;
+  }
   if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
   const uint32_t nprop = c->h_counters[CNT_PROPOSALS];
   c->stats.proposals = nprop;
@@ -895,6 +921,31 @@ int gtsb_set_vertices_host(gtsb_context *c, uint64_t V, const uint32_t *seq_len,
     CK(cudaMemcpyAsync(c->astat.p, astat, V * 4, cudaMemcpyHostToDevice, c->copy_stream));
   }
   return vertices_common(c, V, c->copy_stream);
+}
+
+int gtsb_set_vertices_slice_host(gtsb_context *c, uint64_t V, uint64_t first, uint64_t count, const uint32_t *seq_len,
+                                 const float *astat, const float *copy_num) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (c->world <= 1) return fail(c, "gtsb_set_vertices_slice_host: only for a graph partitioned over ranks (gtsb_dist_init)");
+  if (first + count > V) return fail(c, "gtsb_set_vertices_slice_host: slice outside the vertices");
+  if (!c->seq_len_in.owned) c->seq_len_in = DevBuf();
+  if (!c->copy_num_in.owned) c->copy_num_in = DevBuf();
+  if (!c->astat.owned) c->astat = DevBuf();
+  ENSURE(c->seq_len_in, V * 4);
+  ENSURE(c->copy_num_in, V * 4);
+  ENSURE(c->astat, V * 4);
+  if (copy_stream_follows_main(c) != 0) return -1;
+  if (count) {
+    CK(cudaMemcpyAsync(c->seq_len_in.as<uint32_t>() + first, seq_len, count * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->copy_num_in.as<float>() + first, copy_num, count * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->astat.as<float>() + first, astat, count * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  if (vertices_common(c, V, c->copy_stream) != 0) return -1;      // packs every id; the other slices arrive in gtsb_pipeline
+  c->vertices_sliced = true;
+  c->vslice_first = first;
+  c->vslice_count = count;
+  return 0;
 }
 
 int gtsb_set_vertices_device(gtsb_context *c, uint64_t V, const uint32_t *seq_len, const float *astat,
@@ -1156,6 +1207,44 @@ int gtsb_pipeline(gtsb_context *c, float cn_cutoff, float astat_cutoff, int use_
 }
 
 uint64_t gtsb_nof_edges(const gtsb_context *c) { return c ? c->E : 0; }
+
+int gtsb_components(gtsb_context *c, uint32_t *label, uint8_t *terminal) {
+  if (c == nullptr) return -1;
+  CK(cudaSetDevice(c->device));
+  if (!c->have_graph) return fail(c, "gtsb_components: no graph (call gtsb_build or gtsb_set_graph_host)");
+  if (c->world > 1) return fail(c, "gtsb_components: single-device graphs only");
+  ProfScope ps_(c);
+  if (await_vertices(c) != 0) return -1;
+  const uint64_t V = c->V;
+  cudaStream_t s = c->stream;
+  // work arrays of the filter that are free between its calls
+  ENSURE(c->poly_cur, (V + 1) * 4);          // labels by position
+  ENSURE(c->poly_new, (V + 1) * 4);          // labels by id
+  ENSURE(c->gbits, V + 1);                   // terminal flags by position
+  ENSURE(c->fstat, V + 1);                   // ... by id
+  const GraphArgs g = graph_args(c);
+  uint32_t *lab = c->poly_cur.as<uint32_t>();
+  uint32_t *cnt = c->counters.as<uint32_t>();
+  launch_cc_init(g, lab, c->gbits.as<uint8_t>(), s);
+  c->stats.kernel_launches += 1;
+  uint32_t rounds = 0;
+  for (;;) {
+    CK(cudaMemsetAsync(cnt + CNT_POLY_CHANGED, 0, 4, s));
+    for (int k = 0; k < 4; k++) launch_cc_round(g, lab, cnt + CNT_POLY_CHANGED, s);
+    c->stats.kernel_launches += 8;
+    rounds += 4;
+    if (read_counters(c) != 0) return -1;
+    if (!c->h_counters[CNT_POLY_CHANGED]) break;
+    if (rounds > V + 8) return fail(c, "gtsb_components: labels did not converge");
+  }
+  launch_cc_out(g, lab, c->gbits.as<uint8_t>(), c->poly_new.as<uint32_t>(), c->fstat.as<uint8_t>(), s);
+  c->stats.kernel_launches += 1;
+  if (label != nullptr && V) CK(cudaMemcpyAsync(label, c->poly_new.p, V * 4, cudaMemcpyDeviceToHost, s));
+  if (terminal != nullptr && V) CK(cudaMemcpyAsync(terminal, c->fstat.p, V, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return 0;
+}
 
 int gtsb_get_vertex_states(gtsb_context *c, uint8_t *vstate) {
   if (c == nullptr) return -1;

@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
   uint32_t *s_ls = reinterpret_cast<uint32_t *>(smem);
   uint32_t *s_pc = s_ls + SEG_LINES + 4;
   float *s_std = reinterpret_cast<float *>(s_pc + SEG_REC_CAP);
-  uint32_t *s_bin = reinterpret_cast<uint32_t *>(s_std + SEG_REC_CAP);   // [3][NB_COARSE]
-  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_bin + 3 * NB_COARSE);
+  uint32_t *s_bin = reinterpret_cast<uint32_t *>(s_std + SEG_REC_CAP);   // [3][nb]
+  const uint32_t NB = a.nranks ? (uint32_t) NB_COARSE : a.nb_coarse;
+  uint8_t *s_fl = reinterpret_cast<uint8_t *>(s_bin + 3 * NB);
   uint8_t *s_rf = s_fl + SEG_REC_CAP;
   uint8_t *s_line = s_rf + SEG_REC_CAP;
   __shared__ uint32_t s_bounds[MAX_RANKS + 1];
@@ -323,13 +324,13 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     s_fl[r] = a.flags[g.rec0 + r];
     s_rf[r] = a.rf[g.rec0 + r];
   }
-  for (uint32_t b = threadIdx.x; b < 3 * NB_COARSE; b += blockDim.x) s_bin[b] = 0;
+  for (uint32_t b = threadIdx.x; b < 3 * NB; b += blockDim.x) s_bin[b] = 0;
   __syncthreads();
   for (uint32_t r = threadIdx.x; r < g.n; r += blockDim.x)
     if ((s_rf[r] & RF_CREATOR) == RF_CREATOR) atomicAdd(&s_bin[bin_of(s_pc[r])], 1u);
   __syncthreads();
-  for (uint32_t b = threadIdx.x; b < NB_COARSE; b += blockDim.x)
-    if (s_bin[b]) s_bin[NB_COARSE + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
+  for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x)
+    if (s_bin[b]) s_bin[NB + b] = atomicAdd(&a.tmp_cursor[b], s_bin[b]);
   // creator rank in record order = k - k0[first line]: one block scan per 256 records
   // Partitioned graph: the chunk's entries are first grouped by destination rank in shared memory
   // and then stored by consecutive threads, so that what crosses NVLink are runs of whole entries
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
     }
     if (!remote) {
       if (creator) {
-        const uint32_t at = s_bin[NB_COARSE + b] + atomicAdd(&s_bin[2 * NB_COARSE + b], 1u);
+        const uint32_t at = s_bin[NB + b] + atomicAdd(&s_bin[2 * NB + b], 1u);
         a.tmp_ent[at] = e;
         a.tmp_dest[at] = pc;
       }
@@ -389,8 +390,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_partition(Build2Args a) {
       for (int o = 0; o < a.nranks; o++) {
         s_co[o] = run;
         run += s_cc[o];
-        s_cb[o] = s_bin[NB_COARSE + o] + s_bin[2 * NB_COARSE + o];     // this block's share of rank o, so far
-        s_bin[2 * NB_COARSE + o] += s_cc[o];
+        s_cb[o] = s_bin[NB + o] + s_bin[2 * NB + o];     // this block's share of rank o, so far
+        s_bin[2 * NB + o] += s_cc[o];
       }
       s_co[a.nranks] = run;
     }
@@ -607,8 +608,12 @@ __global__ void __launch_bounds__(P2_THREADS) k2_partition2(Build2Args a) {
 }
 
 // pass B: a tile of coarsely sorted entries, sorted by destination segment and written in runs
-// into the segments' mailbox regions (k2_resolve sorts a segment's mail by line)
-__global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
+// into the segments' mailbox regions (k2_resolve sorts a segment's mail by line).
+// COARSE = true is the same sort one level up, for mail that arrives in no order (the partitioned
+// build, where every rank's creators store into the owner's receive buffers): bins are the
+// NB_COARSE2 position ranges, the output is the coarsely sorted stream pass B then reads.
+template <bool COARSE>
+__global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a, uint32_t n_host) {
   extern __shared__ __align__(16) uint8_t smem[];
   if (block_abort(a.counters)) return;
   uint4 *s_ent = reinterpret_cast<uint4 *>(smem);
@@ -619,10 +624,13 @@ __global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
   uint16_t *s_rank = s_key + D2_TILE;
   uint16_t *s_perm = s_rank + D2_TILE;
   __shared__ uint32_t s_lo, s_hi;
-  const uint32_t n = a.bptr[a.V];
+  const uint32_t n = COARSE ? n_host : a.bptr[a.V];
   const uint64_t tile0 = (uint64_t) blockIdx.x * D2_TILE;
   if (tile0 >= n) return;
   const uint32_t cnt = (uint32_t) min((uint64_t) D2_TILE, n - tile0);
+  const uint4 *in_ent = COARSE ? a.rx_ent : a.mail_ent;
+  const uint32_t *in_dest = COARSE ? a.rx_dest : a.mail_dest;
+  const uint32_t kshift = COARSE ? a.coarse_shift : (uint32_t) RSEG_SHIFT;
   if (threadIdx.x == 0) {
     s_lo = UNSET;
     s_hi = 0;
@@ -630,11 +638,12 @@ __global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
   __syncthreads();
   uint32_t lo = UNSET, hi = 0;
   for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const uint32_t d = a.mail_dest[tile0 + i] - a.pos_base;
+    const uint32_t d = in_dest[tile0 + i] - a.pos_base;
     s_dest[i] = d;
-    s_ent[i] = a.mail_ent[tile0 + i];
-    lo = min(lo, d >> RSEG_SHIFT);
-    hi = max(hi, d >> RSEG_SHIFT);
+    s_ent[i] = in_ent[tile0 + i];
+    if (COARSE && d >= a.V) atomicOr(&a.counters[CNT_ERROR], 8u);     // mail for a row of another rank
+    lo = min(lo, d >> kshift);
+    hi = max(hi, d >> kshift);
   }
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
@@ -643,7 +652,9 @@ __global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
     atomicMax(&s_hi, hi);
   }
   __syncthreads();
-  const uint32_t f_lo = s_lo, nf = s_hi - s_lo + 1u;
+  const uint32_t f_lo = COARSE ? 0u : s_lo, nf = COARSE ? a.nb_coarse : s_hi - s_lo + 1u;
+  uint32_t *cursors = COARSE ? a.tmp_cursor : a.cursor + f_lo;
+  if (COARSE && s_hi >= a.nb_coarse) return;                // flagged above
   if (nf > D2_BINS) {                                       // entries from all over (unsorted input): one by one
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
       const uint32_t at = atomicAdd(&a.cursor[s_dest[i] >> RSEG_SHIFT], 1u);
@@ -652,14 +663,43 @@ __global__ void __launch_bounds__(D2_THREADS) k2_deliver2(Build2Args a) {
     }
     return;
   }
-  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_key[i] = (uint16_t) ((s_dest[i] >> RSEG_SHIFT) - f_lo);
-  tile_sort(cnt, nf, s_key, s_rank, s_perm, s_off, s_gbase, a.cursor + f_lo);
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_key[i] = (uint16_t) ((s_dest[i] >> kshift) - f_lo);
+  tile_sort(cnt, nf, s_key, s_rank, s_perm, s_off, s_gbase, cursors);
   for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) {
     const uint32_t i = s_perm[t], b = s_key[i];
     const uint32_t at = s_gbase[b] + (t - s_off[b]);
-    a.bucket[at] = s_ent[i];
-    a.bucket_line[at] = (uint8_t) (s_dest[i] & (SEG_LINES - 1));
+    if (COARSE) {
+      a.tmp_ent[at] = s_ent[i];
+      a.tmp_dest[at] = s_dest[i] + a.pos_base;
+    } else {
+      a.bucket[at] = s_ent[i];
+      a.bucket_line[at] = (uint8_t) (s_dest[i] & (SEG_LINES - 1));
+    }
   }
+}
+
+// partitioned build: received mail per coarse bin (bins of 2^coarse_shift local positions) ...
+__global__ void __launch_bounds__(256) k2_mail_hist(Build2Args a, uint32_t n, uint32_t *__restrict__ hist) {
+  __shared__ uint32_t s_h[NB_COARSE2];
+  for (uint32_t b = threadIdx.x; b < NB_COARSE2; b += blockDim.x) s_h[b] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t b = (a.rx_dest[i] - a.pos_base) >> a.coarse_shift;
+    if (b < a.nb_coarse) atomicAdd(&s_h[b], 1u); else atomicOr(&a.counters[CNT_ERROR], 8u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < NB_COARSE2; b += blockDim.x)
+    if (s_h[b]) atomicAdd(&hist[b], s_h[b]);
+}
+
+// ... and the bins' first places in the coarsely sorted stream
+__global__ void __launch_bounds__(NB_COARSE2) k2_mail_hist_scan(const uint32_t *__restrict__ hist,
+                                                                 uint32_t *__restrict__ cursor) {
+  uint32_t total;
+  const uint32_t v = hist[threadIdx.x];
+  const uint32_t ex = block_excl_scan(v, &total);
+  cursor[threadIdx.x] = ex;
+  if (threadIdx.x == 0) cursor[NB_COARSE2] = total;
 }
 
 // pass R: resolve every line against its mailbox and write the CSR rows.
@@ -929,7 +969,7 @@ __global__ void __launch_bounds__(256) k2_export_rows(ExportArgs x) {
 // ------------------------------------------------------------------ host driver
 
 size_t build2_smem_classify() { return 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 5 + 16; }
-size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE * 4 + 16; }
+size_t build2_smem_partition() { return (SEG_LINES + 4) * 4 + SEG_REC_CAP * 11 + 3 * NB_COARSE2 * 4 + 16; }
 size_t build2_smem_partition2() {
   return P2_ENT_CAP * (16 + 4 + 6) + (2 * NB_COARSE2 + 4) * 4 + 2 * (SEG_LINES + 4) * 4 + SEG_REC_CAP * 2 + 16;
 }
@@ -943,7 +983,8 @@ static void build2_attrs() {
   cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition());
   cudaFuncSetAttribute(k2_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_resolve());
   cudaFuncSetAttribute(k2_partition2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_partition2());
-  cudaFuncSetAttribute(k2_deliver2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_deliver2());
+  cudaFuncSetAttribute(k2_deliver2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_deliver2());
+  cudaFuncSetAttribute(k2_deliver2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) build2_smem_deliver2());
   attr_done = true;
 }
 
@@ -1006,7 +1047,7 @@ int launch_b2_partition(const Build2Args &a, cudaStream_t s) {
   if (nseg == 0) return 0;
   KernelTimer t_("k2_partition", s);
   k2_init_cursors<<<(a.nb_coarse + 128) / 128, 128, 0, s>>>(a);
-  if (a.mail_sorted && a.nranks == 0)
+  if (a.mail_sorted == 1 && a.nranks == 0)
     k2_partition2<<<(nseg + P2_SEGS - 1) / P2_SEGS, P2_THREADS, build2_smem_partition2(), s>>>(a);
   else
     k2_partition<<<nseg, SEG_THREADS, build2_smem_partition(), s>>>(a);
@@ -1020,18 +1061,31 @@ int launch_b2_count_mail(const Build2Args &a, uint32_t n_mail, cudaStream_t s) {
   return 1;
 }
 
+// partitioned build: the received mail (rx_ent / rx_dest, n_mail entries in no order) -> tmp_ent / tmp_dest
+// sorted by coarse bin; hist = NB_COARSE2 + 1 zeroed words
+int launch_b2_coarse_sort(const Build2Args &a, uint32_t *hist, cudaStream_t s) {
+  build2_attrs();
+  if (a.n_mail == 0) return 0;
+  KernelTimer t_("k2_coarse_sort(3 kernels)", s);
+  k2_mail_hist<<<a.sm_count * 8, 256, 0, s>>>(a, a.n_mail, hist);
+  k2_mail_hist_scan<<<1, NB_COARSE2, 0, s>>>(hist, a.tmp_cursor);
+  k2_deliver2<true><<<(a.n_mail + D2_TILE - 1) / D2_TILE, D2_THREADS, build2_smem_deliver2(), s>>>(a, a.n_mail);
+  return 3;
+}
+
 int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s) {
   build2_attrs();
   const uint32_t nseg = (a.V + SEG_LINES - 1) / SEG_LINES;
   if (nseg == 0) return 0;
   {
     KernelTimer t_("k2_deliver", s);
-    if (a.mail_sorted && a.nranks == 0) {
+    if (a.mail_sorted) {
       const uint32_t nsg = (a.V >> RSEG_SHIFT) + 1;
       k2_init_group_cursors<<<(nsg + 255) / 256, 256, 0, s>>>(a, RSEG_SHIFT);
-      // the grid covers every record (an upper bound of the mail the device knows only after the scan)
-      const uint64_t tiles = (a.R + D2_TILE - 1) / D2_TILE;
-      k2_deliver2<<<(uint32_t) (tiles ? tiles : 1), D2_THREADS, build2_smem_deliver2(), s>>>(a);
+      // the grid covers every record (an upper bound of the mail the device knows only after the scan),
+      // or the mail count the ranks exchanged
+      const uint64_t tiles = ((a.nranks ? (uint64_t) a.n_mail : a.R) + D2_TILE - 1) / D2_TILE;
+      k2_deliver2<false><<<(uint32_t) (tiles ? tiles : 1), D2_THREADS, build2_smem_deliver2(), s>>>(a, 0u);
     } else {
       const uint32_t ngrp = (a.V >> GROUP_SHIFT) + 1;
       k2_init_group_cursors<<<(ngrp + 255) / 256, 256, 0, s>>>(a, GROUP_SHIFT);

@@ -69,7 +69,7 @@ struct gtsb_context {
   DevBuf cnt, bptr, cursor, deg, krank, scan_scratch, entries, bwin, creator_flag, large_list,
       big_rows, counters, lscratch, ltag;
   // filter work
-  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, dirty;
+  DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, vsum, dirty;
   uint32_t n_big_rows = 0, max_deg = 0;
   // .de text on the device (gtsb_parse.cu)
   DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,
@@ -95,6 +95,8 @@ struct gtsb_context {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_order = nullptr, ev_vertices = nullptr, ev_records = nullptr;
   bool vertices_pending = false, records_pending = false;
+  bool vertices_sliced = false;   // only ids [vslice_first, vslice_first + vslice_count) were uploaded (partitioned graph)
+  uint64_t vslice_first = 0, vslice_count = 0;
 
   // rank-partitioned graph (gtsb_dist.cu); world == 1: single device
   int rank = 0, world = 1;
@@ -123,6 +125,7 @@ gtsb::GraphArgs graph_args(gtsb_context *c);
 int get_ambig(gtsb_context *c, float pcutoff);
 int ensure_windows(gtsb_context *c, uint64_t V, uint64_t max_edges);
 int ensure_rows(gtsb_context *c, uint64_t R);
+uint64_t proposal_capacity(uint64_t E);
 int ensure_filter_buffers(gtsb_context *c, uint64_t Vg, uint64_t E, gtsb::FilterArgs &a);
 int await_vertices(gtsb_context *c);      // the main stream waits for late copies (no host sync)
 int await_records(gtsb_context *c);

@@ -88,7 +88,7 @@ struct DistState {
   ncclComm_t comm2 = nullptr;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage, stage2, peer_tab, handles;
+  DevBuf small, bounds, rank_cnt, rx_ent, rx_dest, corr_all, prop_all, stage, stage2, peer_tab, handles, mail_hist;
   uint32_t *h_small = nullptr;     // pinned, world * SMALL_N words
   // every rank's receive buffers, opened through CUDA IPC (peer memory over NVLink)
   void *peer_ptr[MAX_RANKS][2] = {};
@@ -120,9 +120,9 @@ void dist_reset_buffers(gtsb_context *c) {
   if (g_nccl.AllReduce(D->small.p, D->small.p, 1, ncclUint32, ncclSum, D->comm, c->stream) == ncclSuccess)
     cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage, &D->stage2, &D->peer_tab,
-                    &c->vinfo, &c->bucket, &c->bucket_line, &c->srcp, &c->dst, &c->edist, &c->estd,
+                    &c->tmp_ent, &c->tmp_dest, &c->vinfo, &c->bucket, &c->bucket_line, &c->srcp, &c->dst, &c->edist, &c->estd,
                     &c->eflags, &c->eid, &c->estate, &c->wcount, &c->woff, &c->win_start, &c->proposals,
-                    &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat, &c->work_a, &c->work_b, &c->vres, &c->dirty,
+                    &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat, &c->work_a, &c->work_b, &c->vres, &c->vsum, &c->dirty,
                     &c->big_scratch};
   for (DevBuf *b : bufs) {
     if (b->owned && b->p != nullptr) cudaFree(b->p);
@@ -307,6 +307,50 @@ __global__ void k_edges(GraphArgs g, const uint32_t *__restrict__ eid_in, uint32
   flags[s] = g.flags[s] & 0x0Fu;
 }
 
+// order-independent 64-bit digests of the result: sum over this device's edges of a hash of
+// (eid, src id, dst id, dist, std_dev bits, sense/same/reverse flags, state), and over the vertices
+// of a hash of (id, state).  The sums of the ranks of a partitioned graph add up to the digest of
+// the same graph on one device.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {          // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ void digest_add(uint64_t h, unsigned long long *acc) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+  if (lane_id() == 0 && h) atomicAdd(acc, (unsigned long long) h);
+}
+
+__global__ void __launch_bounds__(256) k_digest_edges(GraphArgs g, const uint32_t *__restrict__ eid,
+                                                      unsigned long long *acc) {
+  uint64_t h = 0;
+  for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < ((g.E + 31ull) & ~31ull);
+       s += (uint64_t) gridDim.x * blockDim.x) {
+    if (s >= g.E) continue;
+    const uint32_t sp = g.srcp[s] & S_POS, dp = g.dst[s];
+    uint64_t x = mix64(eid[s]);
+    x = mix64(x ^ (g.vid != nullptr ? g.vid[sp] : sp));
+    x = mix64(x ^ (g.vid != nullptr ? g.vid[dp] : dp));
+    x = mix64(x ^ (uint32_t) g.dist[s]);
+    x = mix64(x ^ __float_as_uint(g.std_dev[s]));
+    x = mix64(x ^ ((g.flags[s] & 0x0Fu) | ((uint32_t) g.estate[s] << 8)));
+    h += x;
+  }
+  digest_add(h, acc);
+}
+
+__global__ void __launch_bounds__(256) k_digest_vertices(uint64_t V, const uint8_t *__restrict__ vstate,
+                                                         unsigned long long *acc) {
+  uint64_t h = 0;
+  for (uint64_t v = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; v < ((V + 31ull) & ~31ull);
+       v += (uint64_t) gridDim.x * blockDim.x)
+    if (v < V) h += mix64(mix64(v) ^ vstate[v]);
+  digest_add(h, acc);
+}
+
 // (re)open every rank's receive buffers; collective
 int open_peer_buffers(gtsb_context *c) {
   DistState *D = static_cast<DistState *>(c->dstate);
@@ -357,7 +401,7 @@ void dist_release(gtsb_context *c) {
     for (int k = 0; k < 2; k++)
       if (r != c->rank && D->peer_ptr[r][k] != nullptr) cudaIpcCloseMemHandle(D->peer_ptr[r][k]);
   for (DevBuf *b : {&D->small, &D->bounds, &D->rank_cnt, &D->rx_ent, &D->rx_dest, &D->corr_all, &D->prop_all, &D->stage,
-                    &D->stage2, &D->peer_tab, &D->handles})
+                    &D->stage2, &D->peer_tab, &D->handles, &D->mail_hist})
     if (b->owned && b->p != nullptr) cudaFree(b->p);
   if (D->h_small != nullptr) cudaFreeHost(D->h_small);
   delete D;
@@ -400,6 +444,8 @@ struct Plan {                     // what the ranks agreed on while building
   float cn_cutoff = 0.f, astat_cutoff = 0.f;
   int use_cn = 0;
   bool facts_on_side = false;     // vinfo was computed and gathered on the side stream
+  std::vector<uint64_t> vlo;      // [N+1] vertex-attribute slices by id (gtsb_set_vertices_slice_host)
+  bool gather_attributes = false;
 };
 
 // contig ids by position and the packed per-neighbour facts of the pairs pass: both depend on
@@ -426,6 +472,10 @@ int dist_side_facts(gtsb_context *c, DistState *D, Plan &P) {
     if (c->vertices_pending) CK(cudaStreamWaitEvent(st, c->ev_vertices, 0));
   } else if (await_vertices(c) != 0) {
     return -1;
+  }
+  if (P.gather_attributes) {                     // each rank uploaded a slice: the rest comes over NVLink
+    if (allgatherv(c, "nccl_allgather_vattr", c->vattr.p, sizeof(VAttr), P.vlo, side) != 0) return -1;
+    if (allgatherv(c, "nccl_allgather_vattr", c->astat.p, 4, P.vlo, side) != 0) return -1;
   }
   if (allgatherv(c, "nccl_allgather_vid", c->vid.p, 4, P.lo, side) != 0) return -1;
   FilterArgs fa{};
@@ -458,9 +508,28 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int se
     CK(cudaMemcpyAsync(&L, a.tile_off + ntiles, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
-  if (exchange(c, setup_rc, "build setup", &L, 1, all) != 0) return -1;
+  // with the line count: which slice of the vertex attributes this rank uploaded (all of them: 0, Vg)
+  const uint32_t setup_mine[3] = {L, c->vertices_sliced ? (uint32_t) c->vslice_first : 0u,
+                                  c->vertices_sliced ? (uint32_t) c->vslice_count : (uint32_t) Vg};
+  if (exchange(c, setup_rc, "build setup", setup_mine, 3, all) != 0) return -1;
   P.lo.assign(N + 1, 0);
-  for (int r = 0; r < N; r++) P.lo[r + 1] = P.lo[r] + all[r];
+  for (int r = 0; r < N; r++) P.lo[r + 1] = P.lo[r] + all[(size_t) r * 3];
+  {
+    bool whole = true, tiled = true;
+    uint64_t at = 0;
+    P.vlo.assign(N + 1, 0);
+    for (int r = 0; r < N; r++) {
+      const uint64_t f = all[(size_t) r * 3 + 1], n = all[(size_t) r * 3 + 2];
+      whole &= f == 0 && n == Vg;
+      tiled &= f == at;
+      at = f + n;
+      P.vlo[r + 1] = at;
+    }
+    tiled &= at == Vg;
+    P.gather_attributes = !whole;
+    if (!whole && !tiled)
+      return fail(c, "gtsb_pipeline: the ranks' vertex slices (gtsb_set_vertices_slice_host) do not tile the vertices");
+  }
   P.L = L;
   P.L_total = P.lo[N];
   if (P.L_total > Vg) return fail(c, "more lines than contigs: a contig heads more than one line");
@@ -530,9 +599,10 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     ENSURE(c->scan_scratch, scan_scratch_elems(scan_n) * 4);
     ENSURE(c->rf, R + 1);
     ENSURE(c->pc, (R + 1) * 4);
-    ENSURE(c->tmp_ent, (R + 1) * sizeof(uint4));
-    ENSURE(c->tmp_dest, (R + 1) * 4);
-    ENSURE(c->tmp_cursor, (NB_COARSE + 2) * 4);
+    // tmp_ent / tmp_dest (the coarsely sorted copy of the received mail) are sized by the largest
+    // mail any rank receives, with the receive buffers below: their growth is rank-uniform
+    ENSURE(c->tmp_cursor, (NB_COARSE2 + 2) * 4);
+    ENSURE(D->mail_hist, (NB_COARSE2 + 2) * 4);
     ENSURE(D->bounds, (MAX_RANKS + 2) * 4);
     ENSURE(D->rank_cnt, (MAX_RANKS + 2) * 4);
     ENSURE(c->corrections, (size_t) (R / 8 + 4096) * sizeof(uint4));
@@ -636,6 +706,9 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   }
   tr.mark(me, "classify+exchange");
 
+  // received mail is sorted by coarse bin first (tile sort), so that counting and delivering it
+  // work inside L2-sized windows; GTSB_MAIL=0: counted and delivered entry by entry (dev switch)
+  const bool mail_sorted = !(getenv("GTSB_MAIL") != nullptr && atoi(getenv("GTSB_MAIL")) == 0);
   // ---- receive buffers, then the messages: k2_partition stores every rank's mail straight into
   // that rank's buffers (peer memory over NVLink) while it computes the next ones
   bool grew = false, rx_grew = false;
@@ -647,6 +720,10 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     grew |= rx_grew;
     ENSURE_U(c->bucket, (M_max + 1) * sizeof(uint4));
     ENSURE_U(c->bucket_line, M_max + 16);
+    if (mail_sorted) {                                   // the coarsely sorted copy of the received mail
+      ENSURE_U(c->tmp_ent, (M_max + 1) * sizeof(uint4));
+      ENSURE_U(c->tmp_dest, (M_max + 1) * 4);
+    }
     const uint64_t max_rows = (M_max + creators_max + 1) / 2 + 1;      // slots = mail + own creators
     if (c->srcp.cap < 2 * max_rows * 4 + 256 || c->estate.cap < 2 * max_rows) {
       grew = true;
@@ -687,6 +764,22 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
   // ---- receiver side: mailboxes of my rows, rows
   a.mail_ent = D->rx_ent.as<uint4>();
   a.mail_dest = D->rx_dest.as<uint32_t>();
+  if (mail_sorted) {
+    a.mail_sorted = 1;
+    a.nb_coarse = NB_COARSE2;
+    uint32_t shift = 0;
+    while (((P.Vloc ? P.Vloc - 1 : 0u) >> shift) >= (uint32_t) NB_COARSE2) shift++;
+    a.coarse_shift = shift;
+    a.rx_ent = D->rx_ent.as<uint4>();
+    a.rx_dest = D->rx_dest.as<uint32_t>();
+    a.n_mail = (uint32_t) M;
+    a.tmp_ent = c->tmp_ent.as<uint4>();                  // may have grown
+    a.tmp_dest = c->tmp_dest.as<uint32_t>();
+    CK(cudaMemsetAsync(D->mail_hist.p, 0, (NB_COARSE2 + 2) * 4, s));
+    c->stats.kernel_launches += launch_b2_coarse_sort(a, D->mail_hist.as<uint32_t>(), s);
+    a.mail_ent = a.tmp_ent;
+    a.mail_dest = a.tmp_dest;
+  }
   a.bucket = c->bucket.as<uint4>();
   a.bucket_line = c->bucket_line.as<uint8_t>();
   a.corrections = c->corrections.as<uint4>();
@@ -780,7 +873,7 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   std::vector<uint32_t> all;
   FilterArgs a{};
   // sized by what the fullest rank holds, so that every rank's buffers grow in the same step
-  bool grew = c->proposals.cap < (P.E_max + 1) * sizeof(uint2) || c->poly_cur.cap < (Vg + 1) * 4 ||
+  bool grew = c->proposals.cap < proposal_capacity(P.E_max) * sizeof(uint2) || c->poly_cur.cap < (Vg + 1) * 4 ||
                     c->vres.cap < (Vg + 1) * 4 ||
                     (P.big_rows_max != 0 &&
                      c->big_scratch.cap < (size_t) (P.big_rows_max < (uint32_t) c->sm_count * 2 ? P.big_rows_max
@@ -819,7 +912,8 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   rc = [&]() -> int {
     if (read_counters(c) != 0) return -1;
     if (c->h_counters[CNT_ERROR] & 4u) return fail(c, "gtsb_filter: a contig is longer than 2^31-1");
-    if (c->h_counters[CNT_OVERFLOW]) return fail(c, "gtsb_filter: proposal list overflow");
+    if (c->h_counters[CNT_OVERFLOW])
+      return fail(c, "gtsb_filter: more polymorphic proposals than a quarter of the slots (the partitioned filter sizes its list for that)");
     return 0;
   }();
   const uint32_t my_prop = c->h_counters[CNT_PROPOSALS];
@@ -918,8 +1012,12 @@ int dist_filter(gtsb_context *c, DistState *D, const Plan &P, float cn_cutoff, f
   }
 
   // final states
+  // the final pass reads a neighbour's fire bits and repeat predicate from the byte summary (and its
+  // polyTime from poly_cur, which every rank holds complete): one byte per vertex crosses NVLink
   launch_vres(a, s);
-  if (allgatherv(c, "nccl_allgather_vres", c->vres.p, 4, P.lo) != 0) return -1;
+  static const bool summary = !(getenv("GTSB_FINAL") != nullptr && atoi(getenv("GTSB_FINAL")) == 1);
+  if (allgatherv(c, "nccl_allgather_vsum", c->vsum.p, 1, P.lo) != 0) return -1;
+  if (!summary && allgatherv(c, "nccl_allgather_vres", c->vres.p, 4, P.lo) != 0) return -1;     // dev switch
   launch_finalize(a, s);
   c->stats.kernel_launches += 2 + (c->n_big_rows ? 1 : 0);
   return 0;
@@ -1029,6 +1127,29 @@ int gtsb_get_edges(gtsb_context *c, uint64_t *nof_edges, uint32_t *eid, uint32_t
   if (flags) CK(cudaMemcpyAsync(flags, c->x_flags.p, E, cudaMemcpyDeviceToHost, s));
   if (estate) CK(cudaMemcpyAsync(estate, c->estate.p, E, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int gtsb_result_digest(gtsb_context *c, uint64_t out[3]) {
+  if (c == nullptr || out == nullptr) return -1;
+  if (!c->have_graph) return fail(c, "gtsb_result_digest: no graph");
+  CK(cudaSetDevice(c->device));
+  if (c->E && c->eid.p == nullptr) return fail(c, "gtsb_result_digest: this graph has no edge ids (not built here)");
+  cudaStream_t s = c->stream;
+  ENSURE(c->x_deg, 64);
+  CK(cudaMemsetAsync(c->x_deg.p, 0, 16, s));
+  unsigned long long *acc = c->x_deg.as<unsigned long long>();
+  const GraphArgs g = graph_args(c);
+  if (c->E) k_digest_edges<<<c->sm_count * 8, 256, 0, s>>>(g, c->eid.as<uint32_t>(), acc);
+  if (c->V) k_digest_vertices<<<c->sm_count * 8, 256, 0, s>>>(c->V, c->vstate.as<uint8_t>(), acc + 1);
+  c->stats.kernel_launches += 2;
+  uint64_t h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  out[0] = c->E;
+  out[1] = h[0];
+  out[2] = h[1];
   return 0;
 }
 

@@ -55,6 +55,7 @@ constexpr uint32_t NONE = 0xffffffffu;
 constexpr uint32_t VI_MARKED = 1u << 31;
 constexpr uint32_t VR_TIME_MASK = (1u << 27) - 1u;   // all ones = never
 constexpr uint32_t VR_F0 = 1u << 27, VR_F1 = 1u << 28, VR_REP = 1u << 29;
+constexpr uint32_t VS_F0 = 1u, VS_F1 = 2u, VS_REP = 4u, VS_POLY = 8u;      // vsum byte
 // fstat bits: 0/1 = F[v, antisense/sense], 2/3 = that direction is decided
 constexpr uint8_t FS_DECIDED_ALL = 0x0C;
 constexpr int WARPS = 8;                             // warps per block of the flat passes
@@ -1077,6 +1078,87 @@ int launch_fire_rounds_all(const FilterArgs &a, uint32_t *ring, uint32_t max_rou
   return cudaLaunchCooperativeKernel((const void *) k_fire_rounds_all, grid, block, args, 0, s) == cudaSuccess ? 0 : -1;
 }
 
+// ------------------------------------------------------------------ components and terminals
+//
+// gt_scaffolder_calc_cc_and_terminals (algorithms.c:379-436) grows its "components" by a
+// breadth-first search from the smallest unvisited unmarked vertex, along UNMARKED edges v -> w
+// between unmarked vertices.  Edge marks are not symmetric (mark_edges_in_twin_dir, :245-258, marks
+// w -> x without x -> w), so the search is over a directed graph, and the component a vertex ends
+// up in is the one of the smallest root that reaches it:  label(v) = min { u : u ->* v } (a vertex
+// claimed by an earlier root has taken everything it reaches with it).  That fixed point is
+// computed by min-label hooking over the usable edges plus pointer jumping
+// (label(v) <- label(label(v)): the label of an ancestor is an ancestor's), a few passes over the
+// slots.  gt_scaffolder_graph_isterminal (:346-373) is "the unmarked edges do not point both ways".
+
+__global__ void __launch_bounds__(256) k_cc_init(GraphArgs g, uint32_t *__restrict__ lab, uint8_t *__restrict__ term) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.V) return;
+  const uint32_t v = id_at(g, p);
+  lab[p] = vertex_state_marked(g.vstate[v]) ? NONE : v;
+  uint32_t dirs = 0;
+  for (uint32_t s = g.row_ptr[p]; s < g.row_ptr[p + 1]; s++)
+    if (!edge_state_marked(g.estate[s])) dirs |= (g.flags[s] & F_SENSE) ? 2u : 1u;
+  term[p] = dirs == 3u ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) k_cc_hook(GraphArgs g, uint32_t *__restrict__ lab, uint32_t *__restrict__ changed) {
+  bool any = false;
+  for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < g.E; s += (uint64_t) gridDim.x * blockDim.x) {
+    if (edge_state_marked(g.estate[s])) continue;
+    const uint32_t lv = lab[g.srcp[s] & S_POS];
+    if (lv == NONE) continue;
+    const uint32_t w = g.dst[s];
+    const uint32_t lw = lab[w];
+    if (lw != NONE && lv < lw) {
+      atomicMin(&lab[w], lv);
+      any = true;
+    }
+  }
+  if (any) *changed = 1u;
+}
+
+__global__ void __launch_bounds__(256) k_cc_jump(GraphArgs g, uint32_t *__restrict__ lab, uint32_t *__restrict__ changed) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.V) return;
+  const uint32_t l = lab[p];
+  if (l == NONE) return;
+  const uint32_t up = lab[g.pos != nullptr ? g.pos[l] : l];      // the label of the vertex named by my label
+  if (up < l) {
+    atomicMin(&lab[p], up);
+    *changed = 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cc_out(GraphArgs g, const uint32_t *__restrict__ lab,
+                                                const uint8_t *__restrict__ term, uint32_t *__restrict__ label_by_id,
+                                                uint8_t *__restrict__ term_by_id) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.V) return;
+  const uint32_t v = id_at(g, p);
+  label_by_id[v] = lab[p];
+  term_by_id[v] = term[p];
+}
+
+void launch_cc_init(const GraphArgs &g, uint32_t *lab, uint8_t *term, cudaStream_t s) {
+  if (g.V == 0) return;
+  KernelTimer t_("k_cc_init", s);
+  k_cc_init<<<(g.V + 255) / 256, 256, 0, s>>>(g, lab, term);
+}
+
+void launch_cc_round(const GraphArgs &g, uint32_t *lab, uint32_t *changed, cudaStream_t s) {
+  if (g.V == 0) return;
+  KernelTimer t_("k_cc_round(2 kernels)", s);
+  if (g.E) k_cc_hook<<<g.sm_count * 16, 256, 0, s>>>(g, lab, changed);
+  k_cc_jump<<<(g.V + 255) / 256, 256, 0, s>>>(g, lab, changed);
+}
+
+void launch_cc_out(const GraphArgs &g, const uint32_t *lab, const uint8_t *term, uint32_t *label_by_id,
+                   uint8_t *term_by_id, cudaStream_t s) {
+  if (g.V == 0) return;
+  KernelTimer t_("k_cc_out", s);
+  k_cc_out<<<(g.V + 255) / 256, 256, 0, s>>>(g, lab, term, label_by_id, term_by_id);
+}
+
 // ------------------------------------------------------------------ final states
 
 __global__ void __launch_bounds__(256) k4_vres(FilterArgs a) {
@@ -1086,8 +1168,12 @@ __global__ void __launch_bounds__(256) k4_vres(FilterArgs a) {
   const uint32_t p = g.row_base + pl;
   const uint32_t t = a.poly_cur[p];
   const uint32_t f = a.fstat[p];
+  const bool rep = a.fused_repeats && a.rep_pred[p];
   a.vres[p] = (t == NO_TIME ? VR_TIME_MASK : t) | ((f & 1u) ? VR_F0 : 0u) | ((f & 2u) ? VR_F1 : 0u) |
-              ((a.fused_repeats && a.rep_pred[p]) ? VR_REP : 0u);
+              (rep ? VR_REP : 0u);
+  // what the final pass needs of a NEIGHBOUR, in one byte (the table stays L2-resident where the
+  // 4-byte one does not): fire bits, repeat predicate, "has a polyTime" (then poly_cur is read too)
+  a.vsum[p] = (uint8_t) ((f & 3u) | (rep ? VS_REP : 0u) | (t != NO_TIME ? VS_POLY : 0u));
   if (t != NO_TIME) g.vstate[id_at(g, p)] = GIS_POLYMORPHIC;
 }
 
@@ -1152,6 +1238,84 @@ __global__ void __launch_bounds__(32 * WARPS, 8) k4_finalize(FilterArgs a) {
     });
 }
 
+// The final pass with the neighbour facts read from the one-byte summary.  A window without a
+// polymorphic vertex in or next to its rows (most of them) needs no vertex ids and no row maxima:
+// an edge is INCONSISTENT iff anything fired into its (row, direction) or its own row fired.  The
+// other windows take the exact route: polyTime of the neighbours that have one (poly_cur, by
+// position -- complete on every rank of a partitioned graph), ids of the firing neighbours of the
+// rows that need the order.
+struct FinalState2 {
+  uint32_t start, n, sp, dst, fl, own, rs;
+};
+
+__global__ void __launch_bounds__(32 * WARPS, 8) k4_finalize2(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  const uint32_t lane = lane_id();
+  for_each_window<1>(g,
+    [&](uint32_t start, uint32_t n) {
+      FinalState2 t;
+      t.start = start;
+      t.n = n;
+      const bool valid = lane < n;
+      const uint32_t s = start + lane;
+      t.sp = valid ? __ldcs(g.srcp + s) : NONE;
+      t.dst = valid ? __ldcs(g.dst + s) : 0u;
+      t.fl = valid ? __ldcs(g.flags + s) : 0u;
+      return t;
+    },
+    [&](FinalState2 &t) {
+      const bool valid = lane < t.n;
+      t.own = valid ? a.vres[t.sp & S_POS] : VR_TIME_MASK;
+      t.rs = valid ? (uint32_t) a.vsum[t.dst] : 0u;
+    },
+    [&](FinalState2 &t) {
+      const Window W = open_window(t.start, t.n, t.sp);
+      const uint32_t f = t.fl, rs = t.rs, own = t.own;
+      const bool fin = W.valid && (rs & ((f & F_RSENSE) ? VS_F1 : VS_F0));
+      const uint32_t dir = twin_dir((f & F_RSENSE) != 0, (f & F_RSAME) != 0) ? 1u : 0u;
+      const bool exact = W.valid && ((own & VR_TIME_MASK) != VR_TIME_MASK || (rs & VS_POLY));
+      const uint32_t FIN0 = __ballot_sync(FULL, fin && !dir), FIN1 = __ballot_sync(FULL, fin && dir);
+      const uint32_t EX = __ballot_sync(FULL, exact);
+      const uint32_t sd = (f & F_SENSE) ? 1u : 0u;
+      if (EX == 0u) {
+        if (!W.valid) return;
+        const bool into = ((sd ? FIN1 : FIN0) & W.rowmask) != 0u;
+        if (into || (own & (sd ? VR_F1 : VR_F0)))
+          __stcs(g.estate + W.s, (uint8_t) GIS_INCONSISTENT);
+        else if (a.fused_repeats)
+          __stcs(g.estate + W.s, (uint8_t) (((own & VR_REP) || (rs & VS_REP)) ? GIS_REPEAT : GIS_UNVISITED));
+        return;
+      }
+      // exact route
+      const bool row_exact = (EX & W.rowmask) != 0u;
+      uint32_t tu = VR_TIME_MASK;
+      if (W.valid && (rs & VS_POLY)) {
+        const uint32_t tt = a.poly_cur[t.dst];
+        tu = tt == NO_TIME ? VR_TIME_MASK : tt;
+      }
+      const uint32_t ru = tu | ((rs & VS_F0) ? VR_F0 : 0u) | ((rs & VS_F1) ? VR_F1 : 0u) | ((rs & VS_REP) ? VR_REP : 0u);
+      int inc0 = -1, inc1 = -1;
+      if ((FIN0 | FIN1) != 0u) {
+        // rows that do not need the order: any non-negative id stands for "something fired into it"
+        const int id = fin ? (row_exact ? (int) id_at(g, t.dst) : 0) : -1;
+        inc0 = row_max(fin && !dir ? id : -1, W.vb, W.ve);
+        inc1 = row_max(fin && dir ? id : -1, W.vb, W.ve);
+      }
+      if (W.valid) final_state(a, W.s, f, ru, own, W.row, inc0, inc1);
+    });
+}
+
+// a neighbour's final facts in the layout of vres, from the byte summary (+ poly_cur where it has a polyTime)
+__device__ __forceinline__ uint32_t neighbour_facts(const FilterArgs &a, uint32_t u) {
+  const uint32_t rs = a.vsum[u];
+  uint32_t tu = VR_TIME_MASK;
+  if (rs & VS_POLY) {
+    const uint32_t tt = a.poly_cur[u];
+    tu = tt == NO_TIME ? VR_TIME_MASK : tt;
+  }
+  return tu | ((rs & VS_F0) ? VR_F0 : 0u) | ((rs & VS_F1) ? VR_F1 : 0u) | ((rs & VS_REP) ? VR_REP : 0u);
+}
+
 // warp per big row
 __global__ void __launch_bounds__(256) k4_finalize_big(FilterArgs a) {
   const GraphArgs &g = a.g;
@@ -1165,7 +1329,7 @@ __global__ void __launch_bounds__(256) k4_finalize_big(FilterArgs a) {
       const uint32_t f = g.flags[r0 + k];
       const bool rs = (f & F_RSENSE) != 0, rm = (f & F_RSAME) != 0;
       const uint32_t u = g.dst[r0 + k];
-      if (a.vres[u] & (rs ? VR_F1 : VR_F0)) {
+      if (a.vsum[u] & (rs ? VS_F1 : VS_F0)) {
         const int id = (int) id_at(g, u);
         if (twin_dir(rs, rm)) inc1 = max(inc1, id); else inc0 = max(inc0, id);
       }
@@ -1174,7 +1338,7 @@ __global__ void __launch_bounds__(256) k4_finalize_big(FilterArgs a) {
     inc1 = __reduce_max_sync(FULL, inc1);
     for (uint32_t k = lane_id(); k < d; k += 32) {
       const uint32_t u = g.dst[r0 + k];
-      final_state(a, r0 + k, g.flags[r0 + k], a.vres[u], own, p, inc0, inc1);
+      final_state(a, r0 + k, g.flags[r0 + k], neighbour_facts(a, u), own, p, inc0, inc1);
     }
   }
 }
@@ -1189,7 +1353,14 @@ void launch_finalize(const FilterArgs &a, cudaStream_t s) {
   if (a.g.V == 0 || a.g.E == 0) return;
   {
     KernelTimer t_("k4_finalize", s);
-    k4_finalize<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
+    static const int summary = [] {
+      const char *e = getenv("GTSB_FINAL");              // 1: neighbour facts from the 4-byte table (dev switch)
+      return (e != nullptr && atoi(e) == 1) ? 0 : 1;
+    }();
+    if (summary)
+      k4_finalize2<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
+    else
+      k4_finalize<<<host_flat_grid(a.g.n_windows), 32 * WARPS, 0, s>>>(a);
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_finalize_big", s);

@@ -70,6 +70,9 @@ struct Build2Args {
   uint32_t *rank_cnt;                       // [nranks] mail this rank sends to every rank
   const uint4 *mail_ent;                    // the stream k2_deliver reads (tmp_ent, or what the ranks sent us)
   const uint32_t *mail_dest;
+  const uint4 *rx_ent;                      // partitioned build with mail_sorted: what the ranks sent us, in no order
+  const uint32_t *rx_dest;                  // (k2_deliver2<COARSE> sorts it into tmp_ent / tmp_dest)
+  uint32_t n_mail;                          // its length
   // partitioned build: k2_partition stores each rank's mail straight into that rank's receive
   // buffers over NVLink (peer memory); entry `at` of my send order goes to index at + peer_shift[r]
   uint4 *const *peer_ent;                   // [nranks] (nullptr: write tmp_ent / tmp_dest)
@@ -114,6 +117,7 @@ int launch_b2_head_write(const Build2Args &a, cudaStream_t s);
 int launch_b2_classify(const Build2Args &a, cudaStream_t s);
 int launch_b2_partition(const Build2Args &a, cudaStream_t s);
 int launch_b2_count_mail(const Build2Args &a, uint32_t n_mail, cudaStream_t s);
+int launch_b2_coarse_sort(const Build2Args &a, uint32_t *hist, cudaStream_t s);
 int launch_b2_deliver_resolve(const Build2Args &a, cudaStream_t s);
 int launch_b2_apply_corrections(const Build2Args &a, const uint4 *list, uint32_t n, cudaStream_t s);
 
@@ -207,6 +211,7 @@ struct FilterArgs {
   uint32_t big_blocks;
   uint2 *vinfo;              // {copy_num, seq_len | marked-on-entry << 31}
   uint32_t *vres;            // polyTime | fire bits | repeat predicate
+  uint8_t *vsum;             // fire bits | repeat predicate | has-polyTime: what the final pass gathers per neighbour
   int fused_repeats;         // fresh graph: edge REPEAT marks are derived, not stored (gtsb_pipeline)
 };
 constexpr uint32_t BIG_SCRATCH_STRIDE = 12;   // cn f32, len u32, u8 marks (padded)
@@ -232,6 +237,12 @@ constexpr int FIRE_ROUNDS_PER_SYNC = 4;
 constexpr int POLY_SWEEPS_PER_SYNC = 4;
 void launch_vres(const FilterArgs &a, cudaStream_t s);          // final per-vertex facts (+ POLYMORPHIC vertex marks)
 void launch_finalize(const FilterArgs &a, cudaStream_t s);      // final edge states; needs every neighbour's vres
+// components of gt_scaffolder_calc_cc_and_terminals: lab/term by position; one round = hooking + pointer
+// jumping, *changed is raised when a label moved
+void launch_cc_init(const GraphArgs &g, uint32_t *lab, uint8_t *term, cudaStream_t s);
+void launch_cc_round(const GraphArgs &g, uint32_t *lab, uint32_t *changed, cudaStream_t s);
+void launch_cc_out(const GraphArgs &g, const uint32_t *lab, const uint8_t *term, uint32_t *label_by_id,
+                   uint8_t *term_by_id, cudaStream_t s);
 // cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)
 int launch_pack_windows(const GraphArgs &g, uint32_t *count, uint32_t *woff, uint32_t *win_start,
                         uint32_t *scan_scratch, cudaStream_t s);

@@ -81,6 +81,12 @@ int gtsb_set_vertices_host(gtsb_context *ctx, uint64_t nof_vertices, const uint3
                            const float *astat, const float *copy_num);
 int gtsb_set_vertices_device(gtsb_context *ctx, uint64_t nof_vertices, const uint32_t *seq_len,
                              const float *astat, const float *copy_num);
+/* Partitioned graph (after gtsb_dist_init): this rank uploads only the attributes of the contigs
+   [first, first + count) -- the arrays hold `count` values -- and gtsb_pipeline gathers the other
+   ranks' slices over NVLink instead of every rank pushing all of them through the host's PCIe.
+   The ranks' slices must tile [0, nof_vertices) in rank order. */
+int gtsb_set_vertices_slice_host(gtsb_context *ctx, uint64_t nof_vertices, uint64_t first, uint64_t count,
+                                 const uint32_t *seq_len, const float *astat, const float *copy_num);
 int gtsb_set_records_host(gtsb_context *ctx, uint64_t nof_records, const uint32_t *root,
                           const uint32_t *ctg, const int32_t *dist, const float *std_dev,
                           const uint8_t *flags);
@@ -203,6 +209,21 @@ int gtsb_dist_init(gtsb_context *ctx, int rank, int world, const void *id128);
    graph->edges[] (creation order; within a vertex, adjacency order = eid order) */
 int gtsb_get_edges(gtsb_context *ctx, uint64_t *nof_edges, uint32_t *eid, uint32_t *src, uint32_t *dst,
                    int32_t *dist, float *std_dev, uint8_t *flags, uint8_t *estate);
+
+/* ---- components and terminal vertices of the current graph and states: the facts
+   gt_scaffolder_calc_cc_and_terminals (gt_scaffolder_algorithms.c:379-436) derives by breadth-first
+   search before removecycles and makescaffold walk the graph.  label[v] = the smallest vertex id
+   from which v is reached along unmarked edges between unmarked vertices (v itself included) --
+   the root of the reference's component of v; 0xFFFFFFFF for a marked vertex.  terminal[v] =
+   gt_scaffolder_graph_isterminal (:346-373): the unmarked edges of v do not point both ways.
+   Single-device graphs. */
+int gtsb_components(gtsb_context *ctx, uint32_t *label, uint8_t *terminal);
+
+/* order-independent digests of the result, for comparing runs too large to fetch: out[0] = edges
+   on this device, out[1] = sum over them of a 64-bit hash of (eid, src, dst, dist, std_dev bits,
+   flags & 15, state), out[2] = sum over ALL vertices of a hash of (id, state).  The ranks' out[0]
+   and out[1] of a partitioned graph add up (mod 2^64) to those of the same graph on one device. */
+int gtsb_result_digest(gtsb_context *ctx, uint64_t out[3]);
 
 /* ---- results (device-resident until fetched; NULL pointers are skipped) */
 uint64_t gtsb_nof_edges(const gtsb_context *ctx);

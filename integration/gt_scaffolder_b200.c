@@ -1077,3 +1077,92 @@ int gt_scaffolder_graph_write_scaffold(GtArray *records, const char *file_name, 
   gt_free(out);
   return had_err;
 }
+
+/* ------------------------------------------------------------------ components */
+
+/* gt_scaffolder_calc_cc_and_terminals (algorithms.c:379-436; external linkage, called by
+   gt_scaffolder_removecycles :510 and gt_scaffolder_makescaffold :784 -- integration/Makefile
+   weakens the reference's definition so that those calls arrive here).  The device labels every
+   unmarked vertex with the root of its component and evaluates gt_scaffolder_graph_isterminal
+   for all vertices (gtsb_components); what is left for the host is the ORDER in which the
+   reference's search stores the terminal vertices of a component with more than one vertex --
+   its own queue loop, restricted to that component.  Components come out in the order of their
+   roots, as the outer loop of the reference finds them. */
+void gt_scaffolder_calc_cc_and_terminals(const GtScaffolderGraph *graph, GtArray *ccs)
+{
+  B200Flat f;
+  gtsb_context *c = b200_context();
+  uint32_t *label, *size;
+  uint8_t *terminal, *seen;
+  GtUword *queue, v, head, tail, eid;
+  int resident;
+
+  gt_assert(graph != NULL);
+  gt_assert(ccs != NULL);
+  if (c == NULL)
+    b200_die("gt_scaffolder_calc_cc_and_terminals");
+  resident = mirror_sync(c, graph);
+  if (resident < 0)
+    b200_die("gt_scaffolder_calc_cc_and_terminals");
+  if (resident == 0) {
+    if (graph_flatten(graph, &f, "calc_cc_and_terminals") != 0)
+      exit(EXIT_FAILURE);
+    if (graph_upload(c, &f) != 0)
+      b200_die("gt_scaffolder_calc_cc_and_terminals");
+    b200_graph_uploads++;
+    flat_free(&f);
+  }
+  label = gt_malloc((graph->nof_vertices + 1) * sizeof (*label));
+  size = gt_calloc(graph->nof_vertices + 1, sizeof (*size));
+  terminal = gt_malloc(graph->nof_vertices + 1);
+  seen = gt_calloc(graph->nof_vertices + 1, 1);
+  queue = gt_malloc((graph->nof_vertices + 1) * sizeof (*queue));
+  if (gtsb_components(c, label, terminal) != 0)
+    b200_die("gt_scaffolder_calc_cc_and_terminals");
+
+  for (v = 0; v < graph->nof_vertices; v++)
+    if (label[v] != UINT32_MAX)
+      size[label[v]]++;
+  for (v = 0; v < graph->nof_vertices; v++) {
+    GtArray *terminal_vertices;
+    GtScaffolderGraphVertex *vertex = graph->vertices + v;
+    if (label[v] != (uint32_t) v)
+      continue;                                   /* marked, or reached from a smaller vertex */
+    terminal_vertices = gt_array_new(sizeof (vertex));
+    if (size[v] == 1) {
+      if (terminal[v])
+        gt_array_add(terminal_vertices, vertex);
+    } else {
+      head = tail = 0;
+      queue[tail++] = v;
+      seen[v] = 1;
+      while (head < tail) {
+        const GtUword cur = queue[head++];
+        GtScaffolderGraphVertex *currentvertex = graph->vertices + cur;
+        if (terminal[cur])
+          gt_array_add(terminal_vertices, currentvertex);
+        for (eid = 0; eid < currentvertex->nof_edges; eid++) {
+          const GtScaffolderGraphEdge *e = currentvertex->edges[eid];
+          const GtUword next = (GtUword) (e->end - graph->vertices);
+          if (e->state == GIS_INCONSISTENT || e->state == GIS_POLYMORPHIC || e->state == GIS_CYCLIC ||
+              e->state == GIS_REPEAT)
+            continue;
+          if (label[next] == (uint32_t) v && !seen[next]) {
+            seen[next] = 1;
+            queue[tail++] = next;
+          }
+        }
+      }
+    }
+    gt_array_add(ccs, terminal_vertices);
+  }
+  /* the states the reference's search leaves behind (algorithms.c:393-397, 419) */
+  for (v = 0; v < graph->nof_vertices; v++)
+    if (label[v] != UINT32_MAX)
+      graph->vertices[v].state = GIS_VISITED;
+  gt_free(label);
+  gt_free(size);
+  gt_free(terminal);
+  gt_free(seen);
+  gt_free(queue);
+}

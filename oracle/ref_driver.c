@@ -258,6 +258,44 @@ int refdrv_write_scaffold(GtScaffolderGraph *g, const char *filename)
   return rc;
 }
 
+/* gt_scaffolder_calc_cc_and_terminals (algorithms.c:379-436; not in the header, external linkage):
+   the components in the order the reference finds them, as arrays.  cc_off[n_cc + 1] cuts
+   terminals[] (vertex ids, in the order the search meets them); returns the number of
+   components, or -1 when a capacity is too small.  Leaves the vertex states as the reference
+   does (every unmarked vertex GIS_VISITED). */
+void gt_scaffolder_calc_cc_and_terminals(const GtScaffolderGraph *graph, GtArray *ccs);
+
+int64_t refdrv_calc_cc(GtScaffolderGraph *g, uint64_t *cc_off, uint64_t cc_cap, uint32_t *terminals,
+                       uint64_t term_cap)
+{
+  GtArray *ccs = gt_array_new(sizeof (GtArray *));
+  GtUword i, j;
+  uint64_t k = 0;
+  int64_t n;
+  gt_scaffolder_calc_cc_and_terminals(g, ccs);
+  n = (int64_t) gt_array_size(ccs);
+  for (i = 0; i < gt_array_size(ccs); i++) {
+    GtArray *t = *(GtArray **) gt_array_get(ccs, i);
+    if (n >= 0 && i < cc_cap)
+      cc_off[i] = k;
+    else
+      n = -1;
+    for (j = 0; j < gt_array_size(t); j++, k++) {
+      if (n >= 0 && k < term_cap)
+        terminals[k] = (uint32_t) (*(GtScaffolderGraphVertex **) gt_array_get(t, j) - g->vertices);
+      else
+        n = -1;
+    }
+    gt_array_delete(t);
+  }
+  if (n >= 0 && (uint64_t) n < cc_cap)
+    cc_off[n] = k;
+  else
+    n = -1;
+  gt_array_delete(ccs);
+  return n;
+}
+
 void refdrv_delete(GtScaffolderGraph *g)
 {
   /* gt_scaffolder_graph_delete calls gt_str_delete on every header;

@@ -240,6 +240,17 @@ class RefGraph(_Common):
     def write_scaffold(self, path):
         return self.L.refdrv_write_scaffold(self.h, path.encode())
 
+    def calc_cc(self):
+        """gt_scaffolder_calc_cc_and_terminals: list of components, each the list of its terminal vertex
+        ids in the order the reference's search stores them (vertex states change as the reference's do)"""
+        off = np.zeros(self.V + 2, np.uint64)
+        term = np.zeros(self.V + 1, np.uint32)
+        self.L.refdrv_calc_cc.restype = C.c_int64
+        n = self.L.refdrv_calc_cc(C.c_void_p(self.h), off.ctypes.data_as(C.c_void_p), C.c_uint64(len(off)),
+                                  term.ctypes.data_as(C.c_void_p), C.c_uint64(len(term)))
+        assert n >= 0
+        return [term[int(off[i]):int(off[i + 1])].tolist() for i in range(int(n))]
+
     def close(self):
         if self.h:
             self.L.refdrv_delete(self.h)

@@ -94,7 +94,10 @@ def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth):
         if name != "ref":
             # the graph crosses the bus ONCE (the records, in new_from_file); mark_repeats and
             # filter run on the device-resident copy and only fetch states
-            assert b"graph uploads 1, calls on the resident graph 2" in r.stderr, (name, r.stderr.decode()[-500:])
+            # (and so do the component searches of removecycles and makescaffold, which send changed states only)
+            import re
+            m = re.search(rb"graph uploads (\d+), calls on the resident graph (\d+)", r.stderr)
+            assert m and int(m.group(1)) == 1 and int(m.group(2)) >= 2, (name, r.stderr.decode()[-500:])
             where = b"host" if (tok == "host" or irregular) else b"device"
             assert b"lib.de tokenised on the " + where in r.stderr, (name, r.stderr.decode()[-500:])
             if tok == "host":

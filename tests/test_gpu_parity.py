@@ -404,3 +404,39 @@ def test_special_values(pkg, synth, seed):
     bad = synth.special_values(seed)
     _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)])
     _run_both(pkg, bad, *PARAMS[seed % len(PARAMS)], force_general=True)
+
+
+@pytest.mark.gpu
+def test_result_digest_equals_its_numpy_statement(pkg, synth):
+    """gtsb_result_digest (what tools/c5_check.py compares between a partitioned and a single-device
+    run of graphs too large to fetch) == the same sums over the fetched arrays; it moves when one
+    state moves."""
+    inp = synth.generate("c2_bacterial", V=30000, seed=3)
+    g = pkg.ScaffoldGraphB200.new_from_records(inp)
+    g.mark_repeats(0.3, 20.0, True)
+    g.filter(0.01, 1.5, 400)
+    e, vs = g.edges(), g.vstate()
+    assert g.digest() == pkg.api.result_digest(e, vs)
+    e2 = dict(e)
+    e2["estate"] = e["estate"].copy()
+    e2["estate"][len(e2["estate"]) // 2] ^= 1
+    assert pkg.api.result_digest(e2, vs)[1] != g.digest()[1]
+    # and equals the digest of the oracle's result on the same input
+    ref = O.best_oracle().build(inp)
+    ref.mark_repeats(0.3, 20.0, use_copy_num=True)
+    ref.filter(0.01, 1.5, 400)
+    r = ref.result()
+    oe = dict(eid=np.arange(len(r["src"]), dtype=np.uint32), src=r["src"], dst=r["dst"], dist=r["dist"],
+              std_dev=r["std_dev"], flags=e["flags"][np.argsort(e["eid"])], estate=r["estate"])
+    assert pkg.api.result_digest(oe, r["vstate"]) == g.digest()
+    g.close()
+
+
+@pytest.mark.gpu
+def test_more_proposals_than_the_list_was_sized_for(pkg, synth):
+    """The proposal list holds E / 4 entries; with every pair ambiguous and a copy-number cutoff that
+    nothing exceeds most slots are proposed, the pairs pass overflows and is run again with room
+    for all of them."""
+    inp = synth.generate("c3_human", V=120000, seed=21)
+    st = _run_both(pkg, inp, 0.0, -1e9, True, -0.5, 9.0, 3000, stagewise=False)
+    assert st["proposals"] > st["nof_edges"] // 4 + 65536, st
