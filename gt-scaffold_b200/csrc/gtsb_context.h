@@ -76,6 +76,7 @@ struct gtsb_context {
       p_line_cnt, p_line_off, num_pairs, p_last, p_astat, p_copy_num;
   DevBuf f_state, f_sense, f_src, f_dst, f_dist, f_len, f_off, f_out;     // .dot lines (gtsb_format.cu)
   DevBuf s_root, s_recoff, s_end, s_dist, s_std, s_flags, s_len_r, s_off_r;   // .scaf records (gtsb_format.cu)
+  DevBuf m_pairs, m_size, m_count, m_pmf, m_logp, m_L, m_c, m_n, m_g, m_slot_pair, m_gmax, m_mag, m_cand;   // distance MLE (gtsb_mle.cu)
   uint64_t names_V = 0, names_mask = 0;
   bool have_names = false, names_dup = false, have_num_pairs = false;
 

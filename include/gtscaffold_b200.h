@@ -210,6 +210,20 @@ int gtsb_dist_init(gtsb_context *ctx, int rank, int world, const void *id128);
 int gtsb_get_edges(gtsb_context *ctx, uint64_t *nof_edges, uint32_t *eid, uint32_t *src, uint32_t *dst,
                    int32_t *dist, float *std_dev, uint8_t *flags, uint8_t *estate);
 
+/* ---- distance estimates between contig pairs from read-pair fragments: estimate_dist_using_mle of
+   gt_scaffolder_bamparser.c (:385-598) for a batch of contig pairs.  Pair p owns the fragments
+   [frag_off[p], frag_off[p+1]) -- (start, end) as calculate_fragment (:600-661) stores them --
+   with its FragmentData.ma and the lengths of the two contigs; pmf / pmf_nof / minp are PmfData's
+   dist / nof / minp, rf the library orientation, min_dist / max_dist the scan range.  Out: dist[p]
+   and pairs_used[p] (the reference's *dist and *nof_pairs).  The likelihood scan runs on the
+   device in the reference's summation order; both logarithms are the host C library's
+   (csrc/gtsb_mle_core.h).  A negative probability anywhere in the distribution is the reference's
+   "negative probability" error. */
+int gtsb_mle_host(gtsb_context *ctx, uint64_t nof_pairs, const uint64_t *frag_off, const int64_t *frag_start,
+                  const int64_t *frag_end, const uint64_t *ma, const uint64_t *len_ref, const uint64_t *len_mref,
+                  const double *pmf, uint64_t pmf_nof, double minp, int rf, int64_t min_dist, int64_t max_dist,
+                  int64_t *dist, uint64_t *pairs_used);
+
 /* ---- components and terminal vertices of the current graph and states: the facts
    gt_scaffolder_calc_cc_and_terminals (gt_scaffolder_algorithms.c:379-436) derives by breadth-first
    search before removecycles and makescaffold walk the graph.  label[v] = the smallest vertex id

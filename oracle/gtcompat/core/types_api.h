@@ -16,6 +16,8 @@ typedef long GtWord;
 #define GT_WU "%lu"
 #define GT_WD "%ld"
 #define GT_WORD_MAX LONG_MAX
+#define GT_WORD_MIN LONG_MIN
+typedef unsigned char GtUchar;
 #define GT_UWORD_MAX ULONG_MAX
 #define GT_UNUSED __attribute__((unused))
 

@@ -1,11 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_dropin.py -m gpu -x -q -k "proposals_than or dropin or binding or config1 or digest_equals" > gpurun_out/r02_gputest_h.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_gputest_h.log
-tail -4 gpurun_out/r02_gputest_h.log
-for v in "GTSB_NB=128" "GTSB_NB=256" "GTSB_MAIL=3 GTSB_NB=128" "GTSB_MAIL=3 GTSB_NB=256"; do
-  tag=$(echo $v | tr '= ' '__')
-  env $v timeout 300 python tools/probe.py c3_human 0 10 > gpurun_out/r02_probe_h_$tag.json 2> gpurun_out/r02_probe_h_$tag.err
-  echo "probe $v rc=$?"
-done
-timeout 900 python tools/c5_check.py --steps 3 --out gpurun_out/r02_c5_n1.json > gpurun_out/c5d.log 2>&1; echo "c5 n1 rc=$?"
-tail -2 gpurun_out/c5d.log | cut -c1-300
-python tools/c5_check.py --compare gpurun_out/r02_c5_n1.json gpurun_out/r02_c5_n2.json | tee gpurun_out/r02_c5_n1_vs_n2.json
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 600 $TR --nproc-per-node 8 --master-port 29541 tests/dist_check.py > gpurun_out/r02_dist_check_n8.log 2>&1; echo "dist_check n8 rc=$?"
+grep -c -- "-> OK" gpurun_out/r02_dist_check_n8.log
+timeout 900 $TR --nproc-per-node 8 --master-port 29542 tools/c5_check.py --steps 5 --out gpurun_out/r02_c5_n8.json > gpurun_out/c5e.log 2>&1; echo "c5 n8 rc=$?"
+tail -1 gpurun_out/c5e.log | cut -c1-400
+timeout 900 $TR --nproc-per-node 8 --master-port 29543 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8_a.json 2> gpurun_out/r02_bench_n8_a.err; echo "bench n8 rc=$?"
+cut -c1-300 gpurun_out/r02_bench_n8_a.json
