@@ -307,7 +307,7 @@ def run_b200_arm(args, pkg):
 
     def set_device_inputs():
         g.set_vertices_device(Vn, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
-        if world == 1 and args.records == "lines":
+        if args.records == "lines":
             g.set_record_lines_device(int(lines[0].shape[0]), lines[0].data_ptr(), lines[1].data_ptr(), Rn,
                                       t["ctg"].data_ptr(), t["dist"].data_ptr(), t["std_dev"].data_ptr(),
                                       t["flags"].data_ptr())
@@ -478,7 +478,7 @@ def run_b200_arm(args, pkg):
             "config": {"workload": args.workload, "vertices_per_gpu": Vn // world, "records_per_gpu": Rn,
                        "edges_per_gpu": int(E), "line_order": args.line_order,
                        "records": ("line-shaped (root + first record per .de line, 13 B/record + 8 B/line)"
-                                   if world == 1 and args.records == "lines" else "flat (17 B/record)"),
+                                   if args.records == "lines" else "flat (17 B/record)"),
                        "graph": ("one graph" if world == 1 else
                                  f"one graph of {Vn} contigs partitioned over {world} ranks by .de line chunk; "
                                  "NCCL all-to-all (mail) and allgathers (vertex facts) inside the timed step"),

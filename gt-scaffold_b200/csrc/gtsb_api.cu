@@ -466,6 +466,12 @@ int do_build(gtsb_context *c) {
   }
   c->line_layout = false;
   c->csr_exported = false;
+  // the general build gives every long bucket 2 * next_pow2(n) scratch entries at a 32-bit offset
+  // (k_resolve_small): their sum is below 8 R, which must not wrap
+  if (8 * R >= 0xFFFFFFF0ull)
+    return fail(c, "gtsb_build: %llu records are more than the general (sort-based) build takes (2^29); "
+                   "only the line-ordered build goes beyond, and this input is outside it (reason mask %u)",
+                (unsigned long long) R, c->fallback_reason);
   if (await_records(c) != 0) return -1;
   if (ensure_root_column(c) != 0) return -1;
 
@@ -1127,9 +1133,15 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
                         const uint8_t *flags, const uint32_t *seq_len, const float *astat,
                         const float *copy_num, const uint8_t *vstate, const uint8_t *estate) {
   if (c == nullptr) return -1;
+  if (E >= 0xFFFFFFF0ull) return fail(c, "too many edges");
+  if (row_ptr == nullptr || (E && (dst == nullptr || dist == nullptr || std_dev == nullptr || flags == nullptr ||
+                                   estate == nullptr)) || (V && vstate == nullptr))
+    return fail(c, "gtsb_set_graph_host: null argument");
+  if (row_ptr[0] != 0 || row_ptr[V] != E) return fail(c, "gtsb_set_graph_host: row_ptr must run from 0 to nof_edges");
+  for (uint64_t v = 0; v < V; v++)
+    if (row_ptr[v + 1] < row_ptr[v]) return fail(c, "gtsb_set_graph_host: row_ptr decreases at vertex %llu", (unsigned long long) v);
   if (gtsb_set_vertices_host(c, V, seq_len, astat, copy_num) != 0) return -1;
   if (await_vertices(c) != 0 || await_records(c) != 0) return -1;
-  if (E >= 0xFFFFFFF0ull) return fail(c, "too many edges");
   cudaStream_t s = c->stream;
   ENSURE(c->row_ptr, (V + 1) * 4);
   ENSURE(c->srcp, E * 4 + 256);
@@ -1157,7 +1169,19 @@ int gtsb_set_graph_host(gtsb_context *c, uint64_t V, uint64_t E, const uint32_t 
   c->stats.kernel_launches += V ? 1 : 0;
   c->stats.kernel_launches += launch_pack_windows(graph_args(c), c->wcount.as<uint32_t>(), c->woff.as<uint32_t>(),
                                                   c->win_start.as<uint32_t>(), c->scan_scratch.as<uint32_t>(), s);
+  // what the filter's closed form assumes of the graph (reverse edges, flags): checked, not trusted
+  ENSURE(c->x_deg, 64);
+  CK(cudaMemsetAsync(c->x_deg.p, 0, 32, s));
+  launch_validate_csr(graph_args(c), c->x_deg.as<unsigned long long>(), c->x_deg.as<uint32_t>() + 4, s);
+  c->stats.kernel_launches += E ? 1 : 0;
+  unsigned long long vsums[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(vsums, c->x_deg.p, 24, cudaMemcpyDeviceToHost, s));
   if (read_counters(c) != 0) return -1;
+  if (vsums[2] & 1u) return fail(c, "gtsb_set_graph_host: an edge points to a vertex >= nof_vertices");
+  if (vsums[2] & 2u) return fail(c, "gtsb_set_graph_host: self edge");
+  if (vsums[0] != vsums[1])
+    return fail(c, "gtsb_set_graph_host: the edges do not pair up (every v -> w needs one w -> v whose sense/same are "
+                   "the reverse flags v -> w lists)");
   c->n_big_rows = c->h_counters[CNT_BIG_ROWS];
   c->max_deg = c->h_counters[CNT_MAX_DEG];
   c->n_windows = V ? c->h_counters[CNT_WINDOWS] : 0;

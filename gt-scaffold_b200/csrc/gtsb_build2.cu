@@ -137,31 +137,73 @@ __global__ void __launch_bounds__(256) k2_head_write(uint64_t R, uint32_t V, uin
   }
 }
 
-__global__ void __launch_bounds__(256) k2_lineless_flags(uint32_t V, const uint32_t *__restrict__ pos,
-                                                          uint8_t *__restrict__ flag) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < V) flag[v] = pos[v] == UNSET ? 1 : 0;
+// Contigs without a line take the positions after the lines, in id order: position = lines +
+// rank among them.  Two passes over the id -> position table in tiles of HEAD_TILE ids (count,
+// scan of the tile counts, rank inside the tile) instead of a flag byte and a prefix sum per vertex.
+__global__ void __launch_bounds__(256) k2_lineless_count(uint32_t Vg, const uint32_t *__restrict__ pos,
+                                                          uint32_t *__restrict__ tile_cnt) {
+  const uint64_t base = (uint64_t) blockIdx.x * HEAD_TILE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < HEAD_TILE / 256; k++) {
+    const uint64_t v = base + (uint64_t) k * 256 + threadIdx.x;
+    if (v < Vg) c += pos[v] == UNSET ? 1u : 0u;
+  }
+  uint32_t total;
+  block_excl_scan(c, &total);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(256) k2_lineless_assign(uint32_t V, uint64_t R,
-                                                           const uint32_t *__restrict__ nlines,
-                                                           const uint8_t *__restrict__ flag,
-                                                           const uint32_t *__restrict__ rank,
+// first = position of the first lineless contig (the number of lines; read on the device when
+// first_dev != nullptr).  write_vid: this device holds the rows of the lineless contigs.
+__global__ void __launch_bounds__(256) k2_lineless_assign(uint32_t Vg, uint32_t Vcap, const uint32_t *__restrict__ first_dev,
+                                                           uint32_t first_host, const uint32_t *__restrict__ tile_off,
                                                            uint32_t *__restrict__ pos, uint32_t *__restrict__ vid,
-                                                           uint32_t *__restrict__ ls,
-                                                           const uint32_t *__restrict__ counters) {
+                                                           int write_vid, const uint32_t *__restrict__ counters) {
+  if (counters[CNT_FALLBACK] | counters[CNT_ERROR]) return;
+  constexpr int ITEMS = HEAD_TILE / 256;
+  const uint32_t first = first_dev != nullptr ? *first_dev : first_host;
+  const uint64_t base = (uint64_t) blockIdx.x * HEAD_TILE + (uint64_t) threadIdx.x * ITEMS;
+  uint32_t mask = 0, c = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const uint64_t v = base + k;
+    if (v < Vg && pos[v] == UNSET) {
+      mask |= 1u << k;
+      c++;
+    }
+  }
+  uint32_t total;
+  uint32_t r = tile_off[blockIdx.x] + block_excl_scan(c, &total);
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    const uint32_t p = first + r++;
+    if (p < Vcap) {
+      pos[base + k] = p;
+      if (write_vid) vid[p] = (uint32_t) (base + k);
+    }
+  }
+}
+
+// line starts of the positions without records, and the end of the last line
+__global__ void __launch_bounds__(256) k2_fill_ls(uint32_t V, uint64_t R, const uint32_t *__restrict__ nlines,
+                                                   uint32_t *__restrict__ ls, const uint32_t *__restrict__ counters) {
   if (counters[CNT_FALLBACK] | counters[CNT_ERROR]) return;
   const uint32_t L = *nlines;
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v > V) return;
-  if (v >= L) ls[v] = (uint32_t) R;                  // positions without records (and ls[V])
-  if (v < V && flag[v]) {
-    const uint32_t p = L + rank[v];
-    if (p < V) {
-      pos[v] = p;
-      vid[p] = v;
-    }
-  }
+  if (v <= V && v >= L) ls[v] = (uint32_t) R;
+}
+
+int launch_lineless(uint32_t Vg, uint32_t Vcap, const uint32_t *first_dev, uint32_t first_host, uint32_t *pos,
+                    uint32_t *vid, int write_vid, uint32_t *tile_cnt, uint32_t *tile_off, uint32_t *scan_scratch,
+                    const uint32_t *counters, cudaStream_t s) {
+  if (Vg == 0) return 0;
+  const uint32_t ntiles = (Vg + HEAD_TILE - 1) / HEAD_TILE;
+  k2_lineless_count<<<ntiles, 256, 0, s>>>(Vg, pos, tile_cnt);
+  exclusive_scan<uint32_t>(tile_cnt, ntiles, tile_off, scan_scratch, s);
+  k2_lineless_assign<<<ntiles, 256, 0, s>>>(Vg, Vcap, first_dev, first_host, tile_off, pos, vid, write_vid, counters);
+  return 5;
 }
 
 // ------------------------------------------------------------------ segments
@@ -994,12 +1036,18 @@ int launch_b3_lines(const Build2Args &a, cudaStream_t s) {
     k3_lines<<<(a.n_lines + 256) / 256, 256, 0, s>>>(a);
   }
   KernelTimer t_("k2_lineless(2 kernels+scan)", s);
-  const uint32_t vb = (a.V + 256) / 256;
-  k2_lineless_flags<<<vb, 256, 0, s>>>(a.V, a.pos, a.lineless_flag);
-  exclusive_scan<uint8_t>(a.lineless_flag, a.V, a.lineless_rank, a.scan_scratch, s);
-  k2_lineless_assign<<<vb, 256, 0, s>>>(a.V, a.R, a.tile_off, a.lineless_flag, a.lineless_rank, a.pos, a.vid, a.ls,
-                                        a.counters);
-  return 1 + 2 + 3;
+  // the line count sits in tile_off[0]; the lineless pass uses its own tile tables behind it
+  k2_fill_ls<<<(a.V + 256) / 256, 256, 0, s>>>(a.V, a.R, a.tile_off, a.ls, a.counters);
+  launch_lineless(a.V, a.V, a.tile_off, 0u, a.pos, a.vid, 1, a.lineless_rank, a.lineless_rank + (a.V / HEAD_TILE + 2),
+                  a.scan_scratch, a.counters, s);
+  return 1 + 1 + 5;
+}
+
+// partitioned build, lines handed in as such: line starts, contig ids and positions of this rank's lines
+int launch_b3_lines_only(const Build2Args &a, cudaStream_t s) {
+  KernelTimer t_("k3_lines", s);
+  k3_lines<<<(a.n_lines + 256) / 256, 256, 0, s>>>(a);
+  return 1;
 }
 
 int launch_b2_head_counts(const Build2Args &a, cudaStream_t s) {
@@ -1024,12 +1072,10 @@ int launch_build2_lines(const Build2Args &a, cudaStream_t s) {
   }
   const uint32_t ntiles = (uint32_t) ((a.R + HEAD_TILE - 1) / HEAD_TILE);
   KernelTimer t_("k2_lineless(2 kernels+scan)", s);
-  const uint32_t vb = (a.V + 256) / 256;
-  k2_lineless_flags<<<vb, 256, 0, s>>>(a.V, a.pos, a.lineless_flag);
-  exclusive_scan<uint8_t>(a.lineless_flag, a.V, a.lineless_rank, a.scan_scratch, s);
-  k2_lineless_assign<<<vb, 256, 0, s>>>(a.V, a.R, a.tile_off + ntiles, a.lineless_flag, a.lineless_rank,
-                                        a.pos, a.vid, a.ls, a.counters);
-  return 2 + 3 + 2 + 3;
+  k2_fill_ls<<<(a.V + 256) / 256, 256, 0, s>>>(a.V, a.R, a.tile_off + ntiles, a.ls, a.counters);
+  launch_lineless(a.V, a.V, a.tile_off + ntiles, 0u, a.pos, a.vid, 1, a.lineless_rank,
+                  a.lineless_rank + (a.V / HEAD_TILE + 2), a.scan_scratch, a.counters, s);
+  return 2 + 3 + 1 + 5;
 }
 
 int launch_b2_classify(const Build2Args &a, cudaStream_t s) {

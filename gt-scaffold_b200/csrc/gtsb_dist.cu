@@ -252,22 +252,6 @@ __global__ void k_dist_check_pos(uint32_t L, uint32_t pos_base, const uint32_t *
   if (l < L && pos[vid[l]] != pos_base + l) atomicOr(&counters[CNT_FALLBACK], FB_MULTIRUN);
 }
 
-// contigs without a line: positions L_total + rank among them, rows on the last rank
-__global__ void k_dist_lineless(uint32_t Vg, uint32_t L_total, const uint8_t *__restrict__ flag,
-                                const uint32_t *__restrict__ rank, uint32_t *__restrict__ pos,
-                                uint32_t *__restrict__ vid_global, int is_last) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= Vg || !flag[v]) return;
-  const uint32_t p = L_total + rank[v];
-  pos[v] = p;
-  if (is_last) vid_global[p] = v;
-}
-
-__global__ void k_dist_flags(uint32_t Vg, const uint32_t *__restrict__ pos, uint8_t *__restrict__ flag) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < Vg) flag[v] = pos[v] == 0xFFFFFFFFu ? 1 : 0;
-}
-
 __global__ void k_dist_fill(uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint32_t value) {
   const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < hi) a[i] = value;
@@ -502,7 +486,10 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int se
   const uint32_t ntiles = (uint32_t) ((R + 4095) / 4096);
   std::vector<uint32_t> all;
   uint32_t L = 0;
-  if (R && setup_rc == 0) {
+  const bool lines_given = c->have_lines && R != 0;      // gtsb_set_record_lines_*: no need to look for the line starts
+  if (lines_given && setup_rc == 0) {
+    L = (uint32_t) c->n_lines;
+  } else if (R && setup_rc == 0) {
     KernelTimer t_("k2_heads(2 kernels+scan)", s);
     c->stats.kernel_launches += launch_b2_head_counts(a, s);
     CK(cudaMemcpyAsync(&L, a.tile_off + ntiles, 4, cudaMemcpyDeviceToHost, s));
@@ -545,7 +532,12 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int se
   a.V = L;                        // capacity of the line lists while the heads are written
   a.pos_base = P.own_lo;
   a.vid = c->vid.as<uint32_t>() + P.own_lo;
-  if (R) {
+  if (lines_given) {
+    a.line_root = c->line_root.as<uint32_t>();
+    a.line_start = c->line_start.as<uint32_t>();
+    a.n_lines = L;
+    c->stats.kernel_launches += launch_b3_lines_only(a, s);
+  } else if (R) {
     KernelTimer t_("k2_heads(2 kernels+scan)", s);
     c->stats.kernel_launches += launch_b2_head_write(a, s);
   }
@@ -554,14 +546,11 @@ int dist_positions(gtsb_context *c, DistState *D, Build2Args &a, Plan &P, int se
     NK(g_nccl.AllReduce(c->pos.p, c->pos.p, Vg, ncclUint32, ncclMin, D->comm, s));
   }
   {
-    KernelTimer t_("k_dist_lineless(4 kernels+scan)", s);
-    const uint32_t vb = (uint32_t) ((Vg + 255) / 256);
+    KernelTimer t_("k_dist_lineless(3 kernels+scan)", s);
     if (L) k_dist_check_pos<<<(L + 255) / 256, 256, 0, s>>>(L, P.own_lo, a.vid, a.pos, cnt);
-    k_dist_flags<<<vb, 256, 0, s>>>((uint32_t) Vg, a.pos, c->lineless_flag.as<uint8_t>());
-    exclusive_scan<uint8_t>(c->lineless_flag.as<uint8_t>(), Vg, c->lineless_rank.as<uint32_t>(),
-                            c->scan_scratch.as<uint32_t>(), s);
-    k_dist_lineless<<<vb, 256, 0, s>>>((uint32_t) Vg, (uint32_t) P.L_total, c->lineless_flag.as<uint8_t>(),
-                                       c->lineless_rank.as<uint32_t>(), a.pos, c->vid.as<uint32_t>(), last ? 1 : 0);
+    launch_lineless((uint32_t) Vg, (uint32_t) Vg, nullptr, (uint32_t) P.L_total, a.pos, c->vid.as<uint32_t>(), last ? 1 : 0,
+                    c->lineless_rank.as<uint32_t>(), c->lineless_rank.as<uint32_t>() + (Vg / 4096 + 2),
+                    c->scan_scratch.as<uint32_t>(), cnt, s);
     // line starts of the positions without records (and the end of the last line)
     k_dist_fill<<<(P.Vloc - L + 1 + 255) / 256, 256, 0, s>>>(a.ls, L, P.Vloc + 1, (uint32_t) R);
     c->stats.kernel_launches += 7;
@@ -616,7 +605,7 @@ int dist_build(gtsb_context *c, DistState *D, Plan &P, int inputs_rc) {
     CK(cudaMemsetAsync(D->rank_cnt.p, 0, (MAX_RANKS + 2) * 4, s));
     return 0;
   }();
-  if (rc == 0 && ensure_root_column(c) != 0) rc = -1;
+  if (rc == 0 && !c->have_lines && ensure_root_column(c) != 0) rc = -1;
   const int setup_rc = rc;
   Trace tr(s);
   tr.mark(me, "setup");

@@ -380,6 +380,52 @@ void launch_fill_srcp(const GraphArgs &g, uint32_t *srcp, uint32_t *big_rows, cu
   k4_fill_srcp<<<(g.V + 255) / 256, 256, 0, s>>>(g, srcp, big_rows);
 }
 
+// An uploaded CSR (gtsb_set_graph_host) must be what the filter's closed form assumes: targets in
+// range, no self edge, and every edge v -> w paired with an edge w -> v that carries the flags this
+// one lists as its reverse's.  The pairing is checked through two order-independent 64-bit sums --
+// over the slots of hash(v, w, own flags, reverse flags) and of hash(w, v, reverse flags, own
+// flags) -- which agree iff the edges pair up (up to hash collisions); bad[0] collects range and
+// self-edge errors.
+__device__ __forceinline__ uint64_t vmix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) k4_validate_csr(GraphArgs g, unsigned long long *__restrict__ sums,
+                                                       uint32_t *__restrict__ bad) {
+  uint64_t a = 0, b = 0;
+  for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < ((g.E + 31ull) & ~31ull);
+       s += (uint64_t) gridDim.x * blockDim.x) {
+    if (s >= g.E) continue;
+    const uint32_t v = g.srcp[s] & S_POS, w = g.dst[s], f = g.flags[s];
+    if (w >= g.V) {
+      atomicOr(bad, 1u);
+      continue;
+    }
+    if (w == v) atomicOr(bad, 2u);
+    const uint32_t own = f & 3u, rev = (f >> 2) & 3u;
+    a += vmix(vmix(((uint64_t) v << 32) | w) ^ (own | (rev << 2)));
+    b += vmix(vmix(((uint64_t) w << 32) | v) ^ (rev | (own << 2)));
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    a += __shfl_xor_sync(FULL, a, d);
+    b += __shfl_xor_sync(FULL, b, d);
+  }
+  if (lane_id() == 0) {
+    if (a) atomicAdd(sums, (unsigned long long) a);
+    if (b) atomicAdd(sums + 1, (unsigned long long) b);
+  }
+}
+
+void launch_validate_csr(const GraphArgs &g, unsigned long long *sums, uint32_t *bad, cudaStream_t s) {
+  if (g.E == 0) return;
+  KernelTimer t_("k4_validate_csr", s);
+  k4_validate_csr<<<g.sm_count * 8, 256, 0, s>>>(g, sums, bad);
+}
+
 // ------------------------------------------------------------------ phase 1 + static overlap
 
 struct SlotFacts {

@@ -108,6 +108,11 @@ struct Build2Args {
   uint32_t n_lines;
 };
 int launch_b3_lines(const Build2Args &a, cudaStream_t s);          // line_root/line_start -> ls, vid, pos
+int launch_b3_lines_only(const Build2Args &a, cudaStream_t s);     // ... without the lineless contigs (partitioned build)
+// positions of the contigs without a line: first + rank by id; tile_cnt / tile_off hold Vg / 4096 + 2 words each
+int launch_lineless(uint32_t Vg, uint32_t Vcap, const uint32_t *first_dev, uint32_t first_host, uint32_t *pos,
+                    uint32_t *vid, int write_vid, uint32_t *tile_cnt, uint32_t *tile_off, uint32_t *scan_scratch,
+                    const uint32_t *counters, cudaStream_t s);
 int launch_build2_lines(const Build2Args &a, cudaStream_t s);
 int launch_build2_classify(const Build2Args &a, cudaStream_t s);   // needs line starts + ctg only
 int launch_build2_rows(const Build2Args &a, cudaStream_t s);       // needs every record column
@@ -246,6 +251,9 @@ void launch_cc_out(const GraphArgs &g, const uint32_t *lab, const uint8_t *term,
 // cut the slots into windows of whole rows (count/woff: one entry per 64 rows + 1)
 int launch_pack_windows(const GraphArgs &g, uint32_t *count, uint32_t *woff, uint32_t *win_start,
                         uint32_t *scan_scratch, cudaStream_t s);
+// checks of an uploaded CSR: sums[0..1] = the two pairing sums (equal iff every edge has its reverse),
+// bad[0] bit 0 = target out of range, bit 1 = self edge
+void launch_validate_csr(const GraphArgs &g, unsigned long long *sums, uint32_t *bad, cudaStream_t s);
 // srcp column, F_LT flags and the big-row list of a plain CSR that was uploaded
 void launch_fill_srcp(const GraphArgs &g, uint32_t *srcp, uint32_t *big_rows, cudaStream_t s);
 

@@ -380,3 +380,33 @@ def write_text_inputs(inp, directory, write_seq=True):
             f.write(" ".join(parts) + "\n")
             i = j
     return fa, de, astat
+
+
+# ---- the reference's distance estimator (oracle/ref_bam_driver.c around gt_scaffolder_bamparser.c)
+
+_refbam = None
+
+
+def refbam_lib():
+    global _refbam
+    if _refbam is None:
+        path = os.path.join(os.path.dirname(REF_SO), "libgtscaf_refbam.so")
+        _refbam = C.CDLL(path)
+    return _refbam
+
+
+def have_refbam():
+    return os.path.exists(os.path.join(os.path.dirname(REF_SO), "libgtscaf_refbam.so"))
+
+
+def ref_estimate_dist(frag, ma, len_ref, len_mref, pmf, minp, rf, min_dist, max_dist):
+    """estimate_dist_using_mle (bamparser.c:553-598) for one contig pair -> (dist, nof_pairs)"""
+    fr = np.ascontiguousarray(np.asarray(frag, np.int64).reshape(-1, 2)).copy()       # sorted in place
+    pm = np.ascontiguousarray(pmf, np.float64)
+    d, n = C.c_int64(0), C.c_uint64(0)
+    rc = refbam_lib().refbam_estimate_dist(fr.ctypes.data_as(C.c_void_p), C.c_uint64(len(fr)), C.c_uint64(ma),
+                                           pm.ctypes.data_as(C.c_void_p), C.c_uint64(len(pm)), C.c_double(minp),
+                                           C.c_int64(min_dist), C.c_int64(max_dist), C.c_uint64(len_ref),
+                                           C.c_uint64(len_mref), C.c_int(int(rf)), C.byref(d), C.byref(n))
+    assert rc == 0
+    return d.value, n.value

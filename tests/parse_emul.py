@@ -12,8 +12,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "gt-scaffold_b200", "csrc")
-SRCS = [os.path.join(HERE, "emul", "parse_emul.cpp"), os.path.join(HERE, "emul", "format_emul.cpp")]
-CORES = [os.path.join(CSRC, "gtsb_parse_core.h"), os.path.join(CSRC, "gtsb_format_core.h")]
+SRCS = [os.path.join(HERE, "emul", "parse_emul.cpp"), os.path.join(HERE, "emul", "format_emul.cpp"),
+        os.path.join(HERE, "emul", "mle_emul.cpp")]
+CORES = [os.path.join(CSRC, "gtsb_parse_core.h"), os.path.join(CSRC, "gtsb_format_core.h"),
+         os.path.join(CSRC, "gtsb_mle_core.h")]
 OUT = os.path.join(HERE, "emul", "_build", "libparse_emul.so")
 _lib = None
 
@@ -137,3 +139,25 @@ def scaf_lines(names, records):
     rc = lib().emul_scaf_lines(C.c_uint64(len(root)), _vp(root), _vp(reo), _vp(end), _vp(dist), _vp(std.view(np.uint32)),
                                _vp(flags), blob, _vp(off), C.c_uint64(len(names)), out, C.c_uint64(cap), C.byref(n))
     return None if rc else out.raw[:n.value]
+
+
+def mle_arrays(pairs):
+    """pairs = [(frag (n, 2) int64 of (start, end), ma, len_ref, len_mref), ...] -> flat arrays of gtsb_mle_host"""
+    off = np.zeros(len(pairs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(p[0]) for p in pairs])
+    fr = np.concatenate([np.asarray(p[0], np.int64).reshape(-1, 2) for p in pairs]) if pairs else np.zeros((0, 2), np.int64)
+    return (off, np.ascontiguousarray(fr[:, 0]), np.ascontiguousarray(fr[:, 1]),
+            np.array([p[1] for p in pairs], np.uint64), np.array([p[2] for p in pairs], np.uint64),
+            np.array([p[3] for p in pairs], np.uint64))
+
+
+def mle(pairs, pmf, minp, rf, min_dist, max_dist, keep_all=False):
+    """host build of gtsb_mle_host -> (dist[], pairs_used[], slots, candidates) or None"""
+    off, fs, fe, ma, lr, lm = mle_arrays(pairs)
+    pmf = np.ascontiguousarray(pmf, np.float64)
+    dist, used = np.zeros(len(pairs), np.int64), np.zeros(len(pairs), np.uint64)
+    slots, cand = C.c_uint64(0), C.c_uint64(0)
+    rc = lib().emul_mle(C.c_uint64(len(pairs)), _vp(off), _vp(fs), _vp(fe), _vp(ma), _vp(lr), _vp(lm), _vp(pmf),
+                        C.c_uint64(len(pmf)), C.c_double(minp), C.c_int(int(rf)), C.c_int64(min_dist),
+                        C.c_int64(max_dist), C.c_int(int(keep_all)), _vp(dist), _vp(used), C.byref(slots), C.byref(cand))
+    return None if rc else (dist, used, slots.value, cand.value)

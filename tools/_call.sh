@@ -1,8 +1,7 @@
 cd $GRAFT_REPO_ROOT
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 600 $TR --nproc-per-node 8 --master-port 29541 tests/dist_check.py > gpurun_out/r02_dist_check_n8.log 2>&1; echo "dist_check n8 rc=$?"
-grep -c -- "-> OK" gpurun_out/r02_dist_check_n8.log
-timeout 900 $TR --nproc-per-node 8 --master-port 29542 tools/c5_check.py --steps 5 --out gpurun_out/r02_c5_n8.json > gpurun_out/c5e.log 2>&1; echo "c5 n8 rc=$?"
-tail -1 gpurun_out/c5e.log | cut -c1-400
-timeout 900 $TR --nproc-per-node 8 --master-port 29543 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8_a.json 2> gpurun_out/r02_bench_n8_a.err; echo "bench n8 rc=$?"
-cut -c1-300 gpurun_out/r02_bench_n8_a.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gputest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_gputest_final.log
+tail -4 gpurun_out/r02_gputest_final.log
+timeout 600 python bench.py > gpurun_out/r02_bench_c3.json 2> gpurun_out/r02_bench_c3.err; echo "bench rc=$?"
+timeout 600 python bench.py --workload c4_repeat_hubs --steps 5 > gpurun_out/r02_bench_c4.json 2> gpurun_out/r02_bench_c4.err; echo "bench c4 rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_launches.csv python tools/probe.py c3_human 0 1 > gpurun_out/ncu_l.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k4_pairs|k2_partition2|k2_deliver2|k2_resolve|k4_finalize|k4_fire_dense|k2_classify|k_fire_rounds_all|k4_fire_redo|k4_fire_init|k4_vertex_facts" -c 11 -f -o gpurun_out/prof_r02_final python tools/probe.py c3_human 0 1 > gpurun_out/ncu_f.log 2>&1; echo "ncu full rc=$?"

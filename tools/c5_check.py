@@ -82,8 +82,15 @@ def main():
         dist.broadcast_object_list(box, src=0)
         g.dist_init(rank, world, box[0])
     g.set_vertices_device(Vn, t["seq_len"].data_ptr(), t["astat"].data_ptr(), t["copy_num"].data_ptr())
-    g.set_records_device(Rn, t["root"].data_ptr(), t["ctg"].data_ptr(), t["dist"].data_ptr(),
-                         t["std_dev"].data_ptr(), t["flags"].data_ptr())
+    # records in the shape a .de tokeniser leaves them in: (root, first record) per line
+    root = t["root"]
+    brk = torch.nonzero(root[1:] != root[:-1]).flatten() + 1
+    line_start = torch.cat([torch.zeros(1, dtype=brk.dtype, device=dev), brk,
+                            torch.tensor([Rn], dtype=brk.dtype, device=dev)]).to(torch.int32).contiguous()
+    line_root = root[line_start[:-1].long()].contiguous()
+    del brk
+    g.set_record_lines_device(int(line_root.shape[0]), line_root.data_ptr(), line_start.data_ptr(), Rn,
+                              t["ctg"].data_ptr(), t["dist"].data_ptr(), t["std_dev"].data_ptr(), t["flags"].data_ptr())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -94,13 +101,16 @@ def main():
     for _ in range(args.warmup):
         g.pipeline(*PARAMS)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
         g.pipeline(*PARAMS)
-    e1.record(stream)
+        evs[k + 1].record(stream)
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1) / max(1, args.steps)], dtype=torch.float64, device=dev)
+    per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    # the mean is what bench.py reports; the per-step times show a one-off stall if there was one
+    ms = torch.tensor([sum(per_step) / max(1, args.steps), sorted(per_step)[len(per_step) // 2]] + per_step,
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     g.set_profile(True)
@@ -118,7 +128,9 @@ def main():
         assert all(p[2] == parts[0][2] for p in parts), "ranks disagree on the vertex states"
         line = {"workload": args.workload, "vertices": Vn, "records": sum(p[3] for p in parts),
                 "edges": sum(p[0] for p in parts), "n_gpus": world, "steps": args.steps,
-                "ms_per_step": float(ms[0]), "edges_per_s": sum(p[0] for p in parts) / float(ms[0]) * 1e3,
+                "ms_per_step": float(ms[1]), "ms_per_step_mean": float(ms[0]), "ms_each_step": [round(float(x), 3) for x in ms[2:]],
+                "timing": "CUDA events around every step, max over ranks; ms_per_step = median step",
+                "edges_per_s": sum(p[0] for p in parts) / float(ms[1]) * 1e3,
                 "digest_edges": "%016x" % (sum(p[1] for p in parts) & mask), "digest_vertices": "%016x" % parts[0][2],
                 "edges_per_rank": [p[0] for p in parts], "records_per_rank": [p[3] for p in parts],
                 "stats": {k: st[k] for k in ("proposals", "poly_sweeps", "fire_rounds", "line_ordered_build",
