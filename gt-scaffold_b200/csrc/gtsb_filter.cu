@@ -612,6 +612,72 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k4_pairs3(FilterArgs a) {
 // block per big row; per-block scratch: copy_num[max_deg] f32, low[max_deg] u32, mark[max_deg] u8.
 // A pair can only propose if cn1 + cn2 < cncutoff, so one of the two has cn < cncutoff / 2:
 // only the pairs with at least one such "low" slot are evaluated (|low| x d instead of d^2 / 2).
+constexpr uint32_t MID_ROW = 256;     // big rows up to this many slots take a warp, longer ones a block
+
+// warp per row, scratch in shared memory: most rows above BIG_ROW are only a little above it
+// (power-law degrees), and a 512-thread block with three barriers per row idles on them
+__global__ void __launch_bounds__(256) k4_pairs_mid(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  __shared__ float s_cn[8][MID_ROW];
+  __shared__ uint16_t s_low[8][MID_ROW];
+  __shared__ uint8_t s_mark[8][MID_ROW];
+  __shared__ uint32_t s_nl[8];
+  const uint32_t wi = threadIdx.x >> 5, lane = lane_id();
+  float *cn = s_cn[wi];
+  uint16_t *low = s_low[wi];
+  uint8_t *mark = s_mark[wi];
+  const float half = __fmul_rn(a.cncutoff, 0.5f);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t li = warp; li < g.n_big_rows; li += nwarps) {
+    const uint32_t p = g.big_rows[li];
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    if (d > MID_ROW || (a.vinfo[p].y & VI_MARKED)) continue;          // warp-uniform
+    if (lane == 0) s_nl[wi] = 0;
+    __syncwarp();
+    for (uint32_t k = lane; k < d; k += 32u) {
+      const float c = __uint_as_float(a.vinfo[g.dst[r0 + k]].x);
+      cn[k] = c;
+      mark[k] = 0;
+      if (!(c > half + fabsf(half) * 1e-6f + 1e-30f)) low[atomicAdd(&s_nl[wi], 1u)] = (uint16_t) k;
+    }
+    __syncwarp();
+    const uint32_t nlow = s_nl[wi];
+    for (uint32_t x = 0; x < nlow; x++) {
+      const uint32_t i = low[x];
+      const int32_t di = g.dist[r0 + i];
+      const float si = g.std_dev[r0 + i], ci = cn[i];
+      const uint32_t fi = g.flags[r0 + i] & F_SENSE;
+      for (uint32_t j = lane; j < d; j += 32u) {
+        if (j == i || (g.flags[r0 + j] & F_SENSE) != fi) continue;
+        const float cj = cn[j];
+        if (!(__fadd_rn(ci, cj) < a.cncutoff)) continue;
+        // check_mark_polymorphic, algorithms.c:232-238 (edge1 = earlier adjacency slot)
+        const bool i_first = i < j;
+        const int32_t dj = g.dist[r0 + j];
+        const float sj = g.std_dev[r0 + j];
+        const bool amb = i_first ? ambiguous_order(di, si, dj, sj, a.ambig) : ambiguous_order(dj, sj, di, si, a.ambig);
+        if (!amb) continue;
+        const float c1 = i_first ? ci : cj, c2 = i_first ? cj : ci;
+        const uint32_t k1 = i_first ? i : j, k2 = i_first ? j : i;
+        mark[c1 < c2 ? k1 : k2] = 1;
+      }
+    }
+    __syncwarp();
+    for (uint32_t k0 = 0; k0 < d; k0 += 32u) {
+      const uint32_t k = k0 + lane;
+      uint32_t t = 0;
+      bool emit = false;
+      if (k < d && mark[k]) {
+        t = g.dst[r0 + k];
+        emit = !(a.vinfo[t].y & VI_MARKED);
+      }
+      warp_append2(emit, make_uint2(p, t), a.proposals, a.proposals_cap, &g.counters[CNT_PROPOSALS],
+                   &g.counters[CNT_OVERFLOW]);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(512) k4_pairs_big(FilterArgs a) {
   const GraphArgs &g = a.g;
   __shared__ uint32_t s_nlow;
@@ -623,6 +689,7 @@ __global__ void __launch_bounds__(512) k4_pairs_big(FilterArgs a) {
     const uint32_t p = g.big_rows[li];
     if (a.vinfo[p].y & VI_MARKED) continue;                        // block-uniform
     const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    if (d <= MID_ROW) continue;                                    // k4_pairs_mid's
     if (threadIdx.x == 0) s_nlow = 0;
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
@@ -692,7 +759,10 @@ void launch_pairs(const FilterArgs &a, cudaStream_t s) {
   }
   if (a.g.n_big_rows) {
     KernelTimer t_("k4_pairs_big", s);
-    k4_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
+    uint32_t mid_blocks = (a.g.n_big_rows + 7) / 8;
+    if (mid_blocks > (uint32_t) a.g.sm_count * 8) mid_blocks = (uint32_t) a.g.sm_count * 8;
+    k4_pairs_mid<<<mid_blocks, 256, 0, s>>>(a);
+    if (a.g.max_deg > MID_ROW) k4_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
   }
 }
 
@@ -1086,13 +1156,32 @@ __global__ void __launch_bounds__(256) k_fire_rounds_all(FilterArgs a, uint32_t 
       const uint32_t idx = base + tid;
       bool again = false;
       uint32_t p = 0;
+      uint32_t r0 = 0, d = 0, und = 0;
+      uint8_t st = FS_DECIDED_ALL;
       if (idx < n_in) {
         p = win[idx];
-        uint8_t st = fstat[p];
-        const uint32_t und = (~(uint32_t) st >> 2) & 3u;
-        uint32_t res = 0;
+        st = fstat[p];
+        und = (~(uint32_t) st >> 2) & 3u;
         const uint32_t rl = p - g.row_base;
-        for (uint32_t s = g.row_ptr[rl]; s < g.row_ptr[rl + 1]; s++) res |= fire_probe(g, fstat, s, und);
+        r0 = g.row_ptr[rl];
+        d = g.row_ptr[rl + 1] - r0;
+      }
+      // rows of at most BIG_ROW slots: one thread each; longer rows (hubs): the whole warp, one after the other
+      const bool big = d > BIG_ROW;
+      uint32_t res = 0;
+      if (!big)
+        for (uint32_t s = r0; s < r0 + d; s++) res |= fire_probe(g, fstat, s, und);
+      unsigned todo = __ballot_sync(FULL, big);
+      while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t rr = __shfl_sync(FULL, r0, l), dd = __shfl_sync(FULL, d, l), uu = __shfl_sync(FULL, und, l);
+        uint32_t part = 0;
+        for (uint32_t k = lane_id(); k < dd; k += 32u) part |= fire_probe(g, fstat, rr + k, uu);
+        part = __reduce_or_sync(FULL, part);
+        if ((int) lane_id() == l) res = part;
+      }
+      if (idx < n_in) {
         st = fire_decide(st, und, res);
         a.fstat[p] = st;
         again = (st & FS_DECIDED_ALL) != FS_DECIDED_ALL;
