@@ -793,6 +793,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
     s_match[at] = NO_MATCH;
   }
   // row offsets
+  uint32_t my_max = 0;
   for (uint32_t j = threadIdx.x; j < g.nlines; j += blockDim.x) {
     const uint32_t p = g.p0 + j;
     const uint32_t row0 = s_bp[j] + s_k0[j], deg = s_bp[j + 1] + s_k0[j + 1] - row0;
@@ -801,11 +802,12 @@ __global__ void __launch_bounds__(SEG_THREADS) k2_resolve(Build2Args a) {
       a.row_ptr[a.V] = row0 + deg;
       a.counters[CNT_EDGES] = row0 + deg;
     }
-    if (deg > BIG_ROW) {
-      atomicMax(&a.counters[CNT_MAX_DEG], deg);
-      a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = a.pos_base + p;
-    }
+    my_max = max(my_max, deg);
+    if (deg > BIG_ROW) a.big_rows[atomicAdd(&a.counters[CNT_BIG_ROWS], 1u)] = a.pos_base + p;
   }
+  // longest row (gtsb_stats.max_degree; sizes the hub kernels' scratch): one atomic per warp that holds lines
+  my_max = __reduce_max_sync(0xffffffffu, my_max);
+  if (lane_id() == 0 && my_max) atomicMax(&a.counters[CNT_MAX_DEG], my_max);
   __syncthreads();
   // own records: creators write their slot (rank among the line's creators from
   // a block scan), down records find their mail

@@ -202,7 +202,12 @@ int gtsb_pipeline(gtsb_context *ctx, float copy_num_cutoff, float astat_cutoff, 
    without a line: last rank).  Vertex states come back complete on every rank;
    edges stay with their rank (gtsb_get_edges).  The exchanges are NCCL over
    NVLink; the 128-byte id from rank 0 has to reach every rank by the caller's
-   own means (MPI, torch.distributed, a file). */
+   own means (MPI, torch.distributed, a file).
+   The partitioned build is the line-ordered one only: a contig heading lines on two ranks, a
+   line of more than 64 records, or a link listed only on the later of its two lines fails
+   gtsb_pipeline on EVERY rank with the reason mask in the message (a single device rebuilds such
+   input with its general sort-based path; the partitioned build has none).  An error on one
+   rank -- also an allocation failure -- reaches all ranks at the next agreed exchange. */
 int gtsb_dist_unique_id(void *id128);
 int gtsb_dist_init(gtsb_context *ctx, int rank, int world, const void *id128);
 /* this device's edges with the reference's vertex ids: eid = index into

@@ -606,7 +606,7 @@ static const GtScaffolderGraphEdge *reverse_edge(const GtScaffolderGraph *graph,
    stderr if the graph is outside what the device path represents */
 static int graph_flatten(const GtScaffolderGraph *graph, B200Flat *f, const char *where)
 {
-  GtUword v, k;
+  GtUword v, k, *stamp;
   uint64_t s = 0;
   memset(f, 0, sizeof (*f));
   f->V = graph->nof_vertices;
@@ -623,19 +623,34 @@ static int graph_flatten(const GtScaffolderGraph *graph, B200Flat *f, const char
   f->flags = gt_malloc(f->E + 1);
   f->estate = gt_malloc(f->E + 1);
   f->slot_edge = gt_malloc((f->E + 1) * sizeof (*f->slot_edge));
+  stamp = gt_calloc(graph->nof_vertices + 1, sizeof (*stamp));
   for (v = 0; v < graph->nof_vertices; v++) {
     const GtScaffolderGraphVertex *vx = graph->vertices + v;
     f->row_ptr[v] = (uint32_t) s;
     for (k = 0; k < vx->nof_edges; k++, s++) {
       GtScaffolderGraphEdge *e = vx->edges[k];
       const GtScaffolderGraphEdge *r = reverse_edge(graph, e);
+      const GtUword end_id = (GtUword) (e->end - graph->vertices);
+      /* two edges from one vertex to the same end: the device's closed form assumes ONE edge per
+         pair and direction (the reference's constructor never creates a second, parser.c:357-379) */
+      if (end_id < graph->nof_vertices) {
+        if (stamp[end_id] == v + 1) {
+          fprintf(stderr, "gt_scaffolder (B200): %s: two edges from one vertex to the same end; the device "
+                          "path handles the graphs gt_scaffolder_graph_new_from_file builds\n", where);
+          gt_free(stamp);
+          return -1;
+        }
+        stamp[end_id] = v + 1;
+      }
       if (r == NULL || e->start != vx) {
         fprintf(stderr, "gt_scaffolder (B200): %s: edge without a reverse edge; the device path "
                         "handles the graphs gt_scaffolder_graph_new_from_file builds\n", where);
+        gt_free(stamp);
         return -1;
       }
       if (e->dist > INT32_MAX || e->dist < INT32_MIN) {
         fprintf(stderr, "gt_scaffolder (B200): %s: distance outside 32 bits\n", where);
+        gt_free(stamp);
         return -1;
       }
       f->dst[s] = (uint32_t) (e->end - graph->vertices);
@@ -648,6 +663,7 @@ static int graph_flatten(const GtScaffolderGraph *graph, B200Flat *f, const char
     }
   }
   f->row_ptr[f->V] = (uint32_t) s;
+  gt_free(stamp);
   return 0;
 }
 

@@ -440,3 +440,14 @@ def test_more_proposals_than_the_list_was_sized_for(pkg, synth):
     inp = synth.generate("c3_human", V=120000, seed=21)
     st = _run_both(pkg, inp, 0.0, -1e9, True, -0.5, 9.0, 3000, stagewise=False)
     assert st["proposals"] > st["nof_edges"] // 4 + 65536, st
+
+
+@pytest.mark.gpu
+def test_stats_report_the_longest_row_on_both_build_paths(pkg, synth):
+    inp = synth.generate("c2_bacterial", V=30000, seed=9)
+    for force_general in (False, True):
+        g = pkg.ScaffoldGraphB200.new_from_records(inp, force_general=force_general)
+        st, r = g.stats(), g.result()
+        assert st["line_ordered_build"] == (0 if force_general else 1)
+        assert st["max_degree"] == int(np.diff(r["row_ptr"].astype(np.int64)).max()), st
+        g.close()
