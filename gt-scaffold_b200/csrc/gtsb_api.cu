@@ -540,6 +540,9 @@ int do_build(gtsb_context *c) {
   if (c->h_counters[CNT_ERROR] & 2u)
     return fail(c, "gtsb_build: self link (root == ctg) is not supported (the reference would "
                    "create two parallel self edges, parser.c:374-377)");
+  if (c->h_counters[CNT_ERROR] & 16u)
+    return fail(c, "gtsb_build: the hub buckets of the general build need more than 2^32 scratch entries "
+                   "(about 5e8 records of hub vertices); split the input");
   const uint32_t nlarge = c->h_counters[CNT_LARGE_BUCKETS];
   c->stats.large_buckets = nlarge;
   if (nlarge) {
@@ -610,6 +613,24 @@ int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a
   if (c->n_big_rows) {
     if (a.big_blocks > c->n_big_rows) a.big_blocks = c->n_big_rows;
     ENSURE(c->big_scratch, (size_t) a.big_blocks * c->max_deg * BIG_SCRATCH_STRIDE);
+  }
+  static const int split_hubs = [] {
+    const char *e = getenv("GTSB_HUBS");                 // 1: pairs of the hub rows split over the grid (dev switch)
+    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
+  }();
+  if (split_hubs && c->world == 1 && c->n_big_rows && c->max_deg > HUB_ROW) {
+    const uint64_t cap = E / HUB_LCH + c->n_big_rows + 1;
+    ENSURE(c->hub_cn, (E + 1) * 4);
+    ENSURE(c->hub_low, (E + 1) * 4);
+    ENSURE(c->hub_mark, E + 1);
+    ENSURE(c->hub_nlow, ((uint64_t) c->n_big_rows + 1) * 4);
+    ENSURE(c->hub_items, cap * sizeof(uint2));
+    a.hub_cn = c->hub_cn.as<float>();
+    a.hub_low = c->hub_low.as<uint32_t>();
+    a.hub_mark = c->hub_mark.as<uint8_t>();
+    a.hub_nlow = c->hub_nlow.as<uint32_t>();
+    a.hub_items = c->hub_items.as<uint2>();
+    a.hub_items_cap = (uint32_t) (cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
   }
   a.g = graph_args(c);
   a.proposals = c->proposals.as<uint2>();
@@ -834,10 +855,19 @@ int gtsb_create(gtsb_context **out, int device) {
         cudaGetLastError();
       }
     }
-    if (getenv("GTSB_TRACE") != nullptr)
-      fprintf(stderr, "[gtsb] L2 %d MB, persisting max %d MB, window max %d MB, pin %zu MB\n",
+    // dev switch: how much the L2 fetches from HBM on a miss (32 / 64 / 128 bytes; a hint, device-wide).
+    // The per-vertex gathers use 4-8 bytes of every sector they fetch.
+    const char *fg = getenv("GTSB_L2_FETCH");
+    if (fg != nullptr && atoi(fg) > 0 &&
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(fg)) != cudaSuccess)
+      cudaGetLastError();
+    if (getenv("GTSB_TRACE") != nullptr) {
+      size_t gran = 0;
+      if (cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity) != cudaSuccess) cudaGetLastError();
+      fprintf(stderr, "[gtsb] L2 %d MB, persisting max %d MB, window max %d MB, pin %zu MB, fetch granularity %zu B\n",
               prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20,
-              c->l2_persist_max >> 20);
+              c->l2_persist_max >> 20, gran);
+    }
   }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -864,7 +894,7 @@ void gtsb_destroy(gtsb_context *c) {
                     &c->cursor, &c->deg, &c->krank, &c->scan_scratch, &c->entries, &c->bwin,
                     &c->creator_flag, &c->large_list, &c->big_rows, &c->counters, &c->lscratch,
                     &c->ltag, &c->proposals, &c->poly_cur, &c->poly_new, &c->gbits, &c->fstat,
-                    &c->work_a, &c->work_b, &c->big_scratch, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->wcount, &c->woff, &c->win_start, &c->vid, &c->pos, &c->ls,
+                    &c->work_a, &c->work_b, &c->big_scratch, &c->hub_cn, &c->hub_low, &c->hub_mark, &c->hub_nlow, &c->hub_items, &c->vinfo, &c->vres, &c->dirty, &c->srcp, &c->pc, &c->nown, &c->k0, &c->wcount, &c->woff, &c->win_start, &c->vid, &c->pos, &c->ls,
                     &c->tile_cnt, &c->tile_off, &c->rf, &c->cnt_in, &c->bptr2, &c->cursor2,
                     &c->tmp_ent, &c->tmp_dest, &c->tmp_cursor, &c->bucket, &c->bucket_line, &c->line_root, &c->line_start,
                     &c->corrections, &c->lineless_flag, &c->lineless_rank, &c->x_row_ptr, &c->x_dst,

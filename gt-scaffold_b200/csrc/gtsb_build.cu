@@ -20,13 +20,16 @@
 //     vertex (graph.c:166-167);
 //   * both directed edges of a pair are decided from the same group, so each
 //     CSR slot also learns the flags of its reverse edge (needed by the filter).
+#include <stdlib.h>
 #include "gtsb_common.cuh"
 #include "gtsb_scan.cuh"
 #include "gtsb_kernels.h"
+#include "gtsb_sort_core.h"
 
 namespace gtsb {
 
 constexpr int RESOLVE_SMALL_MAX = 64;   // bucket entries handled by one thread
+static_assert(gtsbs::SORT_OTHER_MASK == E_OTHER_MASK, "sort key mask");
 
 // ------------------------------------------------------------ histogram
 
@@ -136,7 +139,9 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
 }
 
-// thread per vertex; buckets above RESOLVE_SMALL_MAX are queued for the block path
+// thread per vertex; buckets above MAXN entries are queued for the block path.  A warp lasts as
+// long as its largest bucket's insertion sort (quadratic), so the bound is also a bound on divergence.
+template <int MAXN>
 __global__ void __launch_bounds__(128) k_resolve_small(
     uint32_t V, const uint32_t *__restrict__ bptr, uint4 *__restrict__ entries,
     uint32_t *__restrict__ bwin, uint32_t *__restrict__ deg, uint8_t *__restrict__ creator_flag,
@@ -147,10 +152,11 @@ __global__ void __launch_bounds__(128) k_resolve_small(
     b0 = bptr[v];
     n = bptr[v + 1] - b0;
   }
-  const bool large = n > RESOLVE_SMALL_MAX;
+  const bool large = n > (uint32_t) MAXN;
   if (large) {  // queue for the block path: (vertex, scratch offset)
     const uint32_t pad = next_pow2(n);
     const uint32_t off = atomicAdd(&counters[CNT_LARGE_PAD], 2u * pad);
+    if (n > (1u << 30) || off + 2u * pad < off) atomicOr(&counters[CNT_ERROR], 16u);   // 32-bit scratch offsets wrapped
     const uint32_t slot = atomicAdd(&counters[CNT_LARGE_BUCKETS], 1u);
     large_list[slot] = make_uint2(v, off);
   }
@@ -159,8 +165,8 @@ __global__ void __launch_bounds__(128) k_resolve_small(
     deg[v] = 0;
     return;
   }
-  uint4 e[RESOLVE_SMALL_MAX];
-  uint32_t w[RESOLVE_SMALL_MAX];
+  uint4 e[MAXN];
+  uint32_t w[MAXN];
   for (uint32_t i = 0; i < n; i++) e[i] = entries[b0 + i];
   for (uint32_t i = 1; i < n; i++) {                // insertion sort by (other, idx)
     const uint4 key = e[i];
@@ -283,6 +289,66 @@ __global__ void __launch_bounds__(256) k_resolve_large(
   }
 }
 
+// The same resolution with both sorts blocked through shared memory (gtsb_sort_core.h): the
+// steps of the network whose partners lie inside a chunk of SORT_CHUNK entries run on chip, so a
+// hub of 10^4 edges makes 16 passes over its 512 KB of scratch instead of 120, and a bucket of up to
+// SORT_CHUNK entries is sorted without touching global memory in between.
+__global__ void __launch_bounds__(256) k_resolve_large2(
+    const uint32_t *__restrict__ bptr, uint4 *__restrict__ entries, uint32_t *__restrict__ bwin,
+    uint32_t *__restrict__ deg, uint8_t *__restrict__ creator_flag,
+    const uint2 *__restrict__ large_list, const uint32_t *__restrict__ counters,
+    uint4 *__restrict__ scratch, uint32_t *__restrict__ scratch_tag) {
+  __shared__ uint4 s_a[gtsbs::SORT_CHUNK];
+  __shared__ uint32_t s_t[gtsbs::SORT_CHUNK];
+  __shared__ uint32_t s_groups;
+  const uint32_t nlarge = counters[CNT_LARGE_BUCKETS];
+  for (uint32_t li = blockIdx.x; li < nlarge; li += gridDim.x) {
+    const uint32_t v = large_list[li].x, off = large_list[li].y;
+    const uint32_t b0 = bptr[v], n = bptr[v + 1] - b0;
+    const uint32_t P = next_pow2(n);
+    uint4 *A = scratch + off, *B = scratch + off + P;
+    uint32_t *T = scratch_tag + off;                 // P tags used
+    const uint4 inf = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) A[i] = i < n ? entries[b0 + i] : inf;
+    __syncthreads();
+    gtsbs::blocked_bitonic(A, nullptr, P, 0, s_a, s_t);
+    // group heads -> compact positions (chunked block scan)
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+      const uint32_t i = base + threadIdx.x;
+      bool head = false;
+      if (i < n) head = i == 0 || (A[i].y & E_OTHER_MASK) != (A[i - 1].y & E_OTHER_MASK);
+      uint32_t total;
+      const uint32_t pos = carry + block_excl_scan(head ? 1u : 0u, &total);
+      if (head) {
+        const uint32_t other = A[i].y & E_OTHER_MASK;
+        uint32_t j = i + 1;
+        while (j < n && (A[j].y & E_OTHER_MASK) == other) j++;
+        uint32_t win;
+        B[pos] = resolve_group([&](uint32_t k) { return A[k]; }, i, j, &win, creator_flag);
+        T[pos] = win;
+      }
+      carry += total;
+    }
+    if (threadIdx.x == 0) s_groups = carry;
+    __syncthreads();
+    const uint32_t g = s_groups;
+    const uint32_t P2 = next_pow2(g);
+    for (uint32_t i = g + threadIdx.x; i < P2; i += blockDim.x) {
+      B[i] = inf;
+      T[i] = 0;
+    }
+    __syncthreads();
+    gtsbs::blocked_bitonic(B, T, P2, 1, s_a, s_t);
+    for (uint32_t i = threadIdx.x; i < g; i += blockDim.x) {
+      entries[b0 + i] = B[i];
+      if (bwin != nullptr) bwin[b0 + i] = T[i];
+    }
+    if (threadIdx.x == 0) deg[v] = g;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------ emit CSR
 
 __device__ __forceinline__ void emit_slot(const uint4 e, uint32_t slot,
@@ -357,9 +423,16 @@ void launch_build_scatter_resolve(const BuildArgs &a, cudaStream_t s) {
   k_scatter_halfedges<<<grid_for(a.R, 256, a.sm_count * 16), 256, 0, s>>>(
       a.R, a.V, a.root, a.ctg, a.dist, a.std_dev, a.flags, a.bptr, a.cursor, a.entries); }
   KernelTimer t2_("k_resolve_small", s);
-  if (a.V)
-    k_resolve_small<<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
-                                                      a.creator_flag, a.large_list, a.counters);
+  static const int small32 = [] {
+    const char *e = getenv("GTSB_SMALL_MAX");            // 32: buckets of 33..64 entries take the block path too (dev switch)
+    return (e != nullptr && atoi(e) == 32) ? 1 : 0;
+  }();
+  if (a.V && small32)
+    k_resolve_small<32><<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
+                                                          a.creator_flag, a.large_list, a.counters);
+  else if (a.V)
+    k_resolve_small<RESOLVE_SMALL_MAX><<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
+                                                                         a.creator_flag, a.large_list, a.counters);
 }
 
 void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *scratch_tag,
@@ -367,8 +440,16 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
   if (nlarge == 0) return;
   uint32_t blocks = nlarge < (uint32_t) a.sm_count * 8 ? nlarge : (uint32_t) a.sm_count * 8;
   KernelTimer t_("k_resolve_large", s);
-  k_resolve_large<<<blocks, 256, 0, s>>>(a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
-                                         a.large_list, a.counters, scratch, scratch_tag);
+  static const int blocked = [] {
+    const char *e = getenv("GTSB_HUB_SORT");             // 1: sorts blocked through shared memory (dev switch)
+    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
+  }();
+  if (blocked)
+    k_resolve_large2<<<blocks, 256, 0, s>>>(a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
+                                            a.large_list, a.counters, scratch, scratch_tag);
+  else
+    k_resolve_large<<<blocks, 256, 0, s>>>(a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
+                                           a.large_list, a.counters, scratch, scratch_tag);
 }
 
 void launch_build_emit(const BuildArgs &a, cudaStream_t s) {

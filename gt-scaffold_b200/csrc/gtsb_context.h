@@ -70,6 +70,7 @@ struct gtsb_context {
       big_rows, counters, lscratch, ltag;
   // filter work
   DevBuf proposals, poly_cur, poly_new, gbits, fstat, work_a, work_b, big_scratch, vinfo, vres, vsum, dirty;
+  DevBuf hub_cn, hub_low, hub_mark, hub_nlow, hub_items;   // split pairs pass of the hub rows
   uint32_t n_big_rows = 0, max_deg = 0;
   // .de text on the device (gtsb_parse.cu)
   DevBuf p_names, p_name_off, p_slots, p_flags, p_text, p_chunk_cnt, p_chunk_off, p_line_end,

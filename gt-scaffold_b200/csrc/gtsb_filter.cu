@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k4_pairs3(FilterArgs a) {
 // block per big row; per-block scratch: copy_num[max_deg] f32, low[max_deg] u32, mark[max_deg] u8.
 // A pair can only propose if cn1 + cn2 < cncutoff, so one of the two has cn < cncutoff / 2:
 // only the pairs with at least one such "low" slot are evaluated (|low| x d instead of d^2 / 2).
-constexpr uint32_t MID_ROW = 256;     // big rows up to this many slots take a warp, longer ones a block
+constexpr uint32_t MID_ROW = HUB_ROW;  // big rows up to this many slots take a warp, longer ones a block (or the split pass)
 
 // warp per row, scratch in shared memory: most rows above BIG_ROW are only a little above it
 // (power-law degrees), and a 512-thread block with three barriers per row idles on them
@@ -738,6 +738,115 @@ __global__ void __launch_bounds__(512) k4_pairs_big(FilterArgs a) {
   }
 }
 
+// The pairs of the rows above HUB_ROW slots, split over the grid.  k4_pairs_big gives a row to one
+// block, and the work of a row grows with the square of its length (low-copy-number slots x all
+// slots): with 143 rows of 10^4 slots among 6.7 * 10^3 rows above 256 (config 4) the launch lasts as
+// long as the block that holds the most of them.  Here a row's work is cut into items of HUB_LCH
+// low slots each and the items of all rows are dealt to the blocks:
+//   k4_hub_prep   block per row: neighbour copy numbers by slot, the row's low list, its items
+//   k4_hub_pairs  block per item: the item's low slots staged in shared memory, every thread keeps
+//                 one slot j of the row in registers and meets the staged slots (byte marks; writers
+//                 of a mark all store 1)
+//   k4_hub_emit   block per row: marked slots -> proposals
+// Same pairs, same tests and the same proposals as k4_pairs_big (a pair of two low slots is met
+// from both sides there as well).
+__global__ void __launch_bounds__(256) k4_hub_prep(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  __shared__ uint32_t s_nlow, s_base;
+  const float half = __fmul_rn(a.cncutoff, 0.5f);
+  for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
+    const uint32_t p = g.big_rows[li];
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    if (d <= MID_ROW || (a.vinfo[p].y & VI_MARKED)) continue;          // block-uniform
+    if (threadIdx.x == 0) s_nlow = 0;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
+      const float c = __uint_as_float(a.vinfo[g.dst[r0 + k]].x);
+      a.hub_cn[r0 + k] = c;
+      a.hub_mark[r0 + k] = 0;
+      // the same margin as k4_pairs_big: the exact test decides in k4_hub_pairs
+      if (!(c > half + fabsf(half) * 1e-6f + 1e-30f)) a.hub_low[r0 + atomicAdd(&s_nlow, 1u)] = k;
+    }
+    __syncthreads();
+    const uint32_t nlow = s_nlow, nitems = (nlow + HUB_LCH - 1u) / HUB_LCH;
+    if (threadIdx.x == 0) {
+      a.hub_nlow[li] = nlow;
+      s_base = nitems ? atomicAdd(&g.counters[CNT_HUB_ITEMS], nitems) : 0u;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    for (uint32_t x = threadIdx.x; x < nitems; x += blockDim.x)
+      if (base + x < a.hub_items_cap) a.hub_items[base + x] = make_uint2(li, x);
+    __syncthreads();                                                   // s_nlow / s_base: next row
+  }
+}
+
+__global__ void __launch_bounds__(256) k4_hub_pairs(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  __shared__ uint32_t s_i[HUB_LCH], s_fi[HUB_LCH];
+  __shared__ int32_t s_di[HUB_LCH];
+  __shared__ float s_si[HUB_LCH], s_ci[HUB_LCH];
+  const uint32_t n_items = min(g.counters[CNT_HUB_ITEMS], a.hub_items_cap);
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const uint2 item = a.hub_items[it];
+    const uint32_t p = g.big_rows[item.x];
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    const uint32_t nlow = a.hub_nlow[item.x];
+    const uint32_t x0 = item.y * HUB_LCH;
+    const uint32_t nx = nlow - x0 < HUB_LCH ? nlow - x0 : HUB_LCH;
+    __syncthreads();                                                   // the previous item's staged slots are done with
+    if (threadIdx.x < nx) {
+      const uint32_t i = a.hub_low[r0 + x0 + threadIdx.x];
+      s_i[threadIdx.x] = i;
+      s_di[threadIdx.x] = g.dist[r0 + i];
+      s_si[threadIdx.x] = g.std_dev[r0 + i];
+      s_ci[threadIdx.x] = a.hub_cn[r0 + i];
+      s_fi[threadIdx.x] = g.flags[r0 + i] & F_SENSE;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+      const uint32_t fj = g.flags[r0 + j] & F_SENSE;
+      const float cj = a.hub_cn[r0 + j];
+      const int32_t dj = g.dist[r0 + j];
+      const float sj = g.std_dev[r0 + j];
+      for (uint32_t x = 0; x < nx; x++) {
+        const uint32_t i = s_i[x];
+        if (j == i || s_fi[x] != fj) continue;
+        const float ci = s_ci[x];
+        if (!(__fadd_rn(ci, cj) < a.cncutoff)) continue;
+        // check_mark_polymorphic, algorithms.c:232-238 (edge1 = earlier adjacency slot)
+        const bool i_first = i < j;
+        const bool amb = i_first ? ambiguous_order(s_di[x], s_si[x], dj, sj, a.ambig)
+                                 : ambiguous_order(dj, sj, s_di[x], s_si[x], a.ambig);
+        if (!amb) continue;
+        const float c1 = i_first ? ci : cj, c2 = i_first ? cj : ci;
+        const uint32_t k1 = i_first ? i : j, k2 = i_first ? j : i;
+        a.hub_mark[r0 + (c1 < c2 ? k1 : k2)] = 1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k4_hub_emit(FilterArgs a) {
+  const GraphArgs &g = a.g;
+  for (uint32_t li = blockIdx.x; li < g.n_big_rows; li += gridDim.x) {
+    const uint32_t p = g.big_rows[li];
+    const uint32_t r0 = g.row_ptr[p - g.row_base], d = g.row_ptr[p - g.row_base + 1] - r0;
+    if (d <= MID_ROW || (a.vinfo[p].y & VI_MARKED)) continue;          // block-uniform
+    for (uint32_t k0 = 0; k0 < d; k0 += blockDim.x) {
+      const uint32_t k = k0 + threadIdx.x;
+      uint32_t t = 0;
+      bool emit = false;
+      if (k < d && a.hub_mark[r0 + k]) {
+        t = g.dst[r0 + k];
+        emit = !(a.vinfo[t].y & VI_MARKED);
+      }
+      warp_append2(emit, make_uint2(p, t), a.proposals, a.proposals_cap, &g.counters[CNT_PROPOSALS],
+                   &g.counters[CNT_OVERFLOW]);
+    }
+  }
+}
+
 void launch_pairs(const FilterArgs &a, cudaStream_t s) {
   if (a.g.E == 0) return;
   {
@@ -762,7 +871,15 @@ void launch_pairs(const FilterArgs &a, cudaStream_t s) {
     uint32_t mid_blocks = (a.g.n_big_rows + 7) / 8;
     if (mid_blocks > (uint32_t) a.g.sm_count * 8) mid_blocks = (uint32_t) a.g.sm_count * 8;
     k4_pairs_mid<<<mid_blocks, 256, 0, s>>>(a);
-    if (a.g.max_deg > MID_ROW) k4_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
+    if (a.g.max_deg > MID_ROW && a.hub_cn != nullptr) {
+      uint32_t row_blocks = a.g.n_big_rows < (uint32_t) a.g.sm_count * 8 ? a.g.n_big_rows : (uint32_t) a.g.sm_count * 8;
+      cudaMemsetAsync(&a.g.counters[CNT_HUB_ITEMS], 0, 4, s);
+      k4_hub_prep<<<row_blocks, 256, 0, s>>>(a);
+      k4_hub_pairs<<<a.g.sm_count * 8, 256, 0, s>>>(a);
+      k4_hub_emit<<<row_blocks, 256, 0, s>>>(a);
+    } else if (a.g.max_deg > MID_ROW) {
+      k4_pairs_big<<<a.big_blocks, 512, 0, s>>>(a);
+    }
   }
 }
 

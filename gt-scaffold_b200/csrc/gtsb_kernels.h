@@ -22,7 +22,8 @@ constexpr uint32_t BIG_ROW = 32;    // rows above this take the block-per-row pa
 
 // device counter block (uint32 each)
 enum {
-  CNT_ERROR = 0,          // bit0: vertex id out of range, bit1: self link
+  CNT_ERROR = 0,          // bit0: vertex id out of range, bit1: self link, bit2: seq_len >= 2^31, bit3: mail for
+                          // another rank's row, bit4: scratch offsets of the general build's hub buckets wrapped
   CNT_LARGE_BUCKETS,      // buckets queued for k_resolve_large
   CNT_LARGE_PAD,          // scratch entries they need
   CNT_BIG_ROWS,           // rows with degree > BIG_ROW
@@ -37,6 +38,7 @@ enum {
   CNT_CORRECTIONS,        // reverse-flag corrections posted by k2_resolve
   CNT_WINDOWS,            // windows cut by k4_pack_windows
   CNT_RING0, CNT_RING1, CNT_RING2, CNT_RING_ROUNDS,   // worklist lengths / round count of k_fire_rounds_all
+  CNT_HUB_ITEMS,          // work items (hub row, chunk of its low-copy-number slots) of the split pairs pass
   CNT_NUM
 };
 
@@ -218,7 +220,16 @@ struct FilterArgs {
   uint32_t *vres;            // polyTime | fire bits | repeat predicate
   uint8_t *vsum;             // fire bits | repeat predicate | has-polyTime: what the final pass gathers per neighbour
   int fused_repeats;         // fresh graph: edge REPEAT marks are derived, not stored (gtsb_pipeline)
+  // pairs pass of the rows above HUB_ROW slots split over the grid (null: block per row with big_scratch)
+  float *hub_cn;             // by slot: copy number of the slot's neighbour
+  uint32_t *hub_low;         // by slot: the row's low-copy-number slots, packed at the row's first slots
+  uint8_t *hub_mark;         // by slot: the neighbour is proposed
+  uint32_t *hub_nlow;        // by big-row list index: length of the row's low list
+  uint2 *hub_items;          // {big-row list index, chunk of HUB_LCH low slots}
+  uint32_t hub_items_cap;
 };
+constexpr uint32_t HUB_ROW = 256;     // rows up to this many slots take a warp, longer ones a block (or the split pass)
+constexpr uint32_t HUB_LCH = 32;      // low-copy-number slots per work item of the split pass
 constexpr uint32_t BIG_SCRATCH_STRIDE = 12;   // cn f32, len u32, u8 marks (padded)
 
 // per-vertex facts by position; with do_repeats also the repeat predicate

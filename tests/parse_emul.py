@@ -13,9 +13,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "..", "gt-scaffold_b200", "csrc")
 SRCS = [os.path.join(HERE, "emul", "parse_emul.cpp"), os.path.join(HERE, "emul", "format_emul.cpp"),
-        os.path.join(HERE, "emul", "mle_emul.cpp")]
+        os.path.join(HERE, "emul", "mle_emul.cpp"), os.path.join(HERE, "emul", "sort_emul.cpp")]
 CORES = [os.path.join(CSRC, "gtsb_parse_core.h"), os.path.join(CSRC, "gtsb_format_core.h"),
-         os.path.join(CSRC, "gtsb_mle_core.h")]
+         os.path.join(CSRC, "gtsb_mle_core.h"), os.path.join(CSRC, "gtsb_sort_core.h")]
 OUT = os.path.join(HERE, "emul", "_build", "libparse_emul.so")
 _lib = None
 

@@ -54,7 +54,9 @@ if __name__ == "__main__":
     kern = {n: round(m / 2, 4) for n, (m, c) in sorted(g.profile().items(), key=lambda kv: -kv[1][0])}
     g.set_profile(False)
     E = st["nof_edges"]
+    _, de, dv = g.digest()          # order-independent digests of every edge and vertex state (gtsb_result_digest)
     print(json.dumps({"workload": name, "V": Vn, "R": Rn, "E": E, "ms_per_step": round(ms, 4),
+                      "digest_edges": "%016x" % de, "digest_vertices": "%016x" % dv,
                       "edges_per_s": E / ms * 1e3, "env": {k: v for k, v in os.environ.items() if k.startswith("GTSB_")},
                       "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds",
                                                    "line_ordered_build", "fallback_reason", "kernel_launches")},
