@@ -141,7 +141,11 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
 
 // thread per vertex; buckets above MAXN entries are queued for the block path.  A warp lasts as
 // long as its largest bucket's insertion sort (quadratic), so the bound is also a bound on divergence.
-template <int MAXN>
+constexpr uint32_t MID_MAX = 128;        // bucket entries a warp sorts in shared memory (k_resolve_mid)
+
+// MID: buckets of MAXN + 1 .. MID_MAX entries are listed for k_resolve_mid -- the list grows down
+// from the end of large_list (mid + large buckets <= V, the array has V + 1 places)
+template <int MAXN, bool MID>
 __global__ void __launch_bounds__(128) k_resolve_small(
     uint32_t V, const uint32_t *__restrict__ bptr, uint4 *__restrict__ entries,
     uint32_t *__restrict__ bwin, uint32_t *__restrict__ deg, uint8_t *__restrict__ creator_flag,
@@ -153,7 +157,9 @@ __global__ void __launch_bounds__(128) k_resolve_small(
     n = bptr[v + 1] - b0;
   }
   const bool large = n > (uint32_t) MAXN;
-  if (large) {  // queue for the block path: (vertex, scratch offset)
+  if (large && MID && n <= MID_MAX) {
+    large_list[V - atomicAdd(&counters[CNT_MID_BUCKETS], 1u)] = make_uint2(v, 0u);
+  } else if (large) {  // queue for the block path: (vertex, scratch offset)
     const uint32_t pad = next_pow2(n);
     const uint32_t off = atomicAdd(&counters[CNT_LARGE_PAD], 2u * pad);
     if (n > (1u << 30) || off + 2u * pad < off) atomicOr(&counters[CNT_ERROR], 16u);   // 32-bit scratch offsets wrapped
@@ -205,6 +211,62 @@ __global__ void __launch_bounds__(128) k_resolve_small(
   if (bwin != nullptr)
     for (uint32_t i = 0; i < g; i++) bwin[b0 + i] = w[i];
   deg[v] = g;
+}
+
+// warp per listed bucket of at most MID_MAX entries: the resolution of k_resolve_large with the
+// bucket, both sorts and the group list in shared memory (no block barriers: every warp walks its
+// own buckets)
+__global__ void __launch_bounds__(256) k_resolve_mid(
+    uint32_t V, const uint32_t *__restrict__ bptr, uint4 *__restrict__ entries, uint32_t *__restrict__ bwin,
+    uint32_t *__restrict__ deg, uint8_t *__restrict__ creator_flag, const uint2 *__restrict__ large_list,
+    const uint32_t *__restrict__ counters) {
+  __shared__ uint4 s_a[8][MID_MAX], s_b[8][MID_MAX];
+  __shared__ uint32_t s_t[8][MID_MAX];
+  const uint32_t wi = threadIdx.x >> 5, lane = lane_id();
+  uint4 *A = s_a[wi], *B = s_b[wi];
+  uint32_t *T = s_t[wi];
+  const uint32_t nmid = counters[CNT_MID_BUCKETS];
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint4 inf = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+  for (uint32_t li = warp; li < nmid; li += nwarps) {
+    const uint32_t v = large_list[V - li].x;
+    const uint32_t b0 = bptr[v], n = bptr[v + 1] - b0;             // n <= MID_MAX
+    const uint32_t P = next_pow2(n);
+    for (uint32_t i = lane; i < P; i += 32u) A[i] = i < n ? entries[b0 + i] : inf;
+    __syncwarp();
+    gtsbs::plain_bitonic<gtsbs::WarpGroup>(A, nullptr, P, 0);
+    uint32_t carry = 0;                                            // groups before this round's lanes
+    for (uint32_t base = 0; base < n; base += 32u) {               // warp-uniform trip count
+      const uint32_t i = base + lane;
+      bool head = false;
+      if (i < n) head = i == 0 || (A[i].y & E_OTHER_MASK) != (A[i - 1].y & E_OTHER_MASK);
+      const uint32_t hm = __ballot_sync(0xffffffffu, head);
+      if (head) {
+        const uint32_t pos = carry + __popc(hm & ((1u << lane) - 1u));
+        const uint32_t other = A[i].y & E_OTHER_MASK;
+        uint32_t j = i + 1;
+        while (j < n && (A[j].y & E_OTHER_MASK) == other) j++;
+        uint32_t win;
+        B[pos] = resolve_group([&](uint32_t k) { return A[k]; }, i, j, &win, creator_flag);
+        T[pos] = win;
+      }
+      carry += __popc(hm);
+    }
+    const uint32_t g = carry;
+    const uint32_t P2 = next_pow2(g);
+    for (uint32_t i = g + lane; i < P2; i += 32u) {
+      B[i] = inf;
+      T[i] = 0;
+    }
+    __syncwarp();
+    gtsbs::plain_bitonic<gtsbs::WarpGroup>(B, T, P2, 1);
+    for (uint32_t i = lane; i < g; i += 32u) {
+      entries[b0 + i] = B[i];
+      if (bwin != nullptr) bwin[b0 + i] = T[i];
+    }
+    if (lane == 0) deg[v] = g;
+    __syncwarp();                                                  // A, B, T: next bucket
+  }
 }
 
 // block-wide bitonic sort of P (power of two) entries in global memory.
@@ -422,17 +484,31 @@ void launch_build_scatter_resolve(const BuildArgs &a, cudaStream_t s) {
   { KernelTimer t_("k_scatter_halfedges", s);
   k_scatter_halfedges<<<grid_for(a.R, 256, a.sm_count * 16), 256, 0, s>>>(
       a.R, a.V, a.root, a.ctg, a.dist, a.std_dev, a.flags, a.bptr, a.cursor, a.entries); }
-  KernelTimer t2_("k_resolve_small", s);
-  static const int small32 = [] {
-    const char *e = getenv("GTSB_SMALL_MAX");            // 32: buckets of 33..64 entries take the block path too (dev switch)
-    return (e != nullptr && atoi(e) == 32) ? 1 : 0;
+  static const int small_max = [] {
+    // dev switch.  32: buckets of 33 .. 64 entries take the block path too; 16: buckets of 17 .. 128
+    // entries take a warp each (k_resolve_mid), longer ones the block path
+    const char *e = getenv("GTSB_SMALL_MAX");
+    return e != nullptr ? atoi(e) : 0;
   }();
-  if (a.V && small32)
-    k_resolve_small<32><<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
-                                                          a.creator_flag, a.large_list, a.counters);
-  else if (a.V)
-    k_resolve_small<RESOLVE_SMALL_MAX><<<(a.V + 127) / 128, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
-                                                                         a.creator_flag, a.large_list, a.counters);
+  if (!a.V) return;
+  const uint32_t blocks = (a.V + 127) / 128;
+  {
+    KernelTimer t2_("k_resolve_small", s);
+    if (small_max == 16)
+      k_resolve_small<16, true><<<blocks, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
+                                                       a.large_list, a.counters);
+    else if (small_max == 32)
+      k_resolve_small<32, false><<<blocks, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
+                                                        a.large_list, a.counters);
+    else
+      k_resolve_small<RESOLVE_SMALL_MAX, false><<<blocks, 128, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg,
+                                                                       a.creator_flag, a.large_list, a.counters);
+  }
+  if (small_max == 16) {
+    KernelTimer t3_("k_resolve_mid", s);
+    k_resolve_mid<<<a.sm_count * 6, 256, 0, s>>>(a.V, a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
+                                                 a.large_list, a.counters);
+  }
 }
 
 void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *scratch_tag,

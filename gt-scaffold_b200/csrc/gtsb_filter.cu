@@ -940,10 +940,52 @@ __global__ void __launch_bounds__(256) k4_dirty(FilterArgs a, uint32_t n) {
   }
 }
 
+// the same marks with rows of more than BIG_ROW slots walked by the whole warp: a hub that turned
+// polymorphic costs one thread 10^4 dependent gathers in k4_dirty
+__global__ void __launch_bounds__(256) k4_dirty_w(FilterArgs a, uint32_t n) {
+  const GraphArgs &g = a.g;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = false;
+  uint32_t t = 0, r0 = 0, d = 0;
+  if (i < n) {
+    const uint2 pr = a.proposals[i];
+    t = a.poly_cur[pr.y];                                     // when the target turned polymorphic
+    const uint32_t rl = pr.y - g.row_base;                    // the target's row, if this device holds it
+    if (t == id_at(g, pr.x) && rl < g.V) {                    // the winning proposer
+      act = true;
+      r0 = g.row_ptr[rl];
+      d = g.row_ptr[rl + 1] - r0;
+    }
+  }
+  const bool big = act && d > BIG_ROW;
+  if (act && !big)
+    for (uint32_t s = r0; s < r0 + d; s++) {
+      const uint32_t v = g.dst[s];
+      if (t <= id_at(g, v)) a.dirty[v] = 1;
+    }
+  unsigned todo = __ballot_sync(FULL, big);
+  while (todo) {
+    const int l = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t rr = __shfl_sync(FULL, r0, l), dd = __shfl_sync(FULL, d, l), tt = __shfl_sync(FULL, t, l);
+    for (uint32_t k = lane_id(); k < dd; k += 32u) {
+      const uint32_t v = g.dst[rr + k];
+      if (tt <= id_at(g, v)) a.dirty[v] = 1;
+    }
+  }
+}
+
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s) {
   if (n_proposals == 0) return;
   KernelTimer t_("k4_dirty", s);
-  k4_dirty<<<(n_proposals + 255) / 256, 256, 0, s>>>(a, n_proposals);
+  static const int by_warp = [] {
+    const char *e = getenv("GTSB_HUBS");                 // 1: hub rows walked by a warp (dev switch)
+    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
+  }();
+  if (by_warp && a.g.n_big_rows)
+    k4_dirty_w<<<(n_proposals + 255) / 256, 256, 0, s>>>(a, n_proposals);
+  else
+    k4_dirty<<<(n_proposals + 255) / 256, 256, 0, s>>>(a, n_proposals);
 }
 
 // ------------------------------------------------------------------ phase 2: fire candidates

@@ -19,6 +19,12 @@ void emul_blocked_bitonic(uint32_t *ent, uint32_t *tag, uint32_t P, int mode, in
   gtsbs::blocked_bitonic(reinterpret_cast<gtsbs::Ent *>(ent), tag, P, mode, s_a.data(), s_t.data());
 }
 
+// the network as a warp runs it over a bucket held in shared memory (k_resolve_mid)
+void emul_plain_bitonic(uint32_t *ent, uint32_t *tag, uint32_t P, int mode, int reverse) {
+  gtsbs::emul_reverse = reverse;
+  gtsbs::plain_bitonic<gtsbs::WarpGroup>(reinterpret_cast<gtsbs::Ent *>(ent), tag, P, mode);
+}
+
 uint32_t emul_sort_chunk(void) { return gtsbs::SORT_CHUNK; }
 
 }

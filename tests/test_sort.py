@@ -12,11 +12,11 @@ import parse_emul
 OTHER_MASK = (1 << 27) - 1
 
 
-def _sort(ent, tag, mode, reverse):
+def _sort(ent, tag, mode, reverse, plain=False):
     L = parse_emul.lib()
     ent = np.ascontiguousarray(ent, np.uint32).copy()
     tg = None if tag is None else np.ascontiguousarray(tag, np.uint32).copy()
-    L.emul_blocked_bitonic(ent.ctypes.data_as(C.c_void_p), None if tg is None else tg.ctypes.data_as(C.c_void_p),
+    (L.emul_plain_bitonic if plain else L.emul_blocked_bitonic)(ent.ctypes.data_as(C.c_void_p), None if tg is None else tg.ctypes.data_as(C.c_void_p),
                            C.c_uint32(ent.shape[0]), C.c_int(mode), C.c_int(reverse))
     return ent, tg
 
@@ -42,8 +42,10 @@ def test_blocked_bitonic_equals_a_key_sort(logp, mode):
         ent[:n, 2:] = rng.integers(0, 2 ** 32, (n, 2), dtype=np.uint64).astype(np.uint32)
         ent[n:] = (0xFFFFFFFF, 0xFFFFFFFF, 0, 0)                          # k_resolve_large's padding
         tag = rng.integers(0, 2 ** 32, P, dtype=np.uint64).astype(np.uint32)
-        for tg in (None, tag):
-            got, gtag = _sort(ent, tg, mode, reverse)
+        for tg, plain in ((None, False), (tag, False), (tag, True)):
+            if plain and P > 128:                                         # the warp path holds up to 128 entries
+                continue
+            got, gtag = _sort(ent, tg, mode, reverse, plain)
             order = _expected(ent, mode)
             # keys are unique among the real entries; the padding entries are identical
             assert np.array_equal(got[:n], ent[order][:n]), (logp, mode, reverse)
