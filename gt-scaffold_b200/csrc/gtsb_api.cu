@@ -519,6 +519,7 @@ int do_build(gtsb_context *c) {
   a.large_list = c->large_list.as<uint2>();
   a.big_rows = c->big_rows.as<uint32_t>();
   a.counters = c->counters.as<uint32_t>();
+  a.hubs = (c->fallback_reason & FB_LONGLINE) ? 1 : 0;
   a.row_ptr = c->row_ptr.as<uint32_t>();
   a.dst = c->dst.as<uint32_t>();
   a.eid = c->eid.as<uint32_t>();
@@ -615,8 +616,8 @@ int ensure_filter_buffers(gtsb_context *c, uint64_t V, uint64_t E, FilterArgs &a
     ENSURE(c->big_scratch, (size_t) a.big_blocks * c->max_deg * BIG_SCRATCH_STRIDE);
   }
   static const int split_hubs = [] {
-    const char *e = getenv("GTSB_HUBS");                 // 1: pairs of the hub rows split over the grid (dev switch)
-    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
+    const char *e = getenv("GTSB_HUBS");                 // 0: a block per hub row, as in round 1 (dev switch)
+    return (e != nullptr && atoi(e) == 0) ? 0 : 1;
   }();
   if (split_hubs && c->world == 1 && c->n_big_rows && c->max_deg > HUB_ROW) {
     const uint64_t cap = E / HUB_LCH + c->n_big_rows + 1;

@@ -484,12 +484,16 @@ void launch_build_scatter_resolve(const BuildArgs &a, cudaStream_t s) {
   { KernelTimer t_("k_scatter_halfedges", s);
   k_scatter_halfedges<<<grid_for(a.R, 256, a.sm_count * 16), 256, 0, s>>>(
       a.R, a.V, a.root, a.ctg, a.dist, a.std_dev, a.flags, a.bptr, a.cursor, a.entries); }
-  static const int small_max = [] {
-    // dev switch.  32: buckets of 33 .. 64 entries take the block path too; 16: buckets of 17 .. 128
-    // entries take a warp each (k_resolve_mid), longer ones the block path
+  // A graph with hubs (a.hubs: the line-ordered build met a line longer than it takes): a thread
+  // takes buckets of up to 16 entries, a warp those of 17 .. 128 (k_resolve_mid), a block the rest --
+  // a warp of the thread path lasts as long as its largest bucket's quadratic sort.  Otherwise a
+  // thread takes up to 64 entries, as measured on the uniform configs.  GTSB_SMALL_MAX = 16 / 32 / 64
+  // forces one of the three (dev switch).
+  static const int forced = [] {
     const char *e = getenv("GTSB_SMALL_MAX");
     return e != nullptr ? atoi(e) : 0;
   }();
+  const int small_max = forced ? forced : (a.hubs ? 16 : RESOLVE_SMALL_MAX);
   if (!a.V) return;
   const uint32_t blocks = (a.V + 127) / 128;
   {
@@ -516,11 +520,11 @@ void launch_build_resolve_large(const BuildArgs &a, uint4 *scratch, uint32_t *sc
   if (nlarge == 0) return;
   uint32_t blocks = nlarge < (uint32_t) a.sm_count * 8 ? nlarge : (uint32_t) a.sm_count * 8;
   KernelTimer t_("k_resolve_large", s);
-  static const int blocked = [] {
-    const char *e = getenv("GTSB_HUB_SORT");             // 1: sorts blocked through shared memory (dev switch)
-    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
+  static const int forced = [] {
+    const char *e = getenv("GTSB_HUB_SORT");             // 0 / 1: sorts in global memory / blocked through shared memory (dev switch)
+    return e != nullptr ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
-  if (blocked)
+  if (forced >= 0 ? forced != 0 : a.hubs != 0)
     k_resolve_large2<<<blocks, 256, 0, s>>>(a.bptr, a.entries, a.bwin, a.deg, a.creator_flag,
                                             a.large_list, a.counters, scratch, scratch_tag);
   else

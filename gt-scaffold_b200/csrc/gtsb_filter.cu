@@ -978,11 +978,7 @@ __global__ void __launch_bounds__(256) k4_dirty_w(FilterArgs a, uint32_t n) {
 void launch_dirty(const FilterArgs &a, uint32_t n_proposals, cudaStream_t s) {
   if (n_proposals == 0) return;
   KernelTimer t_("k4_dirty", s);
-  static const int by_warp = [] {
-    const char *e = getenv("GTSB_HUBS");                 // 1: hub rows walked by a warp (dev switch)
-    return (e != nullptr && atoi(e) == 1) ? 1 : 0;
-  }();
-  if (by_warp && a.g.n_big_rows)
+  if (a.hub_cn != nullptr)                               // a single device holding rows above HUB_ROW slots
     k4_dirty_w<<<(n_proposals + 255) / 256, 256, 0, s>>>(a, n_proposals);
   else
     k4_dirty<<<(n_proposals + 255) / 256, 256, 0, s>>>(a, n_proposals);

@@ -161,6 +161,7 @@ struct BuildArgs {
   uint2 *large_list;
   uint32_t *big_rows;
   uint32_t *counters;
+  int hubs;                 // the line-ordered build met a line of more than MAX_LINE_RECS records: hub buckets ahead
   // CSR out
   uint32_t *row_ptr, *dst, *eid, *win_rec;
   int32_t *edist;
