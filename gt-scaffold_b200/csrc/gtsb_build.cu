@@ -139,10 +139,10 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
 }
 
-// thread per vertex; buckets above MAXN entries are queued for the block path.  A warp lasts as
-// long as its largest bucket's insertion sort (quadratic), so the bound is also a bound on divergence.
 constexpr uint32_t MID_MAX = 128;        // bucket entries a warp sorts in shared memory (k_resolve_mid)
 
+// thread per vertex; buckets above MAXN entries are queued for the block path.  A warp lasts as
+// long as its largest bucket's insertion sort (quadratic), so the bound is also a bound on divergence.
 // MID: buckets of MAXN + 1 .. MID_MAX entries are listed for k_resolve_mid -- the list grows down
 // from the end of large_list (mid + large buckets <= V, the array has V + 1 places)
 template <int MAXN, bool MID>
