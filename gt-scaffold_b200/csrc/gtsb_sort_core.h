@@ -17,7 +17,7 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(CUSIM)   // CUSIM: the host model of the device language (tests/emul/cusim)
 #define GTSB_SORT_FN __device__ __forceinline__
 namespace gtsbs {
 typedef uint4 Ent;

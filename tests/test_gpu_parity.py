@@ -75,14 +75,14 @@ def test_small_line_ordered(pkg, synth, seed):
     _run_both(pkg, inp, *PARAMS[seed % len(PARAMS)], force_general=True)
 
 
-def test_fallback_reasons(pkg, synth):
+def test_fallback_reasons(pkg, synth, hub_V=20000):
     """Inputs outside the fast path's preconditions must be detected, not guessed."""
     # a link listed only on the later line
     inp = synth.generate("c2_bacterial", V=3000, one_sided_frac=0.3)
     st = _run_both(pkg, inp, *PARAMS[0], stagewise=False)
     assert st["line_ordered_build"] == 0 and st["fallback_reason"] & 8
     # hubs: lines longer than the per-thread scans accept
-    inp = synth.generate("c4_repeat_hubs", V=20000, max_deg=500)
+    inp = synth.generate("c4_repeat_hubs", V=hub_V, max_deg=500)
     st = _run_both(pkg, inp, *PARAMS[0], stagewise=False)
     assert st["line_ordered_build"] == 0 and st["fallback_reason"] & (2 | 4)
     # records not grouped by root
@@ -216,10 +216,10 @@ def test_filter_on_uploaded_graph_with_arbitrary_states(pkg, synth):
         assert np.array_equal(c["estate"], ref.estate()[eids]), seed
 
 
-def test_line_shaped_input_and_states_by_eid(pkg, synth):
+def test_line_shaped_input_and_states_by_eid(pkg, synth, V=20_000):
     """gtsb_set_record_lines_host / gtsb_get_edge_states: the same graph and marks as the
     flat record input, with 4 B/record less on the way in and 1 B/edge on the way out."""
-    inp = synth.generate("c2_bacterial", V=20_000, seed=21, mirror_diff_frac=0.1, dup_same_line_frac=0.05)
+    inp = synth.generate("c2_bacterial", V=V, seed=21, mirror_diff_frac=0.1, dup_same_line_frac=0.05)
     a = pkg.ScaffoldGraphB200.new_from_records(inp)
     a.mark_repeats()
     a.filter()

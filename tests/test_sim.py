@@ -1,0 +1,207 @@
+"""The product's CUDA sources RUN ON THE HOST (no GPU): gt-scaffold_b200/csrc/*.cu compiled by g++
+against tests/emul/cusim/ -- a functional model of the CUDA runtime and device language in which
+the threads of a block are fibers and barriers, shuffles, ballots and reductions are rendezvous
+(tests/emul/cusim_build.py, TEST INFRASTRUCTURE).  What runs here is the kernels' own logic:
+shared-memory staging, warp windows, counting sorts, the fix-point rounds (cooperative launch
+included), the hub routes, the text kernels.  It is checked the way the GPU tests check the device:
+against the compiled reference / the oracle, the committed golden vectors, the host builds of the
+text stages, and -- through the reference's own driver, linked with the binding and pointed at the
+emulated library -- against the golden `.dot` / `.scaf` files of config 1.
+
+The functions called below ARE the GPU tests (tests/test_gpu_parity.py and friends, `-m gpu`): same
+bodies, same assertions, a package whose ctypes loader was handed the emulated library.  Nothing in
+the product knows the emulation exists; it is not a fallback (gtsb_create of the real library still
+fails without a CUDA device)."""
+import glob
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+import cusim_build  # noqa: E402
+import oracle_lib as O  # noqa: E402
+import test_components as TC  # noqa: E402
+import test_dropin as TD  # noqa: E402
+import test_format as TF  # noqa: E402
+import test_gpu_parity as G  # noqa: E402
+import test_mle as TM  # noqa: E402
+import test_parse as TP  # noqa: E402
+import test_scaf as TS  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sim(pkg):
+    """The package with the emulated library behind its ctypes loader (restored afterwards)."""
+    api = pkg.api
+    saved = (api.LIB_PATH, api._lib)
+    api.LIB_PATH, api._lib = cusim_build.build(), None
+    api.load_library()
+    yield pkg
+    api.LIB_PATH, api._lib = saved
+
+
+def test_the_real_library_still_needs_a_device(pkg):
+    """The emulation is handed to the loader explicitly; the product's own library has no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    assert os.path.basename(pkg.api.LIB_PATH) == "libgtscaffold_b200.so"
+    with pytest.raises(RuntimeError):
+        pkg.ScaffoldGraphB200()
+
+
+# ------------------------------------------------------------------ build + mark_repeats + filter
+
+@pytest.mark.parametrize("seed", range(0, 60, 3))
+def test_tiny_adversarial(sim, synth, seed):
+    G.test_tiny_adversarial(sim, synth, seed)
+
+
+@pytest.mark.parametrize("seed", range(0, 40, 5))
+def test_small_line_ordered(sim, synth, seed):
+    G.test_small_line_ordered(sim, synth, seed)
+
+
+def test_fallbacks_degenerate_and_refused_inputs(sim, synth):
+    G.test_fallback_reasons(sim, synth, hub_V=2500)
+    G.test_empty_and_degenerate(sim, synth)
+    G.test_invalid_records_are_refused(sim, synth)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "diff_*.npz"))))
+def test_committed_differential_vectors(sim, synth, path):
+    G.test_committed_differential_vectors(sim, synth, path)
+
+
+@pytest.mark.parametrize("name,V,kw", [
+    ("c2_bacterial", 2500, {}),
+    ("c2_bacterial", 2000, dict(line_order="id", one_sided_frac=0.2)),
+    ("c3_human", 3000, {}),
+    # hubs: rows above 256 slots (split pairs pass), buckets above 2048 entries (sort in several chunks)
+    ("c4_repeat_hubs", 4000, dict(max_deg=1500)),
+])
+def test_named_shapes(sim, synth, name, V, kw):
+    inp = synth.generate(name, V=V, **kw)
+    for force in (False, True):
+        st = G._run_both(sim, inp, **G.DEFAULT, stagewise=False, force_general=force)
+        assert st["nof_edges"] > 0
+        if name == "c4_repeat_hubs":
+            assert st["max_degree"] > 1024 and st["big_rows"] > 0 and st["large_buckets"] > 0
+            assert st["fallback_reason"] == (0 if force else 2), st        # a long line: the hub routes
+        elif not kw:
+            assert st["line_ordered_build"] == (0 if force else 1), st
+
+
+def test_the_other_entry_points(sim, synth):
+    G.test_win_rec_points_at_the_winning_record(sim, synth)
+    G.test_win_rec_on_the_line_ordered_build(sim, synth)
+    G.test_filter_on_uploaded_graph_with_arbitrary_states(sim, synth)
+    G.test_line_shaped_input_and_states_by_eid(sim, synth, V=2000)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_special_values(sim, synth, seed):
+    G.test_special_values(sim, synth, seed)
+
+
+def test_pipeline_is_the_three_calls_and_the_digest_is_its_numpy_statement(sim, synth):
+    inp = synth.generate("c2_bacterial", V=1500, seed=12)
+    g = sim.ScaffoldGraphB200.new_from_records(inp)
+    g.mark_repeats(0.3, 20.0, True)
+    g.filter(0.01, 1.5, 400)
+    a = g.result()
+    e, vs = g.edges(), g.vstate()
+    assert g.digest() == sim.api.result_digest(e, vs)
+    g.close()
+    g = sim.ScaffoldGraphB200()
+    g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+    g.set_records(inp.root, inp.ctg, inp.dist, inp.std_dev, inp.flags)
+    g.pipeline(0.3, 20.0, True, 0.01, 1.5, 400)
+    b = g.result()
+    g.close()
+    for k in G.KEYS:
+        assert np.array_equal(G._bits(a[k]), G._bits(b[k])), k
+
+
+@pytest.mark.parametrize("order", [1, 7, 12345])
+def test_results_do_not_depend_on_the_order_of_the_threads(sim, synth, order):
+    """The emulation gives the threads of a block their turns in ascending order by default; here
+    descending (1) and pseudo-random per pass (seeded).  Between two rendezvous a thread may only
+    touch what no other thread touches, so the graphs and marks must come out the same -- on the
+    line-ordered build, the general build with its hub routes, and the filter with hub rows."""
+    lib = sim.api.load_library()
+    lib.cusim_set_order.argtypes = [__import__("ctypes").c_uint64]
+    lib.cusim_set_order(order)
+    try:
+        for name, V, kw in (("c2_bacterial", 1500, {}), ("c4_repeat_hubs", 2500, dict(max_deg=1200)),
+                            ("c2_bacterial", 1200, dict(line_order="id", one_sided_frac=0.2, mirror_diff_frac=0.2))):
+            G._run_both(sim, synth.generate(name, V=V, seed=31, **kw), **G.DEFAULT, stagewise=False)
+        G.test_tiny_adversarial(sim, synth, order % 60)
+    finally:
+        lib.cusim_set_order(0)
+
+
+# ------------------------------------------------------------------ text kernels, components, MLE
+
+@pytest.mark.parametrize("seed", [0, 1, 4])
+def test_de_and_astat_tokenisers(sim, seed):
+    TP.test_device_equals_emulation(sim, seed)
+    TP.test_device_astat_equals_emulation(sim, seed)
+
+
+def test_tokeniser_refusals(sim):
+    TP.test_device_long_lines_and_degenerate(sim)
+    TP.test_device_refuses_duplicate_headers(sim)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_dot_and_scaf_writers(sim, synth, seed):
+    TF.test_device_lines_equal_host_build(sim, synth, seed)
+    TS.test_device_equals_host_build(sim, seed)
+
+
+def test_components_and_terminals(sim, synth):
+    rng = np.random.default_rng(50)
+    inp = synth.generate("c2_bacterial", V=3000, seed=60)
+    g = sim.ScaffoldGraphB200.new_from_records(inp)
+    g.mark_repeats(0.3, 20.0, True)
+    g.filter(0.01, 1.5, 400)
+    e, vs = g.edges(), g.vstate()
+    lab, term = g.components()
+    elab, eterm = TC.labels_and_terminals(e["src"], e["dst"], e["flags"] & 1, e["estate"], vs)
+    assert np.array_equal(lab, elab) and np.array_equal(term, eterm)
+    assert len(np.unique(lab)) > 10 and rng is not None
+    g.close()
+
+
+def test_distance_mle(sim):
+    kind, rf, seed = TM.CASES[0]
+    TM.test_device_equals_host_build(sim, kind, rf, seed)
+
+
+# ------------------------------------------------------------------ the reference's own driver
+
+needs_bin = pytest.mark.skipif(not os.path.exists(TD.B200_TESTX), reason="integration/_build/test_b200.x not built")
+
+
+@needs_bin
+@pytest.mark.parametrize("tokeniser", [None, "host"])
+def test_config1_goldens_through_the_binding(tmp_path, tokeniser, monkeypatch):
+    """test.c of the reference, unmodified, linked with the binding; the library it calls is the
+    emulated one (symbols resolved from it first): the four stage `.dot` files and the `.scaf` file of
+    config 1 are byte-identical to the reference's goldens."""
+    monkeypatch.setenv("LD_PRELOAD", cusim_build.build())
+    TD.test_config1_goldens_through_the_binding(tmp_path, tokeniser)
+
+
+@needs_bin
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["tiny1", "tiny3_exponent", "c2_mirror"])
+def test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth, monkeypatch):
+    monkeypatch.setenv("LD_PRELOAD", cusim_build.build())
+    TD.test_binding_equals_reference_binary_on_text_inputs(case, tmp_path, synth)
