@@ -10,8 +10,9 @@
 //     reaches a barrier or a warp collective, where it waits for the others it names;
 //   * __syncthreads / __syncwarp / __shfl*_sync / __ballot_sync / __any_sync / __reduce_*_sync are
 //     rendezvous among the named lanes (lanes that have left the kernel count as arrived);
-//   * atomics are plain read-modify-writes (one host thread runs everything);
-//   * __shared__ is `static` (one block is alive at a time), dynamic shared memory a buffer per block;
+//   * atomics are the compiler's atomic builtins;
+//   * __shared__ is `static thread_local` (one block per emulated device is alive at a time; the
+//     ranks of a partitioned graph are threads), dynamic shared memory a buffer per block;
 //   * streams and events are immediate; device memory is host memory;
 //   * a cooperative launch keeps every block of its grid alive at once (grid-wide barriers).
 //
@@ -39,7 +40,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local      // ranks of a partitioned graph are threads (tests/test_sim.py)
 #define __align__(n) alignas(n)
 #define __constant__ static
 
@@ -74,8 +75,8 @@ struct BlockCtx {
   dim3 bdim, gdim;
   void *dyn_smem;
 };
-extern ThreadCtx *T;
-extern BlockCtx *B;
+extern thread_local ThreadCtx *T;
+extern thread_local BlockCtx *B;
 
 // rendezvous primitives (cusim.cpp)
 void block_barrier();
@@ -227,15 +228,28 @@ static inline uint32_t __reduce_add_sync(uint32_t m, uint32_t v) {
   return r;
 }
 
-// atomics: one host thread runs every fiber, a read-modify-write is atomic by construction
-template <typename A, typename V> static inline A atomicAdd(A *p, V v) { A o = *p; *p = (A) (o + (A) v); return o; }
-template <typename A, typename V> static inline A atomicSub(A *p, V v) { A o = *p; *p = (A) (o - (A) v); return o; }
-template <typename A, typename V> static inline A atomicOr(A *p, V v) { A o = *p; *p = (A) (o | (A) v); return o; }
-template <typename A, typename V> static inline A atomicAnd(A *p, V v) { A o = *p; *p = (A) (o & (A) v); return o; }
-template <typename A, typename V> static inline A atomicMax(A *p, V v) { A o = *p; if ((A) v > o) *p = (A) v; return o; }
-template <typename A, typename V> static inline A atomicMin(A *p, V v) { A o = *p; if ((A) v < o) *p = (A) v; return o; }
-template <typename A, typename V> static inline A atomicExch(A *p, V v) { A o = *p; *p = (A) v; return o; }
-template <typename A, typename V, typename W> static inline A atomicCAS(A *p, V cmp, W v) { A o = *p; if (o == (A) cmp) *p = (A) v; return o; }
+// atomics: GCC builtins -- the fibers of one emulated device share a host thread, but the ranks of
+// a partitioned graph are threads that store into each other's buffers (peer memory)
+template <typename A, typename V> static inline A atomicAdd(A *p, V v) { return __atomic_fetch_add(p, (A) v, __ATOMIC_SEQ_CST); }
+template <typename A, typename V> static inline A atomicSub(A *p, V v) { return __atomic_fetch_sub(p, (A) v, __ATOMIC_SEQ_CST); }
+template <typename A, typename V> static inline A atomicOr(A *p, V v) { return __atomic_fetch_or(p, (A) v, __ATOMIC_SEQ_CST); }
+template <typename A, typename V> static inline A atomicAnd(A *p, V v) { return __atomic_fetch_and(p, (A) v, __ATOMIC_SEQ_CST); }
+template <typename A, typename V> static inline A atomicExch(A *p, V v) { return __atomic_exchange_n(p, (A) v, __ATOMIC_SEQ_CST); }
+template <typename A, typename V, typename W> static inline A atomicCAS(A *p, V cmp, W v) {
+  A expected = (A) cmp;
+  __atomic_compare_exchange_n(p, &expected, (A) v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return expected;
+}
+template <typename A, typename V> static inline A atomicMax(A *p, V v) {
+  A o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while ((A) v > o && !__atomic_compare_exchange_n(p, &o, (A) v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}
+template <typename A, typename V> static inline A atomicMin(A *p, V v) {
+  A o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while ((A) v < o && !__atomic_compare_exchange_n(p, &o, (A) v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
@@ -368,6 +382,7 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaLaunchCooperativeKernel(const void *, dim3, dim3, void **, size_t, cudaStream_t) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+// peer memory: the ranks are threads of one process, a handle is the pointer itself
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

@@ -9,8 +9,8 @@
 
 namespace cusim {
 
-ThreadCtx *T = nullptr;
-BlockCtx *B = nullptr;
+thread_local ThreadCtx *T = nullptr;
+thread_local BlockCtx *B = nullptr;
 
 namespace {
 
@@ -41,15 +41,15 @@ struct Fiber {
   bool done = true;
 };
 
-std::vector<Fiber> fibers;
-std::vector<char *> stacks;
-std::vector<Block> blocks;
-ucontext_t sched_ctx;
-const std::function<void()> *body = nullptr;
-uint32_t cur = 0, total_live = 0;
-uint64_t progress = 0;        // bumped whenever any thread changes the state of a wait
-uint32_t grid_arrived = 0;
-uint64_t grid_gen = 0;
+thread_local std::vector<Fiber> fibers;
+thread_local std::vector<char *> stacks;
+thread_local std::vector<Block> blocks;
+thread_local ucontext_t sched_ctx;
+thread_local const std::function<void()> *body = nullptr;
+thread_local uint32_t cur = 0, total_live = 0;
+thread_local uint64_t progress = 0;        // bumped whenever any thread changes the state of a wait
+thread_local uint32_t grid_arrived = 0;
+thread_local uint64_t grid_gen = 0;
 
 void yield() {
   Fiber &f = fibers[cur];
@@ -83,7 +83,7 @@ uint64_t order_mode = [] {
   return e != nullptr ? (uint64_t) strtoull(e, nullptr, 10) : 0ull;
 }();
 uint64_t order_seed() { return order_mode; }
-uint64_t rng_state = 0;
+thread_local uint64_t rng_state = 0;
 uint32_t next_rand() {
   rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
   return (uint32_t) (rng_state >> 33);

@@ -146,6 +146,117 @@ def test_results_do_not_depend_on_the_order_of_the_threads(sim, synth, order):
         lib.cusim_set_order(0)
 
 
+# ------------------------------------------------------------------ one graph over several ranks
+
+def _partitioned(sim, inp, world, k=0, fail_at=None, reps=2):
+    """gtsb_dist.cu with the ranks as THREADS of this process: one context per rank on the emulated
+    device, NCCL replaced by a rendezvous stand-in (tests/emul/cusim/fake_nccl.cpp), peer memory by
+    plain pointers.  Input handling per case as tests/dist_check.py does under torchrun."""
+    import threading
+    import dist_check as DC
+    api = sim.api
+    uid = api.dist_unique_id()
+    out, err = [None] * world, [None] * world
+
+    def rank_main(r):
+        try:
+            mine = api.shard_lines(inp, world, r)
+            g = sim.ScaffoldGraphB200(device=0)
+            g.dist_init(r, world, uid)
+            if k % 3 != 2:
+                g.set_vertices(inp.seq_len, inp.astat, inp.copy_num)
+            if k % 2 == 1 and len(mine.root):
+                g.set_record_lines(*api.lines_of(mine.root), mine.ctg, mine.dist, mine.std_dev, mine.flags)
+            else:
+                g.set_records(mine.root, mine.ctg, mine.dist, mine.std_dev, mine.flags)
+            if k % 3 == 2:            # every rank uploads its slice of the contig attributes only
+                V = inp.nof_vertices
+                lo, hi = V * r // world, V * (r + 1) // world
+                g._ck(g.L.gtsb_set_vertices_slice_host(
+                    g.h, V, lo, hi - lo, api._ptr(np.ascontiguousarray(inp.seq_len[lo:hi], np.uint32)),
+                    api._ptr(np.ascontiguousarray(inp.astat[lo:hi], np.float32)),
+                    api._ptr(np.ascontiguousarray(inp.copy_num[lo:hi], np.float32))))
+                g.synchronize()
+                g.V = V
+            outcomes = []
+            for rep in range(reps):
+                if fail_at is not None:
+                    # the hook is read when a place is reached; every rank has left the call before it is cleared
+                    barrier.wait()
+                    if r == 0:
+                        if rep == 0:
+                            os.environ["GTSB_FAIL_AT"] = fail_at
+                        else:
+                            os.environ.pop("GTSB_FAIL_AT", None)
+                    barrier.wait()
+                try:
+                    g.pipeline(**DC.PARAMS)
+                    outcomes.append("ok")
+                except RuntimeError as e:
+                    outcomes.append("error: " + str(e))
+            out[r] = (g.edges() if outcomes[-1] == "ok" else None, g.vstate() if outcomes[-1] == "ok" else None,
+                      g.stats(), outcomes)
+            g.close()
+        except BaseException as e:      # noqa: BLE001 -- reported by the caller
+            err[r] = e
+
+    barrier = threading.Barrier(world)
+    threads = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(240)
+    os.environ.pop("GTSB_FAIL_AT", None)
+    assert not any(t.is_alive() for t in threads), "a rank is still waiting in an exchange"
+    assert not any(err), err
+    return out
+
+
+def _merged_equals_the_reference(out, inp):
+    import dist_check as DC
+    for o in out[1:]:
+        assert np.array_equal(o[1], out[0][1]), "vertex states differ between ranks"
+    got = DC.merged_result([o[0] for o in out], out[0][1])
+    ref = O.best_oracle().build(inp)
+    ref.mark_repeats(0.3, 20.0, use_copy_num=True)
+    ref.filter(0.01, 1.5, 400)
+    exp = ref.result()
+    ref.close()
+    for key in G.KEYS:
+        assert np.array_equal(G._bits(got[key]), G._bits(exp[key])), key
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_partitioned_graph_equals_the_reference(sim, synth, world):
+    """The rank-partitioned pipeline (line chunks, mail into the owners' receive buffers, the
+    exchanges of vertex facts, proposals and fire rounds) at 2, 3, 4 and 8 ranks: every rank's edges
+    merged by eid == the compiled reference, every attribute, state and the adjacency order."""
+    import dist_check as DC
+    names = ["one_record", "one_line", "tiny", "small_shuffled", "small_id_order", "mirror"]
+    if world > 3:
+        names = ["one_line", "tiny", "mirror"]
+    for name in names:
+        inp = DC.CASES[name](synth)
+        out = _partitioned(sim, inp, world, k=list(DC.CASES).index(name))
+        _merged_equals_the_reference(out, inp)
+        assert all(o[2]["line_ordered_build"] == 1 for o in out)
+
+
+@pytest.mark.parametrize("place,bad_rank", [("setup", 0), ("facts", 1), ("receive", 0), ("windows", 1),
+                                            ("filter", 0), ("proposals", 1), ("fire", 1)])
+def test_a_failure_on_one_rank_stops_every_rank(sim, synth, place, bad_rank):
+    """tests/dist_fail_check.py on the emulated device: an allocation failure injected on one rank at
+    a place where buffers grow comes back as an error from gtsb_pipeline on EVERY rank (nobody is left
+    in a collective), and the next call on the same contexts succeeds and is correct."""
+    inp = synth.generate("c2_bacterial", V=1500, seed=13, mirror_diff_frac=0.3, dup_same_line_frac=0.2)
+    out = _partitioned(sim, inp, 2, k=0, fail_at=f"{bad_rank}:{place}")
+    firsts = [o[3][0] for o in out]
+    assert all(f.startswith("error") for f in firsts), firsts
+    assert "injected failure" in firsts[bad_rank] and "rank %d failed" % bad_rank in firsts[1 - bad_rank], firsts
+    assert all(o[3][1] == "ok" for o in out), [o[3] for o in out]
+    _merged_equals_the_reference(out, inp)
+
+
 # ------------------------------------------------------------------ text kernels, components, MLE
 
 @pytest.mark.parametrize("seed", [0, 1, 4])
