@@ -7,6 +7,16 @@
 
 #include "cuda_runtime.h"
 
+// AddressSanitizer builds (CUSIM_ASAN=1, tests/emul/cusim_build.py): tell it about the stack switches
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define CUSIM_ASAN_START(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define CUSIM_ASAN_FINISH(save, bottom, size) __sanitizer_finish_switch_fiber(save, bottom, size)
+#else
+#define CUSIM_ASAN_START(save, bottom, size) ((void) 0)
+#define CUSIM_ASAN_FINISH(save, bottom, size) ((void) 0)
+#endif
+
 namespace cusim {
 
 thread_local ThreadCtx *T = nullptr;
@@ -39,6 +49,7 @@ struct Fiber {
   ThreadCtx t;
   uint32_t block = 0, rank = 0;   // index into blocks, thread rank inside the block
   bool done = true;
+  void *asan_fake = nullptr;      // the sanitizer's bookkeeping while this fiber is switched out
 };
 
 thread_local std::vector<Fiber> fibers;
@@ -50,13 +61,19 @@ thread_local uint32_t cur = 0, total_live = 0;
 thread_local uint64_t progress = 0;        // bumped whenever any thread changes the state of a wait
 thread_local uint32_t grid_arrived = 0;
 thread_local uint64_t grid_gen = 0;
+thread_local void *sched_asan_fake = nullptr;
+thread_local const void *sched_stack_bottom = nullptr;
+thread_local size_t sched_stack_size = 0;
 
 void yield() {
   Fiber &f = fibers[cur];
+  CUSIM_ASAN_START(&f.asan_fake, sched_stack_bottom, sched_stack_size);
   swapcontext(&f.ctx, &sched_ctx);
+  CUSIM_ASAN_FINISH(fibers[cur].asan_fake, &sched_stack_bottom, &sched_stack_size);
 }
 
 void fiber_main() {
+  CUSIM_ASAN_FINISH(nullptr, &sched_stack_bottom, &sched_stack_size);
   (*body)();
   Fiber &f = fibers[cur];
   f.done = true;
@@ -65,6 +82,7 @@ void fiber_main() {
   total_live--;
   b.warps[f.rank >> 5].exited |= 1u << (f.rank & 31u);
   progress++;
+  CUSIM_ASAN_START(nullptr, sched_stack_bottom, sched_stack_size);     // this fiber does not come back
   swapcontext(&f.ctx, &sched_ctx);
 }
 
@@ -105,7 +123,9 @@ void schedule(uint32_t n) {
       cur = t;
       T = &fibers[t].t;
       B = &blocks[fibers[t].block].ctx;
+      CUSIM_ASAN_START(&sched_asan_fake, stacks[t], STACK_BYTES);
       swapcontext(&sched_ctx, &fibers[t].ctx);
+      CUSIM_ASAN_FINISH(sched_asan_fake, nullptr, nullptr);
       T = nullptr;
     }
     if (total_live && progress == before)

@@ -42,7 +42,16 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".c")))
 
 
-def build(force=False):
+def build(force=False, asan=None):
+    """asan (default: CUSIM_ASAN=1 in the environment): an AddressSanitizer build, libgtsb_sim_asan.so --
+    device memory is host memory here, so a kernel that reads or writes outside an allocation is
+    reported with its source line.  Run with LD_PRELOAD=libasan.so and ASAN_OPTIONS=detect_leaks=0."""
+    global BUILD, OUT
+    if asan is None:
+        asan = os.environ.get("CUSIM_ASAN") == "1"
+    if asan:
+        BUILD = os.path.join(HERE, "_build", "sim_asan")
+        OUT = os.path.join(HERE, "_build", "libgtsb_sim_asan.so")
     deps = [os.path.join(CSRC, f) for f in sources()] + [os.path.join(SIM, f) for f in os.listdir(SIM)] + [__file__]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
@@ -66,6 +75,8 @@ def build(force=False):
                 with open(path, "w") as o:
                     o.write(text)
     flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I", SIM, "-I", BUILD]
+    if asan:
+        flags += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
     objs = []
     import concurrent.futures as cf
 
@@ -80,7 +91,7 @@ def build(force=False):
                     "-o", os.path.join(BUILD, "gtsb_threshold.o")], check=True)
     subprocess.run(["g++"] + flags + ["-c", os.path.join(SIM, "cusim.cpp"), "-o", os.path.join(BUILD, "cusim.o")], check=True)
     subprocess.run(["g++"] + flags + ["-shared", os.path.join(SIM, "fake_nccl.cpp"), "-o", NCCL, "-lpthread"], check=True)
-    subprocess.run(["g++", "-shared", "-o", OUT] + objs + [os.path.join(BUILD, "gtsb_threshold.o"),
+    subprocess.run(["g++", "-shared"] + (["-fsanitize=address"] if asan else []) + ["-o", OUT] + objs + [os.path.join(BUILD, "gtsb_threshold.o"),
                                                            os.path.join(BUILD, "cusim.o"), "-lm", "-ldl"], check=True)
     return OUT
 
