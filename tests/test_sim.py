@@ -257,6 +257,29 @@ def test_a_failure_on_one_rank_stops_every_rank(sim, synth, place, bad_rank):
     _merged_equals_the_reference(out, inp)
 
 
+def test_refused_inputs_come_back_from_every_rank(sim, synth):
+    """What the partitioned build does not take (a line longer than 64 records,
+    a contig heading several lines, a link listed only on the later line) and what no build takes
+    (a self link, an unknown id): every rank returns the error -- twice in a row -- and nobody waits."""
+    z = synth.generate("c2_bacterial", V=300, seed=8)
+
+    def edited(value):
+        ctg = z.ctg.copy()
+        ctg[5] = value
+        return synth.ScaffoldInput(z.seq_len, z.astat, z.copy_num, z.root, ctg, z.dist, z.std_dev, z.num_pairs, z.flags)
+
+    cases = [(synth.generate("c4_repeat_hubs", V=1500, max_deg=300, seed=3), "reason mask 2"),
+             (synth.tiny_dense(12, 60, 5), "heads more than one line"),
+             (synth.generate("c2_bacterial", V=800, seed=4, one_sided_frac=0.3), "reason mask 8"),
+             (edited(int(z.root[5])), "self link"), (edited(99999), "vertex id >= nof_vertices")]
+    for world in (2, 3):
+        for inp, what in cases:
+            out = _partitioned(sim, inp, world, reps=2)
+            for o in out:
+                assert all(x.startswith("error") for x in o[3]), (what, o[3])
+            assert any(what in o[3][0] for o in out), (what, [o[3][0] for o in out])
+
+
 # ------------------------------------------------------------------ text kernels, components, MLE
 
 @pytest.mark.parametrize("seed", [0, 1, 4])
