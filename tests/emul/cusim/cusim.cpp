@@ -53,7 +53,12 @@ struct Fiber {
 };
 
 thread_local std::vector<Fiber> fibers;
-thread_local std::vector<char *> stacks;
+struct Stacks : std::vector<char *> {      // fiber stacks of this host thread, freed when it ends
+  ~Stacks() {
+    for (char *p : *this) free(p);
+  }
+};
+thread_local Stacks stacks;
 thread_local std::vector<Block> blocks;
 thread_local ucontext_t sched_ctx;
 thread_local const std::function<void()> *body = nullptr;

@@ -46,14 +46,16 @@ def build(force=False, asan=None):
     """asan (default: CUSIM_ASAN=1 in the environment): an AddressSanitizer build, libgtsb_sim_asan.so --
     device memory is host memory here, so a kernel that reads or writes outside an allocation is
     reported with its source line.  Run with LD_PRELOAD=libasan.so and ASAN_OPTIONS=detect_leaks=0."""
-    global BUILD, OUT
+    global BUILD, OUT, NCCL
     if asan is None:
         asan = os.environ.get("CUSIM_ASAN") == "1"
     if asan:
         BUILD = os.path.join(HERE, "_build", "sim_asan")
         OUT = os.path.join(HERE, "_build", "libgtsb_sim_asan.so")
+        NCCL = os.path.join(HERE, "_build", "libnccl_cusim_asan.so")
     deps = [os.path.join(CSRC, f) for f in sources()] + [os.path.join(SIM, f) for f in os.listdir(SIM)] + [__file__]
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
+    if (not force and os.path.exists(OUT) and os.path.exists(NCCL)
+            and min(os.path.getmtime(OUT), os.path.getmtime(NCCL)) >= max(os.path.getmtime(d) for d in deps)):
         return OUT
     os.makedirs(BUILD, exist_ok=True)
     for f in sources():
