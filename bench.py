@@ -233,6 +233,39 @@ def cpu_reference_leg(pkg, workload, sample_vertices, line_order, steps=1, warmu
                       f"{sec:.2f} s per pass, 1 thread"}, sec, E
 
 
+def c4_leg():
+    """BASELINE.json config 4 (5e6 contigs, hubs of up to 1e4 edges) next to the headline config, in
+    processes of their own (tools/probe.py: device-resident inputs, 3 warm-up + 5 timed steps, CUDA
+    events): the device-timed step with the library's routing, and with the hub kernels switched off
+    (round-1 routes), whose result at full size is pinned to the compiled reference by
+    tests/golden/full_size_c4_repeat_hubs.json; the order-independent digests of every edge and vertex
+    state of the two runs must agree.  Whatever goes wrong here is reported in the value, never
+    raised: the headline line does not depend on it."""
+    out = {}
+    try:
+        probe = [sys.executable, os.path.join(ROOT, "tools", "probe.py"), "c4_repeat_hubs", "0", "5"]
+        runs = {"hub_kernels": {}, "round1_kernels": {"GTSB_HUBS": "0", "GTSB_HUB_SORT": "0", "GTSB_SMALL_MAX": "64"}}
+        res = {}
+        for name, extra in runs.items():
+            r = subprocess.run(probe, env=dict(os.environ, **extra), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                               timeout=180)
+            if r.returncode != 0:
+                out[name] = {"error": "probe exited %d: %s" % (r.returncode, r.stderr.decode(errors="replace")[-200:])}
+                continue
+            d = json.loads(r.stdout.decode().strip().splitlines()[-1])
+            res[name] = d
+            top = dict(sorted(d["kernels_ms"].items(), key=lambda kv: -kv[1])[:8])
+            out[name] = {"ms_per_step": d["ms_per_step"], "edges_per_s": d["edges_per_s"], "vertices": d["V"],
+                         "edges": d["E"], "max_degree": d["stats"]["max_degree"], "big_rows": d["stats"]["big_rows"],
+                         "digest_edges": d["digest_edges"], "digest_vertices": d["digest_vertices"], "kernels_ms": top}
+        if len(res) == 2:
+            out["digests_equal"] = all(res["hub_kernels"][k] == res["round1_kernels"][k]
+                                       for k in ("digest_edges", "digest_vertices", "E"))
+    except Exception as e:                                   # noqa: BLE001 -- see the docstring
+        out["error"] = repr(e)[:300]
+    return out
+
+
 def run_reference_arm(args, pkg):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -490,6 +523,8 @@ def run_b200_arm(args, pkg):
             "stats": {k: st[k] for k in ("max_degree", "big_rows", "proposals", "poly_sweeps", "fire_rounds",
                                          "line_ordered_build", "fallback_reason")}}
     line.update(pc)
+    if world == 1 and args.workload == "c3_human" and args.vertices is None and not args.no_c4:
+        line["c4_repeat_hubs"] = c4_leg()
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -512,6 +547,8 @@ def main():
     ap.add_argument("--cpu-sample-vertices", type=int, default=2_000_000)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N x the config's contigs in one graph, strong = the config's size whatever N")
+    ap.add_argument("--no-c4", action="store_true",
+                    help="N = 1, default workload: skip the config-4 (hubs) leg that runs after the headline measurement")
     ap.add_argument("--records", default="lines", choices=["lines", "flat"],
                     help="device-resident record input of the timed step at N = 1")
     args = ap.parse_args()
