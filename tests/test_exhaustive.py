@@ -32,8 +32,9 @@ ALPHABET = [(r, c, sense, same, d, s)
 PARAMS = [(0.01, 1.5, 400, 0.3, 20.0, True), (0.2, 2.5, 0, 0.5, 20.0, True)]
 
 
-def sequences(kind):
-    """kind: 'one_line' (all records under one root, sense block first: what a .de line is),
+def sequences(kind, stride=1, offset=0):
+    """stride / offset: every stride-th sequence only (the emulated device of tests/test_sim.py runs a sample).
+    kind: 'one_line' (all records under one root, sense block first: what a .de line is),
     'lines' (each root's records contiguous, and no link that only the later of its two
     lines lists: what the line-ordered build accepts), 'runs' (each root's records
     contiguous), 'any'."""
@@ -42,6 +43,7 @@ def sequences(kind):
     out += list(itertools.product(range(n), repeat=2))
     out += [(i // (n * n), (i // n) % n, i % n) for i in range(0, n ** 3, 61)]
     out += [(i // n ** 3, (i // n ** 2) % n, (i // n) % n, i % n) for i in range(0, n ** 4, 8009)]
+    out = out[offset::stride]
     if kind == "any":
         return out
 
@@ -74,8 +76,8 @@ def sequences(kind):
     return [s for s in out if keep(s)]
 
 
-def components(synth, kind):
-    seqs = sequences(kind)
+def components(synth, kind, stride=1, offset=0):
+    seqs = sequences(kind, stride, offset)
     ncomp = len(seqs) * len(ATTRS)
     V = 3 * ncomp
     cn = np.tile(np.array([a[0] for a in ATTRS], np.float32).reshape(-1), len(seqs))
@@ -138,8 +140,8 @@ def test_restatement_equals_reference_on_every_small_case(kind, synth):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["one_line", "lines", "runs", "any"])
-def test_cuda_path_equals_oracle_on_every_small_case(pkg, synth, kind):
-    inp = components(synth, kind)
+def test_cuda_path_equals_oracle_on_every_small_case(pkg, synth, kind, stride=1, offset=0):
+    inp = components(synth, kind, stride, offset)
     for params in PARAMS:
         pc, cnc, oc, cn_cut, a_cut, use_cn = params
         exp = run_oracle(O.RefGraph if O.have_ref() else O.PortGraph, inp, params)

@@ -27,6 +27,7 @@ import cusim_build  # noqa: E402
 import oracle_lib as O  # noqa: E402
 import test_components as TC  # noqa: E402
 import test_dropin as TD  # noqa: E402
+import test_exhaustive as TE  # noqa: E402
 import test_format as TF  # noqa: E402
 import test_gpu_parity as G  # noqa: E402
 import test_mle as TM  # noqa: E402
@@ -126,6 +127,15 @@ def test_pipeline_is_the_three_calls_and_the_digest_is_its_numpy_statement(sim, 
     g.close()
     for k in G.KEYS:
         assert np.array_equal(G._bits(a[k]), G._bits(b[k])), k
+
+
+@pytest.mark.parametrize("kind,offset", [("lines", 0), ("runs", 5), ("any", 11)])
+def test_a_sample_of_every_small_case(sim, synth, kind, offset):
+    """tests/test_exhaustive.py (every record sequence of length <= 2 over three contigs, samples of
+    length 3 and 4, six attribute settings, as the components of one graph) -- every 23rd sequence,
+    on both build paths and under both parameter sets."""
+    TE.O.build_oracles()
+    TE.test_cuda_path_equals_oracle_on_every_small_case(sim, synth, kind, stride=23, offset=offset)
 
 
 @pytest.mark.parametrize("order", [1, 7, 12345])
